@@ -1,0 +1,598 @@
+// Per-op kernels of the dual-AR token loop (decode_mode 1) and of prefill.
+// Reference call sites replaced are cited per kernel (paths relative to the
+// reference root, file fish_speech_core/lib/lm/dual_ar.rs unless noted).
+#pragma once
+#include "fsb_common.cuh"
+#include "fsb_sample.cuh"
+
+namespace fsb {
+
+// Device-resident state of the frame loop (single_batch.rs:19-28 fields that the
+// reference keeps on the host: input_pos, previous_codes, prompt/None, rep-pen).
+struct GenState {
+    int *pos;            // (B) cached positions == position of the next token
+    int *active;         // (B) 1 while the row still generates
+    int *eos;            // (B) slow token of the current frame was <|im_end|>
+    int *frame;          // (B) frames emitted so far
+    int *n_active;       // (1) rows still active; kernels no-op when 0
+    uint32_t *cur;       // (B, C+1) codes of the frame being built
+    uint32_t *prev;      // (B, C+1) codes of the previous frame (previous_codes)
+    uint32_t *out;       // (B, max_frames, C+1) every emitted frame
+    RepPenState *rep;    // (B, C)
+    int max_frames;
+    int fixed_len;       // FSB_GEN_FIXED_LEN
+    int C;
+    uint32_t im_end_id;
+};
+
+// ------------------------------------------------------------------ embed
+// DualARTransformer::embed, :532-567.  toks(b, c, s) = toks[(b*(C+1) + c)*S + s].
+template <typename WT>
+__global__ void embed_sum_kernel(const uint32_t *__restrict__ toks, int S, int C, int D, int codebook_size,
+                                 const WT *__restrict__ emb, const WT *__restrict__ cb_emb, uint32_t sem_start,
+                                 uint32_t sem_end, int has_end, float *__restrict__ x, const int *n_active) {
+    if (n_active && *n_active == 0) return;
+    const int row = blockIdx.x;  // b*S + s
+    const int b = row / S, s = row % S;
+    const uint32_t *t = toks + (size_t)b * (C + 1) * S + s;
+    const uint32_t tok0 = t[0];
+    const bool m = has_end ? (tok0 <= sem_end && tok0 >= sem_start) : (tok0 == sem_start);
+    const float mf = m ? 1.f : 0.f;
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+        float acc = to_f32(emb[(size_t)tok0 * D + d]);
+        for (int c = 0; c < C; ++c) {
+            uint32_t code = t[(size_t)(c + 1) * S];
+            acc = __fadd_rn(acc, __fmul_rn(to_f32(cb_emb[((size_t)c * codebook_size + code) * D + d]), mf));
+        }
+        x[(size_t)row * D + d] = acc;
+    }
+}
+
+// ------------------------------------------------------------------ GEMV
+// y[b, r] = epilogue( W[r, :] . xn[b, :] ),  xn = rms_norm(x[b]) * g  (optional)
+// replaces RmsNorm + Linear (+ residual / silu*mul), :160-165,289,383,429-440.
+// One warp streams two weight rows with 16-byte loads; x lives in shared memory.
+enum { EPI_STORE = 0, EPI_RESID = 1, EPI_SWIGLU = 2 };
+
+struct GemvArgs {
+    const void *W;       // (rows, K)
+    const void *W3;      // EPI_SWIGLU: second matrix (w3)
+    const float *x;      // (NB, ldx)
+    const float *norm_w; // (K) f32 or null
+    const float *resid;  // (NB, ldy) for EPI_RESID
+    float *y;            // (NB, ldy)
+    int rows, K, ldx, ldy;
+    float eps;
+    int row0;            // logical row 0 reads weight row `row0`, row r>=1 reads `rest_base + r - 1`
+    int rest_base;
+    const int *n_active;
+};
+
+constexpr int kGemvThreads = 128;
+constexpr int kGemvRowsPerWarp = 2;
+constexpr int kGemvRowsPerCta = (kGemvThreads / 32) * kGemvRowsPerWarp;
+
+template <typename WT>
+__device__ __forceinline__ void load_w8(const WT *p, float (&w)[8]);
+template <>
+__device__ __forceinline__ void load_w8<float>(const float *p, float (&w)[8]) {
+    float4 a = ldg_stream4(p), b = ldg_stream4(p + 4);
+    w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+}
+template <>
+__device__ __forceinline__ void load_w8<__nv_bfloat16>(const __nv_bfloat16 *p, float (&w)[8]) {
+    uint4 u = ldg_stream_u4(p);
+    w[0] = bf16lo(u.x); w[1] = bf16hi(u.x); w[2] = bf16lo(u.y); w[3] = bf16hi(u.y);
+    w[4] = bf16lo(u.z); w[5] = bf16hi(u.z); w[6] = bf16lo(u.w); w[7] = bf16hi(u.w);
+}
+
+template <typename WT, int NB, int EPI>
+__global__ void __launch_bounds__(kGemvThreads) gemv_kernel(GemvArgs a) {
+    if (a.n_active && *a.n_active == 0) return;
+    extern __shared__ float xs[];  // NB * K
+    __shared__ float red[kGemvThreads / 32][NB];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int K = a.K;
+    // ---- prologue: stage x, optional rms_norm ----
+    float ss[NB];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) ss[b] = 0.f;
+    for (int k = tid; k < K; k += kGemvThreads) {
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            float v = a.x[(size_t)b * a.ldx + k];
+            xs[b * K + k] = v;
+            ss[b] += v * v;
+        }
+    }
+    if (a.norm_w) {
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            float v = warp_sum(ss[b]);
+            if (lane == 0) red[warp][b] = v;
+        }
+        __syncthreads();
+        const float *g = a.norm_w;
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            float tot = 0.f;
+#pragma unroll
+            for (int w = 0; w < kGemvThreads / 32; ++w) tot += red[w][b];
+            const float denom = sqrtf(tot / (float)K + a.eps);
+            for (int k = tid; k < K; k += kGemvThreads)
+                xs[b * K + k] = __fmul_rn(__fdiv_rn(xs[b * K + k], denom), g[k]);
+        }
+    }
+    __syncthreads();
+    // ---- main: 2 rows per warp ----
+    const WT *W = reinterpret_cast<const WT *>(a.W);
+    const WT *W3 = reinterpret_cast<const WT *>(a.W3);
+    for (int r0 = (blockIdx.x * (kGemvThreads / 32) + warp) * kGemvRowsPerWarp; r0 < a.rows;
+         r0 += gridDim.x * kGemvRowsPerCta) {
+        const int r1 = r0 + 1;
+        const bool has1 = r1 < a.rows;
+        const size_t wr0 = (size_t)(r0 == 0 ? a.row0 : a.rest_base + r0 - 1);
+        const size_t wr1 = (size_t)(has1 ? (a.rest_base + r1 - 1) : wr0);
+        const WT *p0 = W + wr0 * K, *p1 = W + wr1 * K;
+        float acc0[NB], acc1[NB], acc30[NB], acc31[NB];
+#pragma unroll
+        for (int b = 0; b < NB; ++b) acc0[b] = acc1[b] = acc30[b] = acc31[b] = 0.f;
+#pragma unroll 4
+        for (int k = lane * 8; k < K; k += 256) {
+            float w0[8], w1[8];
+            load_w8<WT>(p0 + k, w0);
+            load_w8<WT>(p1 + k, w1);
+            float v0[8], v1[8];
+            if (EPI == EPI_SWIGLU) {
+                load_w8<WT>(W3 + wr0 * K + k, v0);
+                load_w8<WT>(W3 + wr1 * K + k, v1);
+            }
+#pragma unroll
+            for (int b = 0; b < NB; ++b) {
+                const float4 xa = *reinterpret_cast<const float4 *>(&xs[b * K + k]);
+                const float4 xb = *reinterpret_cast<const float4 *>(&xs[b * K + k + 4]);
+                const float xv[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    acc0[b] = fmaf(w0[j], xv[j], acc0[b]);
+                    acc1[b] = fmaf(w1[j], xv[j], acc1[b]);
+                    if (EPI == EPI_SWIGLU) {
+                        acc30[b] = fmaf(v0[j], xv[j], acc30[b]);
+                        acc31[b] = fmaf(v1[j], xv[j], acc31[b]);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            float s0 = warp_sum(acc0[b]), s1 = warp_sum(acc1[b]);
+            float t0 = 0.f, t1 = 0.f;
+            if (EPI == EPI_SWIGLU) { t0 = warp_sum(acc30[b]); t1 = warp_sum(acc31[b]); }
+            if (lane == 0) {
+                float *yo = a.y + (size_t)b * a.ldy;
+                if (EPI == EPI_STORE) {
+                    yo[r0] = s0;
+                    if (has1) yo[r1] = s1;
+                } else if (EPI == EPI_RESID) {
+                    const float *rs = a.resid + (size_t)b * a.ldy;
+                    yo[r0] = __fadd_rn(rs[r0], s0);
+                    if (has1) yo[r1] = __fadd_rn(rs[r1], s1);
+                } else {
+                    yo[r0] = __fmul_rn(silu_f(s0), t0);
+                    if (has1) yo[r1] = __fmul_rn(silu_f(s1), t1);
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------ RoPE + KV append (decode, one token per row)
+// rope_i (:246-247) on q and k, Tensor::cat replaced by an in-place write (:316-324).
+// qkv (B, (H+2KV)*hd) -> q (B, H*hd) roped; K/V cache row `pos`.
+// cache layout: (B, KV, max_len, hd).  pos = pos_ptr ? pos_ptr[b] : pos_imm.
+__global__ void rope_append_kernel(const float *__restrict__ qkv, float *__restrict__ q, float *__restrict__ kc,
+                                   float *__restrict__ vc, const float *__restrict__ cosT,
+                                   const float *__restrict__ sinT, const int *pos_ptr, int pos_imm, int rope_delta,
+                                   int H, int KV, int hd, int max_len, const int *n_active) {
+    if (n_active && *n_active == 0) return;
+    const int b = blockIdx.x;
+    const int pos = pos_ptr ? pos_ptr[b] : pos_imm;  // cache slot
+    const int rpos = pos + rope_delta;                // RoPE row (== input_pos)
+    const int half = hd / 2;
+    const float *src = qkv + (size_t)b * (H + 2 * KV) * hd;
+    const int n_q = H * half, n_k = KV * half, n_v = KV * hd;
+    for (int i = threadIdx.x; i < n_q + n_k + n_v; i += blockDim.x) {
+        if (i < n_q + n_k) {
+            const bool is_q = i < n_q;
+            const int j = is_q ? i : i - n_q;
+            const int h = j / half, p = j % half;
+            const float *s = src + (is_q ? 0 : H * hd) + h * hd + 2 * p;
+            const float c = cosT[(size_t)rpos * half + p], sn = sinT[(size_t)rpos * half + p];
+            const float x0 = s[0], x1 = s[1];
+            const float o0 = __fsub_rn(__fmul_rn(x0, c), __fmul_rn(x1, sn));
+            const float o1 = __fadd_rn(__fmul_rn(x0, sn), __fmul_rn(x1, c));
+            float *dst = is_q ? (q + (size_t)b * H * hd + h * hd + 2 * p)
+                              : (kc + (((size_t)b * KV + h) * max_len + pos) * hd + 2 * p);
+            dst[0] = o0;
+            dst[1] = o1;
+        } else {
+            const int j = i - n_q - n_k;
+            const int h = j / hd, d = j % hd;
+            vc[(((size_t)b * KV + h) * max_len + pos) * hd + d] = src[(H + KV) * hd + h * hd + d];
+        }
+    }
+}
+
+// ------------------------------------------------------------------ decode attention (split-KV, GQA shared K/V)
+// replaces repeat_kv + scaled_dot_product_attention (:252-279,327-376; unary.cu:8-58):
+// the 8 query heads of a KV group read each cached K/V row once.
+// grid (nsplit, KV, B), block = n_rep warps.  partial: (B, H, nsplit, hd + 2).
+constexpr int kAttnMaxRep = 8;
+__global__ void attn_decode_split_kernel(const float *__restrict__ q, const float *__restrict__ kc,
+                                         const float *__restrict__ vc, const int *pos_ptr, int pos_imm, int H,
+                                         int KV, int hd, int max_len, float scale, float *__restrict__ partial,
+                                         const int *n_active) {
+    if (n_active && *n_active == 0) return;
+    extern __shared__ float qs[];  // n_rep * hd
+    const int split = blockIdx.x, nsplit = gridDim.x, kvh = blockIdx.y, b = blockIdx.z;
+    const int n_rep = H / KV;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int h = kvh * n_rep + warp;
+    const int len = (pos_ptr ? pos_ptr[b] : pos_imm) + 1;
+    int chunk = (len + nsplit - 1) / nsplit;
+    chunk = (chunk + 31) & ~31;
+    const int j0 = split * chunk, j1 = min(len, j0 + chunk);
+    for (int i = threadIdx.x; i < n_rep * hd; i += blockDim.x)
+        qs[i] = q[(size_t)b * H * hd + (size_t)kvh * n_rep * hd + i];
+    __syncthreads();
+    const float *qh = qs + warp * hd;
+    const float *kb = kc + ((size_t)b * KV + kvh) * max_len * hd;
+    const float *vb = vc + ((size_t)b * KV + kvh) * max_len * hd;
+    float m = -INFINITY, l = 0.f, o0 = 0.f, o1 = 0.f;  // lane owns dims lane, lane+32 (hd == 64)
+    for (int t = j0; t < j1; t += 32) {
+        const int j = t + lane;
+        float sc = -INFINITY;
+        if (j < j1) {
+            const float4 *kr = reinterpret_cast<const float4 *>(kb + (size_t)j * hd);
+            float acc = 0.f;
+#pragma unroll
+            for (int d4 = 0; d4 < 16; ++d4) {
+                float4 kk = kr[d4];
+                acc = fmaf(qh[4 * d4 + 0], kk.x * scale, acc);
+                acc = fmaf(qh[4 * d4 + 1], kk.y * scale, acc);
+                acc = fmaf(qh[4 * d4 + 2], kk.z * scale, acc);
+                acc = fmaf(qh[4 * d4 + 3], kk.w * scale, acc);
+            }
+            sc = acc;
+        }
+        const float m_new = fmaxf(m, warp_max(sc));
+        const float corr = expf(m - m_new);  // exp(-inf) == 0 on the first tile
+        const float p = (j < j1) ? expf(sc - m_new) : 0.f;
+        l = l * corr + warp_sum(p);
+        o0 *= corr;
+        o1 *= corr;
+        const int cnt = min(32, j1 - t);
+        for (int jj = 0; jj < cnt; ++jj) {
+            const float pj = __shfl_sync(0xffffffffu, p, jj);
+            const float *vr = vb + (size_t)(t + jj) * hd;
+            o0 = fmaf(pj, vr[lane], o0);
+            o1 = fmaf(pj, vr[lane + 32], o1);
+        }
+        m = m_new;
+    }
+    float *out = partial + (((size_t)b * H + h) * nsplit + split) * (hd + 2);
+    out[lane] = o0;
+    out[lane + 32] = o1;
+    if (lane == 0) { out[hd] = m; out[hd + 1] = l; }
+}
+
+// grid (B*H), block hd.  y (B, H*hd).
+__global__ void attn_decode_combine_kernel(const float *__restrict__ partial, int nsplit, int hd,
+                                           float *__restrict__ y, const int *n_active) {
+    if (n_active && *n_active == 0) return;
+    const int bh = blockIdx.x, d = threadIdx.x;
+    const float *p = partial + (size_t)bh * nsplit * (hd + 2);
+    float M = -INFINITY;
+    for (int s = 0; s < nsplit; ++s) M = fmaxf(M, p[s * (hd + 2) + hd]);
+    float L = 0.f, o = 0.f;
+    for (int s = 0; s < nsplit; ++s) {
+        const float ms = p[s * (hd + 2) + hd];
+        if (ms == -INFINITY) continue;
+        const float w = expf(ms - M);
+        L = fmaf(p[s * (hd + 2) + hd + 1], w, L);
+        o = fmaf(p[s * (hd + 2) + d], w, o);
+    }
+    y[(size_t)bh * hd + d] = o / L;
+}
+
+// ------------------------------------------------------------------ prefill kernels (S > 1, one sequence)
+// rms_norm over rows: one warp per row.
+__global__ void rmsnorm_rows_kernel(const float *__restrict__ x, const float *__restrict__ g, float eps, int M, int D,
+                                    float *__restrict__ y) {
+    const int row = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= M) return;
+    const float *xr = x + (size_t)row * D;
+    float ss = 0.f;
+    for (int k = lane; k < D; k += 32) ss += xr[k] * xr[k];
+    ss = warp_sum(ss);
+    const float denom = sqrtf(ss / (float)D + eps);
+    for (int k = lane; k < D; k += 32) y[(size_t)row * D + k] = __fmul_rn(__fdiv_rn(xr[k], denom), g[k]);
+}
+
+// C[M, N] = A[M, K] . W[N, K]^T (+ resid), fp32 accumulate on CUDA cores.
+// 64x64 tile, BK 16, 256 threads, 4x4 micro-tile.  Used for prefill and for
+// decode batches too wide for the GEMV path; the fp32-parity companion of the
+// tcgen05 path.
+constexpr int kGemmBM = 64, kGemmBN = 64, kGemmBK = 16;
+template <typename WT, int EPI>
+__global__ void __launch_bounds__(256) gemm_nt_kernel(const float *__restrict__ A, const WT *__restrict__ W,
+                                                      const float *__restrict__ resid, float *__restrict__ Cm, int M,
+                                                      int N, int K) {
+    __shared__ float As[kGemmBK][kGemmBM + 4];
+    __shared__ float Ws[kGemmBK][kGemmBN + 4];
+    const int tid = threadIdx.x;
+    const int m0 = blockIdx.y * kGemmBM, n0 = blockIdx.x * kGemmBN;
+    const int tx = tid % 16, ty = tid / 16;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    const int lr = tid / 4, lk = (tid % 4) * 4;  // 64 rows x 16 k, 4 consecutive k per thread
+    for (int k0 = 0; k0 < K; k0 += kGemmBK) {
+        {
+            float v[4] = {0.f, 0.f, 0.f, 0.f};
+            if (m0 + lr < M) {
+                const float4 t = *reinterpret_cast<const float4 *>(A + (size_t)(m0 + lr) * K + k0 + lk);
+                v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) As[lk + i][lr] = v[i];
+            float w[4] = {0.f, 0.f, 0.f, 0.f};
+            if (n0 + lr < N) {
+                const WT *wp = W + (size_t)(n0 + lr) * K + k0 + lk;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) w[i] = to_f32(wp[i]);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) Ws[lk + i][lr] = w[i];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < kGemmBK; ++kk) {
+            float a[4], w[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) w[j] = Ws[kk][tx * 4 + j];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], w[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int m = m0 + ty * 4 + i;
+        if (m >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int n = n0 + tx * 4 + j;
+            if (n >= N) continue;
+            float v = acc[i][j];
+            if (EPI == EPI_RESID) v = __fadd_rn(resid[(size_t)m * N + n], v);
+            Cm[(size_t)m * N + n] = v;
+        }
+    }
+}
+
+// h = silu(g1) * g3   (g1 = x . w1^T, g3 = x . w3^T), in place into g1 allowed
+__global__ void swiglu_rows_kernel(const float *g1, const float *__restrict__ g3, size_t n, float *h) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n) return;
+    h[idx] = __fmul_rn(silu_f(g1[idx]), g3[idx]);
+}
+
+// RoPE + KV write for S consecutive positions of row `b` starting at pos0.
+// qkv (S, (H+2KV)*hd) -> q (S, H*hd) roped, caches at pos0 + s.
+__global__ void rope_append_rows_kernel(const float *__restrict__ qkv, float *__restrict__ q, float *__restrict__ kc,
+                                        float *__restrict__ vc, const float *__restrict__ cosT,
+                                        const float *__restrict__ sinT, int b, int pos0, int rope_delta, int H,
+                                        int KV, int hd, int max_len) {
+    const int s = blockIdx.x;
+    const int pos = pos0 + s;
+    const int rpos = pos + rope_delta;
+    const int half = hd / 2;
+    const float *src = qkv + (size_t)s * (H + 2 * KV) * hd;
+    const int n_q = H * half, n_k = KV * half, n_v = KV * hd;
+    for (int i = threadIdx.x; i < n_q + n_k + n_v; i += blockDim.x) {
+        if (i < n_q + n_k) {
+            const bool is_q = i < n_q;
+            const int j = is_q ? i : i - n_q;
+            const int h = j / half, p = j % half;
+            const float *sp = src + (is_q ? 0 : H * hd) + h * hd + 2 * p;
+            const float c = cosT[(size_t)rpos * half + p], sn = sinT[(size_t)rpos * half + p];
+            const float x0 = sp[0], x1 = sp[1];
+            const float o0 = __fsub_rn(__fmul_rn(x0, c), __fmul_rn(x1, sn));
+            const float o1 = __fadd_rn(__fmul_rn(x0, sn), __fmul_rn(x1, c));
+            float *dst = is_q ? (q + (size_t)s * H * hd + h * hd + 2 * p)
+                              : (kc + (((size_t)b * KV + h) * max_len + pos) * hd + 2 * p);
+            dst[0] = o0;
+            dst[1] = o1;
+        } else {
+            const int j = i - n_q - n_k;
+            const int h = j / hd, d = j % hd;
+            vc[(((size_t)b * KV + h) * max_len + pos) * hd + d] = src[(H + KV) * hd + h * hd + d];
+        }
+    }
+}
+
+// Causal attention with KV offset for prefill (get_mask_abs, :702-712: query s sees
+// cached positions [0, pos0 + s]).  grid (ceil(S/4), H), block 128: one warp per query.
+__global__ void attn_prefill_kernel(const float *__restrict__ q, const float *__restrict__ kc,
+                                    const float *__restrict__ vc, int b, int pos0, int S, int H, int KV, int hd,
+                                    int max_len, float scale, float *__restrict__ y) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int s = blockIdx.x * 4 + warp, h = blockIdx.y;
+    if (s >= S) return;
+    __shared__ float qsm[4][64];
+    const int kvh = h / (H / KV);
+    qsm[warp][lane] = q[((size_t)s * H + h) * hd + lane];
+    qsm[warp][lane + 32] = q[((size_t)s * H + h) * hd + lane + 32];
+    __syncwarp();
+    const float *qh = qsm[warp];
+    const float *kb = kc + ((size_t)b * KV + kvh) * max_len * hd;
+    const float *vb = vc + ((size_t)b * KV + kvh) * max_len * hd;
+    const int len = pos0 + s + 1;
+    float m = -INFINITY, l = 0.f, o0 = 0.f, o1 = 0.f;
+    for (int t = 0; t < len; t += 32) {
+        const int j = t + lane;
+        float sc = -INFINITY;
+        if (j < len) {
+            const float4 *kr = reinterpret_cast<const float4 *>(kb + (size_t)j * hd);
+            float acc = 0.f;
+#pragma unroll
+            for (int d4 = 0; d4 < 16; ++d4) {
+                float4 kk = kr[d4];
+                acc = fmaf(qh[4 * d4 + 0], kk.x * scale, acc);
+                acc = fmaf(qh[4 * d4 + 1], kk.y * scale, acc);
+                acc = fmaf(qh[4 * d4 + 2], kk.z * scale, acc);
+                acc = fmaf(qh[4 * d4 + 3], kk.w * scale, acc);
+            }
+            sc = acc;
+        }
+        const float m_new = fmaxf(m, warp_max(sc));
+        const float corr = expf(m - m_new);
+        const float p = (j < len) ? expf(sc - m_new) : 0.f;
+        l = l * corr + warp_sum(p);
+        o0 *= corr;
+        o1 *= corr;
+        const int cnt = min(32, len - t);
+        for (int jj = 0; jj < cnt; ++jj) {
+            const float pj = __shfl_sync(0xffffffffu, p, jj);
+            const float *vr = vb + (size_t)(t + jj) * hd;
+            o0 = fmaf(pj, vr[lane], o0);
+            o1 = fmaf(pj, vr[lane + 32], o1);
+        }
+        m = m_new;
+    }
+    y[((size_t)s * H + h) * hd + lane] = o0 / l;
+    y[((size_t)s * H + h) * hd + lane + 32] = o1 / l;
+}
+
+// ------------------------------------------------------------------ samplers
+// Slow head: constrained logits (generate/utils.rs:6-33) -> token (utils.rs:36-56),
+// EOS bookkeeping (single_batch.rs:153-156,199-204).  grid B, block 1024.
+// logits (B, ld) holds rows [im_end | semantic_start ..) i.e. n = V' entries.
+__global__ void __launch_bounds__(kSampleThreads) sample_slow_kernel(const float *__restrict__ logits, int ld, int n,
+                                                                      SampleParams sp, GenState st,
+                                                                      uint32_t sem_start, const float *hidden,
+                                                                      float *fast_x, int D) {
+    if (*st.n_active == 0) return;
+    const int b = blockIdx.x;
+    if (!st.active[b]) return;
+    extern __shared__ unsigned char smem_raw[];
+    int n_pad = 1;
+    while (n_pad < n) n_pad <<= 1;
+    unsigned long long *keys = reinterpret_cast<unsigned long long *>(smem_raw);
+    float *vals = reinterpret_cast<float *>(keys + n_pad);
+    float *red = vals + n_pad;
+    for (int i = threadIdx.x; i < n; i += kSampleThreads) {
+        float v = logits[(size_t)b * ld + i];
+        if (i == 0 && st.fixed_len) v = -INFINITY;
+        vals[i] = v;
+    }
+    __syncthreads();
+    const int frame = st.frame[b];
+    const float u = philox_uniform(sp.seed, (uint64_t)frame * (st.C + 1), (uint32_t)b);
+    const int idx = block_sample(vals, keys, red, n, n_pad, sp, u);
+    const uint32_t tok = (idx == 0) ? st.im_end_id : (sem_start + (uint32_t)idx - 1);
+    const bool eos = (tok == st.im_end_id);
+    if (threadIdx.x == 0) {
+        st.cur[b * (st.C + 1)] = tok;
+        st.eos[b] = eos ? 1 : 0;
+        if (eos)
+            for (int c = 0; c < st.C; ++c) st.cur[b * (st.C + 1) + 1 + c] = 0;
+    }
+    // fast stack input = pre-norm hidden (Q1, :629-634)
+    for (int d = threadIdx.x; d < D; d += kSampleThreads) fast_x[(size_t)b * D + d] = hidden[(size_t)b * D + d];
+}
+
+// Fast head for codebook `cb`: rep-pen (from the 2nd frame, single_batch.rs:162-168)
+// + sample + fast_embeddings gather (:176-182); after the last codebook, frame
+// bookkeeping (:193-204).  grid B, block 1024.
+template <typename WT>
+__global__ void __launch_bounds__(kSampleThreads) sample_fast_kernel(const float *__restrict__ logits, int n, int cb,
+                                                                      SampleParams sp, GenState st,
+                                                                      const WT *__restrict__ fast_emb,
+                                                                      float *fast_x, int D) {
+    if (*st.n_active == 0) return;
+    const int b = blockIdx.x;
+    if (!st.active[b]) return;
+    const int C = st.C;
+    const bool eos = st.eos[b] != 0;
+    extern __shared__ unsigned char smem_raw[];
+    int n_pad = 1;
+    while (n_pad < n) n_pad <<= 1;
+    unsigned long long *keys = reinterpret_cast<unsigned long long *>(smem_raw);
+    float *vals = reinterpret_cast<float *>(keys + n_pad);
+    float *red = vals + n_pad;
+    const int frame = st.frame[b];
+    if (!eos) {
+        RepPenState *rp = st.rep + (size_t)b * C + cb;
+        if (frame > 0) {
+            if (threadIdx.x == 0) rep_pen_update(rp, st.prev[b * (C + 1) + 1 + cb]);
+            __syncthreads();
+        }
+        for (int i = threadIdx.x; i < n; i += kSampleThreads) {
+            float v = logits[(size_t)b * n + i];
+            if (frame > 0 && ((rp->seen[i >> 5] >> (i & 31)) & 1u)) v = __fdiv_rn(v, sp.penalty);
+            vals[i] = v;
+        }
+        __syncthreads();
+        const float u = philox_uniform(sp.seed, (uint64_t)frame * (C + 1) + cb + 1, (uint32_t)b);
+        const int a = block_sample(vals, keys, red, n, n_pad, sp, u);
+        if (threadIdx.x == 0) st.cur[b * (C + 1) + 1 + cb] = (uint32_t)a;
+        if (cb != C - 1)
+            for (int d = threadIdx.x; d < D; d += kSampleThreads)
+                fast_x[(size_t)b * D + d] = to_f32(fast_emb[(size_t)a * D + d]);
+    }
+    if (cb == C - 1) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t *o = st.out + ((size_t)b * st.max_frames + frame) * (C + 1);
+            for (int c = 0; c <= C; ++c) {
+                const uint32_t v = st.cur[b * (C + 1) + c];
+                o[c] = v;
+                st.prev[b * (C + 1) + c] = v;
+            }
+            const int nf = frame + 1;
+            st.frame[b] = nf;
+            if (eos || nf >= st.max_frames) {
+                st.active[b] = 0;
+                atomicSub(st.n_active, 1);
+            }
+        }
+    }
+}
+
+// pos[b] += 1 for rows that are still active (input_pos bookkeeping, single_batch.rs:193-197).
+__global__ void advance_pos_kernel(GenState st, int B) {
+    const int b = threadIdx.x;
+    if (b < B && st.active[b]) st.pos[b] += 1;
+}
+
+// repeat_kv (candle-gqa-kernels/src/unary.cu:8-58) for callers that still want the copy.
+template <typename T>
+__global__ void repeat_kv_kernel(const T *__restrict__ src, T *__restrict__ dst, int n_rep, int seqlen, int hd) {
+    const int s = blockIdx.x, h = blockIdx.y;
+    const T *in = src + ((size_t)h * seqlen + s) * hd;
+    for (int r = 0; r < n_rep; ++r) {
+        T *out = dst + (((size_t)h * n_rep + r) * seqlen + s) * hd;
+        for (int d = threadIdx.x; d < hd; d += blockDim.x) out[d] = in[d];
+    }
+}
+
+}  // namespace fsb
