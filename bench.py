@@ -1,0 +1,322 @@
+#!/usr/bin/env python
+"""bench.py -- codec tokens/s (frames/s) + 44.1 kHz samples/s of the fish-speech hot path on B200.
+
+One "step" = one pass of the hot path over one batch of synthetic utterances per GPU:
+prompt (C+1, P) -> prefill -> N frames of dual-AR decode (slow step + 8 fast steps, device-side
+sampling) -> Firefly vocoder -> PCM.  Default workload = BASELINE.json configs[1] ("cfg2":
+Fish 1.5, batch 1, temp 0.7 / top_p 0.8, 10 s utterance = 216 frames, P = 384).  Utterances are
+independent, so N GPUs run N shards with no collective on the data path ("weak" scaling).
+
+  value  : frames/s from device time only (CUDA events on the library's stream: prefill + frame loop
+           + vocoder kernels), inputs resident in HBM
+  e2e    : frames/s by wall clock through the C ABI with HOST buffers (pinned), copies included
+  roofline: weight-streaming GEMV kernel, algorithmic bytes / CUDA-event duration per launch,
+           against MEASURED_PEAKS.json
+  cpu_baseline: the oracle (restated Candle-CPU path, PyTorch CPU fp32) timed on a bounded sample
+
+`--impl reference` times the oracle alone on the host cores (the Rust/Candle reference cannot be built
+here: no cargo).  Only this file's cpu legs import `oracle/`.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+CONFIGS = {
+    # name: (fish_version, batch per GPU, prompt lens fn, frames, temp, top_p)
+    "cfg2": dict(version="1.5", batch=1, prompt_lens=lambda b: [384] * b, frames=216, temp=0.7, top_p=0.8,
+                 desc="Fish 1.5 B=1 temp=0.7 top_p=0.8 10 s utterance (P=384, N=216)"),
+    "cfg3": dict(version="1.5", batch=16, prompt_lens=lambda b: [300 + 28 * i for i in range(b)], frames=216,
+                 temp=0.7, top_p=0.8, desc="Fish 1.5 B=16 mixed prompts 300..720, N=216 each"),
+    "cfg5": dict(version="1.5", batch=32, prompt_lens=lambda b: [384] * b, frames=1292, temp=0.7, top_p=0.8,
+                 desc="Fish 1.5 B=32/GPU long-form 60 s (P=384, N=1292)"),
+}
+FRAME_RATE = 44100.0 / 2048.0  # 21.533 frames/s (reference prints with 21.535, single_batch.rs:292-295)
+
+
+def measured_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_inputs(cfgname, rank):
+    from fish_speech_rs_b200 import synth
+    c = CONFIGS[cfgname]
+    mcfg = dict(synth.FISH15 if c["version"] == "1.5" else synth.FISH14)
+    tok = dict(synth.FISH15_TOKENS if c["version"] == "1.5" else synth.FISH14_TOKENS)
+    voice = np.load(os.path.join(ROOT, "tests", "golden", "default_voice.npy"))
+    B = c["batch"]
+    prompts = [synth.make_prompt(mcfg, tok, P, seed=1000 + rank * B + i, voice=voice)
+               for i, P in enumerate(c["prompt_lens"](B))]
+    return c, mcfg, tok, prompts
+
+
+# ------------------------------------------------------------------------------------------------ CPU legs
+def cpu_reference_sample(cfgname, lm_w, codec_w, sample_frames, threads):
+    """Oracle (restated Candle-CPU path) on a bounded sample of the workload: prefill of one prompt +
+    `sample_frames` decode frames + vocoding of those frames; scaled to the full workload's
+    prefill : decode : vocode proportions.  Returns (frames/s, description)."""
+    import torch
+    from oracle import codec as ocodec
+    from oracle import dual_ar as olm
+    from oracle import generate as ogen
+    from oracle import sampling as osamp
+    torch.set_num_threads(threads)
+    c, mcfg, tok, prompts = build_inputs(cfgname, 0)
+    model = olm.DualARTransformer(lm_w, olm.BaseModelArgs(**mcfg), olm.TokenConfig(**tok), c["version"])
+    args = osamp.SamplingArgs(c["temp"], c["top_p"], 256, 1.4, seed=1)
+    prompt = torch.from_numpy(prompts[0].astype(np.int64))
+    with torch.no_grad():
+        gen = ogen.SingleBatchGenerator(model, prompt, 100000, args, True, 0, fixed_len=sample_frames)
+        t0 = time.perf_counter()
+        frames = [gen.next()]
+        t1 = time.perf_counter()
+        for _ in range(sample_frames - 1):
+            frames.append(gen.next())
+        t2 = time.perf_counter()
+        codes = torch.tensor(frames, dtype=torch.int64).T[1:].clamp(max=999)[None]
+        ocodec.decode(codes, codec_w)
+        t3 = time.perf_counter()
+    model.clear_slow_layer_caches()
+    t_prefill = t1 - t0  # includes the first frame's fast loop
+    t_frame = (t2 - t1) / max(sample_frames - 1, 1)
+    t_voc = (t3 - t2) / sample_frames
+    N, B = c["frames"], c["batch"]
+    total = B * (t_prefill + (N - 1) * t_frame + N * t_voc)
+    desc = (f"oracle on 1 utterance: prefill P={prompt.shape[1]} ({t_prefill:.2f}s) + {sample_frames - 1} decode frames "
+            f"({t_frame * 1e3:.0f} ms/frame) + vocoder on {sample_frames} frames ({t_voc * 1e3:.0f} ms/frame); "
+            f"scaled to B={B} x {N} frames")
+    return B * N / total, desc
+
+
+def make_weights(version, want_lm=True, want_codec=True):
+    from fish_speech_rs_b200 import synth
+    mcfg = synth.FISH15 if version == "1.5" else synth.FISH14
+    lm_w = synth.make_lm_weights(mcfg, seed=1234) if want_lm else None
+    codec_w = synth.make_codec_weights(seed=4321, with_encoder=False) if want_codec else None
+    return lm_w, codec_w
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    c = CONFIGS[a.config]
+    threads = os.cpu_count() or 1
+    lm_w, codec_w = make_weights(c["version"])
+    vals = []
+    desc = ""
+    for i in range(a.warmup + a.steps):
+        v, desc = cpu_reference_sample(a.config, lm_w, codec_w, a.cpu_sample_frames, threads)
+        if i >= a.warmup:
+            vals.append(v)
+    v = float(np.mean(vals))
+    out = {"impl": "reference", "metric": "codec_tokens_per_sec", "value": v, "unit": "frames/s", "n_gpus": a.gpus,
+           "steps": a.steps, "warmup": a.warmup, "ms_per_step": c["batch"] * c["frames"] / v * 1e3,
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": a.config, "desc": c["desc"]},
+           "audio_samples_per_sec": v * 2048, "rtf": v / FRAME_RATE,
+           "cpu_baseline": {"value": v, "unit": "frames/s", "cores": threads, "kind": "port", "sample": desc},
+           "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+    from fish_speech_rs_b200 import DualARTransformer, FireflyCodec, SamplingArgs, generate_static_batch
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    c, mcfg, tok, prompts = build_inputs(a.config, rank)
+    B, N = c["batch"], c["frames"]
+    lm_w, codec_w = make_weights(c["version"])
+    max_len = max(p.shape[1] for p in prompts) + N + 8
+    lm = DualARTransformer(lm_w, mcfg, tok, fish_version=c["version"], device=local, dtype=a.dtype, max_batch=B,
+                           max_seq_len=max_len)
+    codec = FireflyCodec(codec_w, fish_version=c["version"], device=local, max_frames=N)
+    if not (a.cpu_baseline and rank == 0):
+        del lm_w
+    sargs = SamplingArgs(c["temp"], c["top_p"], 256, 1.4, seed=1234 + rank)
+    # pinned host buffers for the e2e leg
+    pin_prompts = []
+    for p in prompts:
+        t = torch.empty(p.shape, dtype=torch.int32).pin_memory()
+        v = t.numpy().view(np.uint32)
+        v[...] = p
+        pin_prompts.append(v)
+    pcm_pin = [torch.empty((1, 1, 2048 * N), dtype=torch.float32).pin_memory().numpy() for _ in range(B)]
+    h2d = sum(p.nbytes for p in prompts) + B * 8 * N * 4
+    d2h = B * 8 * N * 4 + B * 2048 * N * 4
+
+    def step():
+        codes = generate_static_batch(lm, pin_prompts, 100000, sargs, fixed_len=N)
+        st = lm.stats()
+        # synthetic-weight LMs emit codes >= 1000 that the FSQ table rejects (Q11): harness-side clamp
+        cl = [np.minimum(x, 999) for x in codes]
+        codec.decode_batch(cl, out=pcm_pin)
+        cs = codec.stats()
+        dev_ms = st["prefill_ms"] + st["decode_ms"] + cs["device_ms"]
+        return dev_ms, st, cs, sum(x.shape[1] for x in codes)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(a.warmup):
+        step()
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    t0 = time.perf_counter()
+    dev_ms_tot, frames_tot, launches = 0.0, 0, 0
+    lm_pre, lm_dec, voc = 0.0, 0.0, 0.0
+    for _ in range(a.steps):
+        dev_ms, st, cs, nf = step()
+        dev_ms_tot += dev_ms
+        frames_tot += nf
+        launches += st["kernel_launches"] + cs["kernel_launches"]
+        lm_pre += st["prefill_ms"]
+        lm_dec += st["decode_ms"]
+        voc += cs["device_ms"]
+    barrier()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
+    # one extra, untimed, profiled step: per-launch CUDA events around the weight-streaming GEMV
+    lm.set_profile(True)
+    generate_static_batch(lm, pin_prompts, 100000, sargs, fixed_len=min(N, 12))
+    pst = lm.stats()
+    lm.set_profile(False)
+
+    t = torch.tensor([dev_ms_tot, wall * 1e3], dtype=torch.float64, device="cuda")
+    fr = torch.tensor([float(frames_tot), float(launches)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(fr, op=dist.ReduceOp.SUM)
+    dev_ms_max, wall_ms_max = t.tolist()
+    frames_all, launches_all = fr.tolist()
+    if rank == 0:
+        peaks, peak_kind = measured_peaks()
+        value = frames_all / (dev_ms_max / 1e3)
+        e2e = frames_all / (wall_ms_max / 1e3)
+        n_l = max(pst["dominant_kernel_launches"], 1)
+        avg_ms = pst["dominant_kernel_ms"] / n_l
+        bytes_per_launch = pst["dominant_kernel_bytes"] / n_l
+        achieved = bytes_per_launch / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
+        wb = pst["weight_bytes_per_frame"]
+        out = {
+            "metric": "codec_tokens_per_sec", "value": value, "unit": "frames/s", "n_gpus": world, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": dev_ms_max / a.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": a.dtype, "data": "synthetic",
+            "config": {"workload": a.config, "desc": c["desc"], "utterances_per_gpu": B, "frames": N,
+                       "weights": "seeded random init, Fish 1.5 shapes", "codec_dtype": "f32",
+                       "l2": "no flush: per-frame weight stream (%.0f MB) >> 126 MB L2" % (wb / 1e6)},
+            "audio_samples_per_sec": value * 2048, "rtf": value / FRAME_RATE,
+            "breakdown_ms_per_step": {"lm_prefill": lm_pre / a.steps, "lm_decode": lm_dec / a.steps,
+                                      "vocoder": voc / a.steps},
+            "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "audio_samples_per_sec": e2e * 2048, "rtf": e2e / FRAME_RATE},
+            "gpu_launches": int(launches_all),
+            "roofline": {"bound": "hbm", "kernel": "gemv_kernel (weight-streaming GEMV, fused rmsnorm/residual/swiglu)",
+                         "achieved": achieved, "peak": peaks["hbm_gbs"], "peak_kind": peak_kind, "unit": "GB/s",
+                         "frac": achieved / peaks["hbm_gbs"], "traffic": None,
+                         "launches_timed": int(pst["dominant_kernel_launches"]),
+                         "avg_launch_us": avg_ms * 1e3, "algorithmic_bytes_per_launch": bytes_per_launch,
+                         "frame_bytes": wb,
+                         "frame_level_frac": (wb * (N - 1) * a.steps / (lm_dec / 1e3) / 1e9) / peaks["hbm_gbs"]},
+            "clocks": clocks,
+        }
+        if a.cpu_baseline:
+            threads = os.cpu_count() or 1
+            v, desc = cpu_reference_sample(a.config, lm_w, codec_w, a.cpu_sample_frames, threads)
+            out["cpu_baseline"] = {"value": v, "unit": "frames/s", "cores": threads, "kind": "port", "sample": desc}
+        print(json.dumps(out))
+    lm.close()
+    codec.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS))
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
+    ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    ap.add_argument("--cpu-sample-frames", type=int, default=16)
+    a = ap.parse_args()
+    if a.impl == "reference":
+        return run_reference(a)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if a.gpus > 1 and world == 1:
+        # convenience: re-launch under torchrun
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={a.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.abspath(__file__)] + sys.argv[1:]
+        return subprocess.call(cmd)
+    return run_ours(a)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

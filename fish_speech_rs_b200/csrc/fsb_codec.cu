@@ -1,0 +1,527 @@
+// FireflyCodec behind the C ABI: host-side mirror of fish_speech_core/lib/codec/
+// {firefly,decoder,encoder,quantizer,hifi_gan,convnext}.rs for Fish >= 1.4.
+#include <algorithm>
+#include <memory>
+
+#include "fsb_codec_kernels.cuh"
+
+namespace fsb {
+
+struct ConvW {
+    float *wt = nullptr;  // (Cin, K, Cout)
+    float *bias = nullptr;
+    int Cin = 0, Cout = 0, K = 0;
+};
+
+struct ConvNeXtW {
+    float *dw_w = nullptr, *dw_b = nullptr, *ln_w = nullptr, *ln_b = nullptr;
+    float *pw1_w = nullptr, *pw1_b = nullptr, *pw2_w = nullptr, *pw2_b = nullptr, *gamma = nullptr;
+    int dim = 0;
+};
+
+constexpr int kUpRates[5] = {8, 8, 2, 2, 2};     // codec/config.rs presets (hifi_gan.rs:145-167)
+constexpr int kUpKernels[5] = {16, 16, 4, 4, 4};
+constexpr int kResKernels[3] = {3, 7, 11};       // hifi_gan.rs:100-107
+constexpr int kResDilations[3] = {1, 3, 5};
+constexpr int kGroups = 8, kDim = 512;
+constexpr int kEncDims[4] = {128, 256, 384, 512};
+constexpr int kEncDepths[4] = {3, 3, 9, 3};
+
+}  // namespace fsb
+using namespace fsb;
+
+struct fsb_codec {
+    fsb_codec_options opt;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    std::vector<void *> owned;
+    // quantizer
+    float *proj_out_w = nullptr, *proj_out_b = nullptr;  // (G,64,4), (G,64)
+    float *proj_in_w = nullptr, *proj_in_b = nullptr;    // (G,4,64), (G,4)
+    ConvW up_conv[2], down_conv[2];
+    ConvNeXtW up_block[2], down_block[2];
+    // head
+    ConvW conv_pre, conv_post, ups[5];
+    ConvW res_c1[5][3][3], res_c2[5][3][3];
+    // encoder
+    ConvW stem;
+    float *stem_ln_w = nullptr, *stem_ln_b = nullptr;
+    float *mid_ln_w[4] = {}, *mid_ln_b[4] = {};
+    ConvW mid_conv[4];
+    std::vector<ConvNeXtW> enc_blocks[4];
+    float *enc_norm_w = nullptr, *enc_norm_b = nullptr;
+    // scratch
+    int max_frames = 0;
+    uint32_t *d_codes = nullptr;
+    int *d_err = nullptr;
+    float *buf[4] = {};  // 4 activation buffers of 32768 * max_frames floats
+    float *cn_h = nullptr, *cn_g = nullptr;
+    long long *d_idx = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evd0 = nullptr, evd1 = nullptr;
+    double device_ms_acc = 0;
+    fsb_codec_stats stats;
+    uint64_t launches = 0;
+};
+
+namespace fsb {
+
+#define CLAUNCH_CHECK(c)                                                                          \
+    do {                                                                                          \
+        cudaError_t _e = cudaGetLastError();                                                      \
+        if (_e != cudaSuccess) {                                                                  \
+            set_error("%s:%d: kernel launch -> %s", __FILE__, __LINE__, cudaGetErrorString(_e)); \
+            return FSB_ERR_CUDA;                                                                  \
+        }                                                                                         \
+        (c)->launches++;                                                                          \
+    } while (0)
+
+template <typename T>
+static int calloc_dev(fsb_codec *c, T **p, size_t n) {
+    void *q = nullptr;
+    cudaError_t e = cudaMalloc(&q, std::max<size_t>(n, 1) * sizeof(T));
+    if (e != cudaSuccess) {
+        set_error("cudaMalloc(%zu bytes) failed: %s", n * sizeof(T), cudaGetErrorString(e));
+        return e == cudaErrorMemoryAllocation ? FSB_ERR_OOM : FSB_ERR_CUDA;
+    }
+    c->owned.push_back(q);
+    *p = reinterpret_cast<T *>(q);
+    return FSB_OK;
+}
+
+// dst[(i1*d2 + i2)*d0 + i0] = src[(i0*d1 + i1)*d2 + i2]   (Cout,Cin,K) -> (Cin,K,Cout)
+__global__ void relayout_021_to_120(const float *__restrict__ src, float *__restrict__ dst, int d0, int d1, int d2) {
+    const size_t n = (size_t)d0 * d1 * d2;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int i2 = (int)(i % d2), i1 = (int)((i / d2) % d1), i0 = (int)(i / ((size_t)d1 * d2));
+        dst[((size_t)i1 * d2 + i2) * d0 + i0] = src[i];
+    }
+}
+// dst[(i0*d2 + i2)*d1 + i1] = src[(i0*d1 + i1)*d2 + i2]   (Cin,Cout,K) -> (Cin,K,Cout)
+__global__ void relayout_012_to_021(const float *__restrict__ src, float *__restrict__ dst, int d0, int d1, int d2) {
+    const size_t n = (size_t)d0 * d1 * d2;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int i2 = (int)(i % d2), i1 = (int)((i / d2) % d1), i0 = (int)(i / ((size_t)d1 * d2));
+        dst[((size_t)i0 * d2 + i2) * d1 + i1] = src[i];
+    }
+}
+
+static int load_vec(fsb_codec *c, const fsb_tensor *w, size_t n, const std::string &name, std::vector<int64_t> shape,
+                    float **out) {
+    DevTensor t;
+    FSB_TRY(upload_tensor(w, n, name, shape, FSB_F32, c->stream, &t, &c->owned));
+    *out = (float *)t.ptr;
+    return FSB_OK;
+}
+
+// Conv1d weight (Cout, Cin, K) / ConvTranspose1d weight (Cin, Cout, K) -> ConvW
+static int load_conv(fsb_codec *c, const fsb_tensor *w, size_t n, const std::string &prefix, int Cin, int Cout, int K,
+                     bool transposed, ConvW *out) {
+    DevTensor raw;
+    std::vector<void *> tmp_owned;
+    std::vector<int64_t> shape = transposed ? std::vector<int64_t>{Cin, Cout, K} : std::vector<int64_t>{Cout, Cin, K};
+    int st = upload_tensor(w, n, prefix + ".weight", shape, FSB_F32, c->stream, &raw, &tmp_owned);
+    if (st != FSB_OK) return st;
+    float *dst = nullptr;
+    st = calloc_dev(c, &dst, (size_t)Cin * Cout * K);
+    if (st == FSB_OK) {
+        if (transposed) relayout_012_to_021<<<256, 256, 0, c->stream>>>((const float *)raw.ptr, dst, Cin, Cout, K);
+        else relayout_021_to_120<<<256, 256, 0, c->stream>>>((const float *)raw.ptr, dst, Cout, Cin, K);
+        cudaError_t e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) {
+            set_error("weight relayout: %s", cudaGetErrorString(e));
+            st = FSB_ERR_CUDA;
+        }
+    }
+    for (void *p : tmp_owned) cudaFree(p);
+    FSB_TRY(st);
+    out->wt = dst;
+    out->Cin = Cin;
+    out->Cout = Cout;
+    out->K = K;
+    return load_vec(c, w, n, prefix + ".bias", {Cout}, &out->bias);
+}
+
+static int load_convnext(fsb_codec *c, const fsb_tensor *w, size_t n, const std::string &p, int dim, ConvNeXtW *o) {
+    o->dim = dim;
+    FSB_TRY(load_vec(c, w, n, p + "dwconv.conv.weight", {dim, 1, 7}, &o->dw_w));
+    FSB_TRY(load_vec(c, w, n, p + "dwconv.conv.bias", {dim}, &o->dw_b));
+    FSB_TRY(load_vec(c, w, n, p + "norm.weight", {dim}, &o->ln_w));
+    FSB_TRY(load_vec(c, w, n, p + "norm.bias", {dim}, &o->ln_b));
+    FSB_TRY(load_vec(c, w, n, p + "pwconv1.weight", {4 * dim, dim}, &o->pw1_w));
+    FSB_TRY(load_vec(c, w, n, p + "pwconv1.bias", {4 * dim}, &o->pw1_b));
+    FSB_TRY(load_vec(c, w, n, p + "pwconv2.weight", {dim, 4 * dim}, &o->pw2_w));
+    FSB_TRY(load_vec(c, w, n, p + "pwconv2.bias", {dim}, &o->pw2_b));
+    FSB_TRY(load_vec(c, w, n, p + "gamma", {dim}, &o->gamma));  // layer_scale_init_value > 0 in every preset
+    return FSB_OK;
+}
+
+// ---------------------------------------------------------------- launches
+static int launch_conv(fsb_codec *c, ConvArgs a) {
+    const int BN = 128;
+    const int off_lo = std::min(0, (a.K - 1) * a.dil) - a.pad, off_hi = std::max(0, (a.K - 1) * a.dil) - a.pad;
+    const int span = (BN - 1) * a.stride + off_hi - off_lo + 1;
+    const int gx = (a.Lout + BN - 1) / BN;
+    if (a.Lout <= 0) return FSB_OK;
+#define CONV_CASE(BM, TM)                                                                          \
+    {                                                                                              \
+        const size_t smem = ((size_t)kConvCK * a.K * BM + (size_t)kConvCK * span) * sizeof(float); \
+        FSB_REQUIRE(smem <= 200 * 1024, FSB_ERR_UNSUPPORTED, "conv tile needs %zu B of smem", smem); \
+        if (smem > 48 * 1024)                                                                      \
+            FSB_CUDA_OK(cudaFuncSetAttribute(conv1d_kernel<BM, TM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        conv1d_kernel<BM, TM><<<dim3(gx, (a.Cout + BM - 1) / BM), 256, smem, c->stream>>>(a);     \
+    }
+    if (a.Cout >= 64) CONV_CASE(64, 8)
+    else if (a.Cout >= 32) CONV_CASE(32, 4)
+    else CONV_CASE(16, 2)
+#undef CONV_CASE
+    CLAUNCH_CHECK(c);
+    return FSB_OK;
+}
+
+// FishConvNet::forward: y (Cout, Lout) = conv(x (Cin, Lin)), Lout = (Lin + pad - (K-1)*dil - 1)/stride + 1 == Lin/stride
+static int conv_fwd(fsb_codec *c, const ConvW &w, const float *x, int Lin, float *y, int dil, int stride,
+                    bool pre_silu, const float *res, int acc_mode, float scale, bool post_tanh, int *Lout_out) {
+    ConvArgs a;
+    memset(&a, 0, sizeof(a));
+    const int pad = (w.K - 1) * dil + 1 - stride;  // utils/mod.rs:43,55
+    const int Lout = (Lin + pad - (w.K - 1) * dil - 1) / stride + 1;
+    a.x = x; a.wt = w.wt; a.bias = w.bias; a.res = res; a.y = y;
+    a.Cin = w.Cin; a.Cout = w.Cout; a.Lin = Lin; a.Lout = Lout; a.Ly = Lout;
+    a.K = w.K; a.Kw = w.K; a.k0 = 0; a.kstep = 1;
+    a.dil = dil; a.pad = pad; a.stride = stride; a.ostride = 1; a.ooff = 0;
+    a.pre_silu = pre_silu; a.acc_mode = acc_mode; a.scale = scale; a.post_tanh = post_tanh;
+    if (Lout_out) *Lout_out = Lout;
+    return launch_conv(c, a);
+}
+
+// FishTransConvNet::forward: y (Cout, Lin*stride); kernel K in {stride, 2*stride}
+static int convT_fwd(fsb_codec *c, const ConvW &w, const float *x, int Lin, float *y, int stride, bool pre_silu) {
+    FSB_REQUIRE(w.K == stride || w.K == 2 * stride, FSB_ERR_UNSUPPORTED, "ConvTranspose1d k=%d s=%d unsupported", w.K,
+                stride);
+    for (int r = 0; r < stride; ++r) {
+        ConvArgs a;
+        memset(&a, 0, sizeof(a));
+        a.x = x; a.wt = w.wt; a.bias = w.bias; a.res = nullptr; a.y = y;
+        a.Cin = w.Cin; a.Cout = w.Cout; a.Lin = Lin; a.Lout = Lin; a.Ly = Lin * stride;
+        a.K = w.K / stride; a.Kw = w.K; a.k0 = r; a.kstep = stride;
+        a.dil = -1; a.pad = 0; a.stride = 1; a.ostride = stride; a.ooff = r;
+        a.pre_silu = pre_silu;
+        FSB_TRY(launch_conv(c, a));
+    }
+    return FSB_OK;
+}
+
+// ConvNeXtBlock::forward in place on x (C, L)
+static int convnext_fwd(fsb_codec *c, const ConvNeXtW &w, float *x, int L) {
+    const int C = w.dim;
+    const int warps = 4;
+    dwconv_ln_kernel<<<(L + warps - 1) / warps, warps * 32, warps * C * sizeof(float), c->stream>>>(
+        x, C, L, w.dw_w, w.dw_b, w.ln_w, w.ln_b, 1e-6f, c->cn_h);
+    CLAUNCH_CHECK(c);
+    pw_gemm_kernel<0><<<dim3((4 * C + 63) / 64, (L + 63) / 64), 256, 0, c->stream>>>(c->cn_h, w.pw1_w, w.pw1_b, nullptr,
+                                                                                     nullptr, c->cn_g, L, 4 * C, C);
+    CLAUNCH_CHECK(c);
+    pw_gemm_kernel<1><<<dim3((C + 63) / 64, (L + 63) / 64), 256, 0, c->stream>>>(c->cn_g, w.pw2_w, w.pw2_b, w.gamma, x,
+                                                                                 x, L, C, 4 * C);
+    CLAUNCH_CHECK(c);
+    return FSB_OK;
+}
+
+// FireflyDecoder::decode for one utterance; codes already on the device at c->d_codes (8, T)
+static int decode_device(fsb_codec *c, int T, float *pcm_dev_out /* device (2048*T) */) {
+    float *A = c->buf[0], *B = c->buf[1], *R = c->buf[2], *X1 = c->buf[3];
+    cudaStream_t st = c->stream;
+    FSB_CUDA_OK(cudaMemsetAsync(c->d_err, 0, sizeof(int), st));
+    fsq_decode_kernel<<<dim3((T + 127) / 128, kGroups), 128, 0, st>>>(c->d_codes, T, kGroups, c->proj_out_w,
+                                                                      c->proj_out_b, A, c->d_err);
+    CLAUNCH_CHECK(c);
+    // quantizer.upsample: upsample.0 then upsample.1 (quantizer.rs:126-133)
+    int L = T;
+    float *cur = A, *nxt = B;
+    for (int i = 0; i < 2; ++i) {
+        FSB_TRY(convT_fwd(c, c->up_conv[i], cur, L, nxt, 2, false));
+        L *= 2;
+        FSB_TRY(convnext_fwd(c, c->up_block[i], nxt, L));
+        std::swap(cur, nxt);
+    }
+    // HiFiGAN::forward (hifi_gan.rs:207-216)
+    FSB_TRY(conv_fwd(c, c->conv_pre, cur, L, nxt, 1, 1, false, nullptr, 0, 0.f, false, nullptr));
+    std::swap(cur, nxt);  // cur = M (stage input), nxt = U
+    const float third = (float)(1.0 / 3.0);
+    for (int i = 0; i < 5; ++i) {
+        float *M = cur, *U = nxt;
+        FSB_TRY(convT_fwd(c, c->ups[i], M, L, U, kUpRates[i], true));
+        L *= kUpRates[i];
+        for (int j = 0; j < 3; ++j) {
+            const float *xin = U;
+            for (int m = 0; m < 3; ++m) {
+                const int d = kResDilations[m];
+                FSB_TRY(conv_fwd(c, c->res_c1[i][j][m], xin, L, X1, d, 1, true, nullptr, 0, 0.f, false, nullptr));
+                if (m < 2) {
+                    FSB_TRY(conv_fwd(c, c->res_c2[i][j][m], X1, L, R, d, 1, true, xin, 0, 0.f, false, nullptr));
+                    xin = R;
+                } else {
+                    // last conv of the block feeds only stack+mean (hifi_gan.rs:113-118)
+                    FSB_TRY(conv_fwd(c, c->res_c2[i][j][m], X1, L, M, d, 1, true, xin, j == 0 ? 0 : (j == 1 ? 1 : 2),
+                                     third, false, nullptr));
+                }
+            }
+        }
+        // M holds the stage output; U is free
+    }
+    FSB_TRY(conv_fwd(c, c->conv_post, cur, L, pcm_dev_out, 1, 1, true, nullptr, 0, 0.f, true, nullptr));
+    return FSB_OK;
+}
+
+static int codec_create_impl(fsb_codec *c, const fsb_tensor *w, size_t n) {
+    FSB_TRY(select_device(c->opt.device));
+    if (c->opt.stream) c->stream = (cudaStream_t)c->opt.stream;
+    else {
+        FSB_CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        c->own_stream = true;
+    }
+    FSB_CUDA_OK(cudaEventCreate(&c->ev0));
+    FSB_CUDA_OK(cudaEventCreate(&c->ev1));
+    FSB_CUDA_OK(cudaEventCreate(&c->evd0));
+    FSB_CUDA_OK(cudaEventCreate(&c->evd1));
+    // FSQ projections, gathered per group into one array each
+    FSB_TRY(calloc_dev(c, &c->proj_out_w, (size_t)kGroups * 64 * 4));
+    FSB_TRY(calloc_dev(c, &c->proj_out_b, (size_t)kGroups * 64));
+    FSB_TRY(calloc_dev(c, &c->proj_in_w, (size_t)kGroups * 4 * 64));
+    FSB_TRY(calloc_dev(c, &c->proj_in_b, (size_t)kGroups * 4));
+    for (int g = 0; g < kGroups; ++g) {
+        const std::string p = "quantizer.residual_fsq.rvqs." + std::to_string(g) + ".";
+        float *t = nullptr;
+        FSB_TRY(load_vec(c, w, n, p + "project_out.weight", {64, 4}, &t));
+        FSB_CUDA_OK(cudaMemcpyAsync(c->proj_out_w + (size_t)g * 256, t, 256 * 4, cudaMemcpyDeviceToDevice, c->stream));
+        FSB_TRY(load_vec(c, w, n, p + "project_out.bias", {64}, &t));
+        FSB_CUDA_OK(cudaMemcpyAsync(c->proj_out_b + (size_t)g * 64, t, 64 * 4, cudaMemcpyDeviceToDevice, c->stream));
+        if (c->opt.with_encoder) {
+            FSB_TRY(load_vec(c, w, n, p + "project_in.weight", {4, 64}, &t));
+            FSB_CUDA_OK(cudaMemcpyAsync(c->proj_in_w + (size_t)g * 256, t, 256 * 4, cudaMemcpyDeviceToDevice, c->stream));
+            FSB_TRY(load_vec(c, w, n, p + "project_in.bias", {4}, &t));
+            FSB_CUDA_OK(cudaMemcpyAsync(c->proj_in_b + (size_t)g * 4, t, 4 * 4, cudaMemcpyDeviceToDevice, c->stream));
+        }
+    }
+    for (int i = 0; i < 2; ++i) {
+        const std::string p = "quantizer.upsample." + std::to_string(i) + ".";
+        FSB_TRY(load_conv(c, w, n, p + "0.conv", kDim, kDim, 2, true, &c->up_conv[i]));
+        FSB_TRY(load_convnext(c, w, n, p + "1.", kDim, &c->up_block[i]));
+    }
+    FSB_TRY(load_conv(c, w, n, "head.conv_pre.conv", kDim, kDim, 13, false, &c->conv_pre));
+    for (int i = 0; i < 5; ++i) {
+        const int cin = kDim >> i, cout = kDim >> (i + 1);
+        FSB_TRY(load_conv(c, w, n, "head.ups." + std::to_string(i) + ".conv", cin, cout, kUpKernels[i], true, &c->ups[i]));
+        for (int j = 0; j < 3; ++j)
+            for (int m = 0; m < 3; ++m) {
+                const std::string p = "head.resblocks." + std::to_string(i) + ".blocks." + std::to_string(j) + ".";
+                FSB_TRY(load_conv(c, w, n, p + "convs1." + std::to_string(m) + ".conv", cout, cout, kResKernels[j], false,
+                                  &c->res_c1[i][j][m]));
+                FSB_TRY(load_conv(c, w, n, p + "convs2." + std::to_string(m) + ".conv", cout, cout, kResKernels[j], false,
+                                  &c->res_c2[i][j][m]));
+            }
+    }
+    FSB_TRY(load_conv(c, w, n, "head.conv_post.conv", 16, 1, 13, false, &c->conv_post));
+    if (c->opt.with_encoder) {
+        for (int i = 0; i < 2; ++i) {
+            const std::string p = "quantizer.downsample." + std::to_string(i) + ".";
+            FSB_TRY(load_conv(c, w, n, p + "0.conv", kDim, kDim, 2, false, &c->down_conv[i]));
+            FSB_TRY(load_convnext(c, w, n, p + "1.", kDim, &c->down_block[i]));
+        }
+        const std::string d = "backbone.downsample_layers.";
+        FSB_TRY(load_conv(c, w, n, d + "0.0.conv", 160, kEncDims[0], 7, false, &c->stem));
+        FSB_TRY(load_vec(c, w, n, d + "0.1.weight", {kEncDims[0]}, &c->stem_ln_w));
+        FSB_TRY(load_vec(c, w, n, d + "0.1.bias", {kEncDims[0]}, &c->stem_ln_b));
+        for (int i = 1; i < 4; ++i) {
+            const std::string p = d + std::to_string(i) + ".";
+            FSB_TRY(load_vec(c, w, n, p + "0.weight", {kEncDims[i - 1]}, &c->mid_ln_w[i]));
+            FSB_TRY(load_vec(c, w, n, p + "0.bias", {kEncDims[i - 1]}, &c->mid_ln_b[i]));
+            FSB_TRY(load_conv(c, w, n, p + "1", kEncDims[i - 1], kEncDims[i], 1, false, &c->mid_conv[i]));
+        }
+        for (int i = 0; i < 4; ++i) {
+            c->enc_blocks[i].resize(kEncDepths[i]);
+            for (int j = 0; j < kEncDepths[i]; ++j)
+                FSB_TRY(load_convnext(c, w, n, "backbone.stages." + std::to_string(i) + "." + std::to_string(j) + ".",
+                                      kEncDims[i], &c->enc_blocks[i][j]));
+        }
+        FSB_TRY(load_vec(c, w, n, "backbone.norm.weight", {kDim}, &c->enc_norm_w));
+        FSB_TRY(load_vec(c, w, n, "backbone.norm.bias", {kDim}, &c->enc_norm_b));
+    }
+    // scratch
+    const size_t T = (size_t)c->max_frames;
+    FSB_TRY(calloc_dev(c, &c->d_codes, (size_t)kGroups * T));
+    FSB_TRY(calloc_dev(c, &c->d_err, 1));
+    for (int i = 0; i < 4; ++i) FSB_TRY(calloc_dev(c, &c->buf[i], 32768 * T));
+    FSB_TRY(calloc_dev(c, &c->cn_h, 4 * T * kDim));
+    FSB_TRY(calloc_dev(c, &c->cn_g, 4 * T * kDim * 4));
+    FSB_TRY(calloc_dev(c, &c->d_idx, (size_t)kGroups * T));
+    FSB_CUDA_OK(cudaStreamSynchronize(c->stream));
+    return FSB_OK;
+}
+
+static void codec_free(fsb_codec *c) {
+    if (!c) return;
+    for (void *p : c->owned) cudaFree(p);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->evd0) cudaEventDestroy(c->evd0);
+    if (c->evd1) cudaEventDestroy(c->evd1);
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+static int decode_one(fsb_codec *c, const uint32_t *codes, int T, float *pcm) {
+    FSB_REQUIRE(codes && pcm, FSB_ERR_INVALID, "decode: null pointer");
+    FSB_REQUIRE(T >= 1 && T <= c->max_frames, FSB_ERR_INVALID, "decode: %d frames outside [1, max_frames=%d]", T,
+                c->max_frames);
+    cudaStream_t st = c->stream;
+    FSB_CUDA_OK(cudaMemcpyAsync(c->d_codes, codes, (size_t)kGroups * T * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    // final PCM lands in buf[3] (X1 is free by then)
+    float *pcm_dev = c->buf[3];
+    FSB_CUDA_OK(cudaEventRecord(c->evd0, st));
+    FSB_TRY(decode_device(c, T, pcm_dev));
+    FSB_CUDA_OK(cudaEventRecord(c->evd1, st));
+    int err = 0;
+    FSB_CUDA_OK(cudaMemcpyAsync(pcm, pcm_dev, (size_t)T * 2048 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    FSB_CUDA_OK(cudaMemcpyAsync(&err, c->d_err, sizeof(int), cudaMemcpyDeviceToHost, st));
+    FSB_CUDA_OK(cudaStreamSynchronize(st));
+    FSB_REQUIRE(err == 0, FSB_ERR_INVALID, "decode: a code is >= 1000 (outside the FSQ implicit codebook, Q11)");
+    float dms = 0.f;
+    FSB_CUDA_OK(cudaEventElapsedTime(&dms, c->evd0, c->evd1));
+    c->device_ms_acc += dms;
+    return FSB_OK;
+}
+
+}  // namespace fsb
+
+extern "C" {
+
+int fsb_codec_create(const fsb_tensor *weights, size_t n_weights, const fsb_codec_options *opts, fsb_codec **out) {
+    FSB_REQUIRE(weights && opts && out, FSB_ERR_INVALID, "fsb_codec_create: null argument");
+    *out = nullptr;
+    FSB_REQUIRE(opts->fish_version == FSB_FISH_1_4 || opts->fish_version == FSB_FISH_1_5, FSB_ERR_UNSUPPORTED,
+                "only the causal (Fish >= 1.4) codec is implemented");
+    FSB_REQUIRE(opts->max_frames >= 1, FSB_ERR_INVALID, "max_frames must be >= 1");
+    std::unique_ptr<fsb_codec> c(new fsb_codec());
+    c->opt = *opts;
+    c->max_frames = opts->max_frames;
+    memset(&c->stats, 0, sizeof(c->stats));
+    int st = codec_create_impl(c.get(), weights, n_weights);
+    if (st != FSB_OK) {
+        codec_free(c.release());
+        (void)cudaGetLastError();
+        return st;
+    }
+    *out = c.release();
+    return FSB_OK;
+}
+
+int fsb_codec_destroy(fsb_codec *c) {
+    if (!c) return FSB_OK;
+    cudaSetDevice(c->opt.device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    codec_free(c);
+    (void)cudaGetLastError();
+    return FSB_OK;
+}
+
+int fsb_codec_decode(fsb_codec *c, const uint32_t *codes, int32_t n_frames, float *pcm) {
+    FSB_REQUIRE(c, FSB_ERR_INVALID, "null codec handle");
+    FSB_CUDA_OK(cudaSetDevice(c->opt.device));
+    const uint64_t l0 = c->launches;
+    c->device_ms_acc = 0;
+    FSB_CUDA_OK(cudaEventRecord(c->ev0, c->stream));
+    FSB_TRY(decode_one(c, codes, n_frames, pcm));
+    FSB_CUDA_OK(cudaEventRecord(c->ev1, c->stream));
+    FSB_CUDA_OK(cudaEventSynchronize(c->ev1));
+    float ms = 0.f;
+    FSB_CUDA_OK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    c->stats.decode_ms = ms;
+    c->stats.device_ms = c->device_ms_acc;
+    c->stats.kernel_launches = c->launches - l0;
+    return FSB_OK;
+}
+
+int fsb_codec_decode_batch(fsb_codec *c, const uint32_t *const *codes, const int32_t *n_frames, int32_t n,
+                           float *const *pcm) {
+    FSB_REQUIRE(c && codes && n_frames && pcm && n >= 1, FSB_ERR_INVALID, "decode_batch: bad arguments");
+    FSB_CUDA_OK(cudaSetDevice(c->opt.device));
+    const uint64_t l0 = c->launches;
+    c->device_ms_acc = 0;
+    FSB_CUDA_OK(cudaEventRecord(c->ev0, c->stream));
+    for (int i = 0; i < n; ++i) FSB_TRY(decode_one(c, codes[i], n_frames[i], pcm[i]));
+    FSB_CUDA_OK(cudaEventRecord(c->ev1, c->stream));
+    FSB_CUDA_OK(cudaEventSynchronize(c->ev1));
+    float ms = 0.f;
+    FSB_CUDA_OK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    c->stats.decode_ms = ms;
+    c->stats.device_ms = c->device_ms_acc;
+    c->stats.kernel_launches = c->launches - l0;
+    return FSB_OK;
+}
+
+int fsb_codec_encode_mel(fsb_codec *c, const float *mel, int32_t n_mel_frames, int64_t *codes, size_t cap,
+                         size_t *out_len) {
+    FSB_REQUIRE(c && mel && codes && out_len, FSB_ERR_INVALID, "encode_mel: null argument");
+    FSB_REQUIRE(c->opt.with_encoder, FSB_ERR_STATE, "codec was created without the encoder");
+    FSB_CUDA_OK(cudaSetDevice(c->opt.device));
+    const int Lm = n_mel_frames;
+    FSB_REQUIRE(Lm >= 4 && Lm <= 4 * c->max_frames, FSB_ERR_INVALID, "encode_mel: %d mel frames outside [4, %d]", Lm,
+                4 * c->max_frames);
+    cudaStream_t st = c->stream;
+    float *A = c->buf[0], *B = c->buf[1];
+    // mel (160, Lm) staged in buf[2]
+    FSB_CUDA_OK(cudaMemcpyAsync(c->buf[2], mel, (size_t)160 * Lm * sizeof(float), cudaMemcpyHostToDevice, st));
+    // ConvNeXtEncoder::forward (convnext.rs:325-334)
+    FSB_TRY(conv_fwd(c, c->stem, c->buf[2], Lm, A, 1, 1, false, nullptr, 0, 0.f, false, nullptr));
+    ln_channels_first_kernel<<<(Lm + 3) / 4, 128, 0, st>>>(A, kEncDims[0], Lm, c->stem_ln_w, c->stem_ln_b, 1e-6f, B);
+    CLAUNCH_CHECK(c);
+    float *cur = B, *oth = A;
+    for (int i = 0; i < 4; ++i) {
+        if (i > 0) {
+            ln_channels_first_kernel<<<(Lm + 3) / 4, 128, 0, st>>>(cur, kEncDims[i - 1], Lm, c->mid_ln_w[i],
+                                                                   c->mid_ln_b[i], 1e-6f, oth);
+            CLAUNCH_CHECK(c);
+            // plain Conv1d 1x1 (convnext.rs:249-257): no causal padding is needed for k == 1
+            FSB_TRY(conv_fwd(c, c->mid_conv[i], oth, Lm, cur, 1, 1, false, nullptr, 0, 0.f, false, nullptr));
+        }
+        for (auto &blk : c->enc_blocks[i]) FSB_TRY(convnext_fwd(c, blk, cur, Lm));
+    }
+    ln_channels_first_kernel<<<(Lm + 3) / 4, 128, 0, st>>>(cur, kDim, Lm, c->enc_norm_w, c->enc_norm_b, 1e-6f, oth);
+    CLAUNCH_CHECK(c);
+    std::swap(cur, oth);
+    // DownsampleFiniteScalarQuantizer::encode (quantizer.rs:104-124)
+    int L = Lm;
+    for (int i = 0; i < 2; ++i) {
+        int Lo = 0;
+        FSB_TRY(conv_fwd(c, c->down_conv[i], cur, L, oth, 1, 2, false, nullptr, 0, 0.f, false, &Lo));
+        L = Lo;
+        FSB_TRY(convnext_fwd(c, c->down_block[i], oth, L));
+        std::swap(cur, oth);
+    }
+    FSB_REQUIRE((size_t)L <= cap, FSB_ERR_INVALID, "encode_mel: capacity %zu < %d code frames", cap, L);
+    fsq_encode_kernel<<<dim3((L + 127) / 128, kGroups), 128, 0, st>>>(cur, L, kGroups, c->proj_in_w, c->proj_in_b,
+                                                                      c->d_idx);
+    CLAUNCH_CHECK(c);
+    std::vector<long long> host((size_t)kGroups * L);
+    FSB_CUDA_OK(cudaMemcpyAsync(host.data(), c->d_idx, host.size() * sizeof(long long), cudaMemcpyDeviceToHost, st));
+    FSB_CUDA_OK(cudaStreamSynchronize(st));
+    for (int g = 0; g < kGroups; ++g)
+        for (int t = 0; t < L; ++t) codes[(size_t)g * cap + t] = host[(size_t)g * L + t];
+    *out_len = (size_t)L;
+    return FSB_OK;
+}
+
+int fsb_codec_get_stats(fsb_codec *c, fsb_codec_stats *out) {
+    FSB_REQUIRE(c && out, FSB_ERR_INVALID, "null argument");
+    *out = c->stats;
+    return FSB_OK;
+}
+
+int32_t fsb_codec_sample_rate(const fsb_codec *c) {
+    (void)c;
+    return 44100;  // codec/config.rs: every Fish >= 1.4 preset
+}
+
+}  // extern "C"

@@ -1,0 +1,315 @@
+// Firefly-GAN-VQ codec kernels (fp32, batch 1 per launch).
+// Activations are channel-major (C, L) like the reference's (1, C, L) tensors.
+// Reference call sites are cited per kernel (paths relative to the reference
+// root, fish_speech_core/lib/codec/).
+#pragma once
+#include "fsb_common.cuh"
+
+namespace fsb {
+
+// gelu() of Candle == tanh approximation (Q10): 0.5 x (1 + tanh( sqrt(2/pi) x (1 + 0.044715 x^2) ))
+__device__ __forceinline__ float gelu_tanh_f(float x) {
+    const float k = 0.7978845608028654f;
+    return 0.5f * x * (1.0f + tanhf(k * x * (1.0f + 0.044715f * x * x)));
+}
+
+// ------------------------------------------------------------------ FSQ lookup + project_out
+// GroupedResidualFSQ::get_output_from_indices, grouped_residual_fsq.rs:95-114,175-185;
+// FSQ::indices_to_codes, fsq.rs:132-159.  codes (G, T) u32 -> z (G*64, T).
+// levels (8,5,5,5), basis (1,8,40,200); err[0] set to 1 if a code >= 1000 (Q11).
+__global__ void fsq_decode_kernel(const uint32_t *__restrict__ codes, int T, int G,
+                                  const float *__restrict__ proj_w,  // (G, 64, 4)
+                                  const float *__restrict__ proj_b,  // (G, 64)
+                                  float *__restrict__ z, int *err) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int g = blockIdx.y;
+    if (t >= T) return;
+    const uint32_t idx = codes[(size_t)g * T + t];
+    if (idx >= 1000u) {
+        *err = 1;
+        return;
+    }
+    // floor(idx / basis) mod levels, then (d - half) / half in f32 like the reference
+    const float fi = (float)idx;
+    const float lv[4] = {8.f, 5.f, 5.f, 5.f}, bs[4] = {1.f, 8.f, 40.f, 200.f};
+    float c[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float q = floorf(fi / bs[i]);
+        q = q - floorf(q / lv[i]) * lv[i];
+        const float hw = floorf(lv[i] / 2.0f);
+        c[i] = (q - hw) / hw;
+    }
+    const float *w = proj_w + (size_t)g * 64 * 4;
+    const float *b = proj_b + (size_t)g * 64;
+    for (int j = 0; j < 64; ++j) {
+        // Linear(4 -> 64): sequential f32 dot + bias
+        float acc = c[0] * w[j * 4 + 0];
+        acc = fmaf(c[1], w[j * 4 + 1], acc);
+        acc = fmaf(c[2], w[j * 4 + 2], acc);
+        acc = fmaf(c[3], w[j * 4 + 3], acc);
+        z[(size_t)(g * 64 + j) * T + t] = acc + b[j];
+    }
+}
+
+// ------------------------------------------------------------------ dense causal conv as implicit GEMM on FP32 FMA
+// FishConvNet::forward (utils/mod.rs:53-63): left pad (K-1)*dil + 1 - stride, Conv1d.
+// FishTransConvNet::forward (utils/mod.rs:110-122) runs through the same kernel, one
+// launch per output phase r (= t mod stride): taps {r, r + s}, x index j - tap.
+//   y[co, t*ostride + ooff] = epi( bias[co] + sum_ci sum_k Wt[(ci*Kw + k0 + k*kstep)*Cout + co] * pre(x[ci, t*stride + k*dil - pad]) )
+// Wt is the weight re-laid out at load time as (Cin, Kw, Cout) so tiles load coalesced.
+struct ConvArgs {
+    const float *x;     // (Cin, Lin)
+    const float *wt;    // (Cin, Kw, Cout)
+    const float *bias;  // (Cout) or null
+    const float *res;   // (Cout, Lres) residual added to the conv result, or null
+    float *y;           // (Cout, Ly)
+    int Cin, Cout, Lin, Lout;  // Lout = number of t positions this launch computes
+    int Ly;                    // row stride of y (and res)
+    int K;                     // taps this launch walks
+    int Kw, k0, kstep;         // tap k reads weight slot k0 + k*kstep of Kw
+    int dil, pad, stride;      // x index = t*stride + k*dil - pad   (dil may be negative)
+    int ostride, ooff;         // output column = t*ostride + ooff
+    int pre_silu;              // silu on the input (hifi_gan.rs:76-79,211-213)
+    int acc_mode;              // 0: y = v;  1: y = y + v;  2: y = (y + v) * scale   (stack + mean, hifi_gan.rs:113-118)
+    float scale;
+    int post_tanh;             // hifi_gan.rs:215
+};
+
+constexpr int kConvCK = 8;  // input channels staged per step
+
+template <int BM, int TM>
+__global__ void __launch_bounds__(256) conv1d_kernel(ConvArgs a) {
+    constexpr int BN = 128, TN = 4, NTX = 32;  // 32 lanes along t (stride-32 interleave -> conflict-free, coalesced)
+    constexpr int NTY = BM / TM;               // 8 warps along co
+    static_assert(NTY * NTX == 256, "256 threads");
+    extern __shared__ float smem[];
+    const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+    const int t0 = blockIdx.x * BN, co0 = blockIdx.y * BM;
+    // span of x indices needed for the tile: t in [t0, t0+BN), k in [0, K)
+    const int off_lo = min(0, (a.K - 1) * a.dil) - a.pad;
+    const int off_hi = max(0, (a.K - 1) * a.dil) - a.pad;
+    const int x_lo = t0 * a.stride + off_lo;
+    const int span = (BN - 1) * a.stride + off_hi - off_lo + 1;
+    float *ws = smem;                       // [kConvCK][K][BM]
+    float *xs = smem + kConvCK * a.K * BM;  // [kConvCK][span]
+    float acc[TM][TN];
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+    for (int c0 = 0; c0 < a.Cin; c0 += kConvCK) {
+        const int nc = min(kConvCK, a.Cin - c0);
+        // stage weights: (nc, K, BM)
+        for (int i = tid; i < nc * a.K * BM; i += 256) {
+            const int co = i % BM, k = (i / BM) % a.K, ci = i / (BM * a.K);
+            float w = 0.f;
+            if (co0 + co < a.Cout) w = a.wt[((size_t)(c0 + ci) * a.Kw + a.k0 + k * a.kstep) * a.Cout + co0 + co];
+            ws[i] = w;
+        }
+        // stage x with the causal zero padding
+        for (int i = tid; i < nc * span; i += 256) {
+            const int ci = i / span, p = i % span;
+            const int xi = x_lo + p;
+            float v = 0.f;
+            if (xi >= 0 && xi < a.Lin) {
+                v = a.x[(size_t)(c0 + ci) * a.Lin + xi];
+                if (a.pre_silu) v = silu_f(v);
+            }
+            xs[i] = v;
+        }
+        __syncthreads();
+        for (int ci = 0; ci < nc; ++ci) {
+            const float *wrow = ws + (size_t)ci * a.K * BM + ty * TM;
+            const float *xrow = xs + (size_t)ci * span - off_lo - a.pad;  // xrow[t_local*stride + k*dil]
+            for (int k = 0; k < a.K; ++k) {
+                float w[TM], xv[TN];
+#pragma unroll
+                for (int i = 0; i < TM; ++i) w[i] = wrow[k * BM + i];
+#pragma unroll
+                for (int j = 0; j < TN; ++j) xv[j] = xrow[(tx + j * NTX) * a.stride + k * a.dil];
+#pragma unroll
+                for (int i = 0; i < TM; ++i)
+#pragma unroll
+                    for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(w[i], xv[j], acc[i][j]);
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < TM; ++i) {
+        const int co = co0 + ty * TM + i;
+        if (co >= a.Cout) continue;
+        const float bv = a.bias ? a.bias[co] : 0.f;
+#pragma unroll
+        for (int j = 0; j < TN; ++j) {
+            const int t = t0 + tx + j * NTX;
+            if (t >= a.Lout) continue;
+            const size_t o = (size_t)co * a.Ly + (size_t)t * a.ostride + a.ooff;
+            float v = acc[i][j] + bv;
+            if (a.res) v = a.res[o] + v;
+            if (a.acc_mode == 1) v = a.y[o] + v;
+            else if (a.acc_mode == 2) v = (a.y[o] + v) * a.scale;
+            if (a.post_tanh) v = tanhf(v);
+            a.y[o] = v;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ ConvNeXt block pieces (convnext.rs:109-127)
+// depthwise causal conv k=7 (pad 6) + LayerNorm over channels (biased variance, eps) -> h (L, C) time-major.
+// One warp per time step.
+__global__ void dwconv_ln_kernel(const float *__restrict__ x, int C, int L, const float *__restrict__ dw_w,  // (C, 7)
+                                 const float *__restrict__ dw_b, const float *__restrict__ ln_w,
+                                 const float *__restrict__ ln_b, float eps, float *__restrict__ h) {
+    const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (t >= L) return;
+    extern __shared__ float sm[];
+    float *row = sm + (size_t)(threadIdx.x >> 5) * C;
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) {
+        float acc = 0.f;
+#pragma unroll
+        for (int k = 0; k < 7; ++k) {
+            const int xi = t + k - 6;
+            if (xi >= 0) acc = fmaf(dw_w[c * 7 + k], x[(size_t)c * L + xi], acc);
+        }
+        acc += dw_b[c];
+        row[c] = acc;
+        s += acc;
+    }
+    s = warp_sum(s);
+    const float mean = s / (float)C;
+    float v = 0.f;
+    for (int c = lane; c < C; c += 32) {
+        const float d = row[c] - mean;
+        v = fmaf(d, d, v);
+    }
+    v = warp_sum(v);
+    const float rstd = 1.0f / sqrtf(v / (float)C + eps);
+    for (int c = lane; c < C; c += 32) h[(size_t)t * C + c] = (row[c] - mean) * rstd * ln_w[c] + ln_b[c];
+}
+
+// C[M, N] = A[M, K] . W[N, K]^T + bias, epilogues for the two pointwise convs:
+//   EPI 0: gelu_tanh(v)                               -> Cm (M, N) row-major
+//   EPI 1: res[n, m] + gamma[n] * v, stored transposed -> Cm (N, M)  (back to channel-major + residual)
+template <int EPI>
+__global__ void __launch_bounds__(256) pw_gemm_kernel(const float *__restrict__ A, const float *__restrict__ W,
+                                                      const float *__restrict__ bias, const float *__restrict__ gamma,
+                                                      const float *res, float *Cm, int M,
+                                                      int N, int K) {
+    constexpr int BM = 64, BN = 64, BK = 16;
+    __shared__ float As[BK][BM + 4];
+    __shared__ float Ws[BK][BN + 4];
+    const int tid = threadIdx.x;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const int tx = tid % 16, ty = tid / 16;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    const int lr = tid / 4, lk = (tid % 4) * 4;
+    for (int k0 = 0; k0 < K; k0 += BK) {
+        float v[4] = {0.f, 0.f, 0.f, 0.f}, w[4] = {0.f, 0.f, 0.f, 0.f};
+        if (m0 + lr < M) {
+            const float4 t = *reinterpret_cast<const float4 *>(A + (size_t)(m0 + lr) * K + k0 + lk);
+            v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+        }
+        if (n0 + lr < N) {
+            const float4 t = *reinterpret_cast<const float4 *>(W + (size_t)(n0 + lr) * K + k0 + lk);
+            w[0] = t.x; w[1] = t.y; w[2] = t.z; w[3] = t.w;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            As[lk + i][lr] = v[i];
+            Ws[lk + i][lr] = w[i];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < BK; ++kk) {
+            float a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b[j] = Ws[kk][tx * 4 + j];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int m = m0 + ty * 4 + i;
+        if (m >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int n = n0 + tx * 4 + j;
+            if (n >= N) continue;
+            float v = acc[i][j] + bias[n];
+            if (EPI == 0) {
+                Cm[(size_t)m * N + n] = gelu_tanh_f(v);
+            } else {
+                if (gamma) v = gamma[n] * v;
+                Cm[(size_t)n * M + m] = res[(size_t)n * M + m] + v;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------ encoder-only pieces
+// LayerNormChannelsFirst (convnext.rs:144-154): normalise over channels at each t.  One warp per t.
+__global__ void ln_channels_first_kernel(const float *__restrict__ x, int C, int L, const float *__restrict__ w,
+                                         const float *__restrict__ b, float eps, float *__restrict__ y) {
+    const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (t >= L) return;
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) s += x[(size_t)c * L + t];
+    s = warp_sum(s);
+    const float u = s / (float)C;
+    float v = 0.f;
+    for (int c = lane; c < C; c += 32) {
+        const float d = x[(size_t)c * L + t] - u;
+        v = fmaf(d, d, v);
+    }
+    v = warp_sum(v);
+    const float den = sqrtf(v / (float)C + eps);
+    for (int c = lane; c < C; c += 32) y[(size_t)c * L + t] = (x[(size_t)c * L + t] - u) / den * w[c] + b[c];
+}
+
+// FSQ encode of one group at one position (grouped_residual_fsq.rs:75-93, fsq.rs:68-130):
+// project_in (64 -> 4), bound twice, round half away from zero, index = sum digit * basis.
+// z (512, L) channel-major -> idx (G, L) int64.
+__global__ void fsq_encode_kernel(const float *__restrict__ z, int L, int G, const float *__restrict__ pin_w,  // (G,4,64)
+                                  const float *__restrict__ pin_b,                                               // (G,4)
+                                  long long *__restrict__ idx) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int g = blockIdx.y;
+    if (t >= L) return;
+    const float lv[4] = {8.f, 5.f, 5.f, 5.f}, bs[4] = {1.f, 8.f, 40.f, 200.f};
+    float out = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float acc = 0.f;
+        for (int d = 0; d < 64; ++d) acc = fmaf(z[(size_t)(g * 64 + d) * L + t], pin_w[((size_t)g * 4 + i) * 64 + d], acc);
+        acc += pin_b[g * 4 + i];
+        const float half_l = (lv[i] - 1.0f) * 1.001f / 2.0f;
+        const float offset = (lv[i] - floorf(lv[i] / 2.0f) * 2.0f == 0.f) ? 0.5f : 0.f;
+        const float r = offset / half_l;
+        const float shift = logf((1.0f + r) / (1.0f - r)) * 0.5f;  // atanh
+        float v = tanhf(acc + shift) * half_l - offset;             // implicit first step
+        v = tanhf(v + shift) * half_l - offset;                     // FSQ::forward bounds again
+        const float q = copysignf(floorf(fabsf(v) + 0.5f), v);      // round half away from zero
+        const float hw = floorf(lv[i] / 2.0f);
+        const float zhat = (q / hw) * hw + hw;
+        out += zhat * bs[i];
+    }
+    idx[(size_t)g * L + t] = (long long)out;
+}
+
+}  // namespace fsb

@@ -1,0 +1,1016 @@
+// DualARTransformer + generation loops behind the C ABI (include/fsb.h).
+// Host-side mirror of fish_speech_core/lib/lm/dual_ar.rs:443-713 and
+// lm/generate/single_batch.rs; the device work is in fsb_lm_kernels.cuh and
+// fsb_lm_mega.cuh.  No CPU fallback: every entry point needs an sm_100 device.
+#include <algorithm>
+#include <cmath>
+#include <memory>
+
+#include "fsb_lm_kernels.cuh"
+
+namespace fsb {
+
+struct LayerW {
+    DevTensor wqkv, wo, w1, w2, w3;
+    DevTensor attn_norm, ffn_norm;  // always f32
+};
+
+struct Scratch {
+    float *x = nullptr, *xn = nullptr, *qkv = nullptr, *q = nullptr, *att = nullptr, *g1 = nullptr, *g3 = nullptr;
+    float *partial = nullptr;
+    float *logits = nullptr;       // (B, V)   step API only
+    float *slow_logits = nullptr;  // (B, V')
+    float *hidden = nullptr;       // (B, D)
+    float *fast_x = nullptr;       // (B, D)
+    float *fast_logits = nullptr;  // (B, CS)
+    uint32_t *toks = nullptr;      // (C+1, Mmax) prompt staging
+};
+
+}  // namespace fsb
+
+using namespace fsb;
+
+struct fsb_lm {
+    fsb_model_args cfg;
+    fsb_token_config tok;
+    fsb_lm_options opt;
+    int D, I, H, KV, hd, V, C, CS, QKV, NL, NFL;
+    int max_batch, max_len, fast_len;
+    int wdt;  // weight dtype
+    int prefill_rows;
+    int nsplit;
+    int n_slow_logits, slow_row0, slow_rest_base;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    bool poisoned = false;
+    std::vector<void *> owned;
+    DevTensor emb, cb_emb, out_w, fast_emb, fast_out, norm, fast_norm;
+    std::vector<LayerW> layers, fast_layers;
+    float *cosT = nullptr, *sinT = nullptr;
+    float *kc = nullptr, *vc = nullptr;    // (NL, B, KV, max_len, hd)
+    float *fkc = nullptr, *fvc = nullptr;  // (NFL, B, KV, fast_len, hd)
+    Scratch s;
+    // generation state
+    GenState h_st;            // host copy of the device struct
+    GenState *d_st = nullptr;
+    std::vector<int> kv_len;  // host mirror of pos[] between calls
+    int *h_pin = nullptr;     // pinned staging (ints)
+    std::map<int, cudaGraphExec_t> frame_graphs;  // keyed by bsz
+    std::map<int, cudaGraphExec_t> tail_graphs;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
+    fsb_lm_stats stats;
+    uint64_t launches = 0;
+    // profile mode: event pairs around the weight-streaming kernel
+    bool profile = false;
+    std::vector<cudaEvent_t> prof_ev;
+    size_t prof_used = 0;
+    uint64_t prof_bytes = 0;
+};
+
+namespace fsb {
+
+static size_t esize(int dt) { return dt == FSB_F32 ? 4 : 2; }
+
+template <typename T>
+static int dev_alloc(fsb_lm *lm, T **p, size_t n) {
+    void *q = nullptr;
+    cudaError_t e = cudaMalloc(&q, std::max<size_t>(n, 1) * sizeof(T));
+    if (e != cudaSuccess) {
+        set_error("cudaMalloc(%zu bytes) failed: %s", n * sizeof(T), cudaGetErrorString(e));
+        return e == cudaErrorMemoryAllocation ? FSB_ERR_OOM : FSB_ERR_CUDA;
+    }
+    lm->owned.push_back(q);
+    *p = reinterpret_cast<T *>(q);
+    return FSB_OK;
+}
+
+#define LAUNCH_CHECK(lm)                                                          \
+    do {                                                                          \
+        cudaError_t _e = cudaGetLastError();                                      \
+        if (_e != cudaSuccess) {                                                  \
+            set_error("%s:%d: kernel launch -> %s", __FILE__, __LINE__, cudaGetErrorString(_e)); \
+            return FSB_ERR_CUDA;                                                  \
+        }                                                                         \
+        (lm)->launches++;                                                         \
+    } while (0)
+
+// ---------------------------------------------------------------- GEMV dispatch
+static int pick_gemv_grid(int rows) {
+    const int ctas = (rows + kGemvRowsPerCta - 1) / kGemvRowsPerCta;
+    return std::max(1, std::min(ctas, 148 * 4));
+}
+
+template <typename WT, int EPI>
+static int launch_gemv_nb(fsb_lm *lm, GemvArgs a, int nb) {
+    const int grid = pick_gemv_grid(a.rows);
+    // rows of `x`/`y` are processed in groups of <= 8; a group re-reads the weights (L2-resident)
+    for (int b0 = 0; b0 < nb; b0 += 8) {
+        GemvArgs g = a;
+        const int n = std::min(8, nb - b0);
+        g.x = a.x + (size_t)b0 * a.ldx;
+        g.y = a.y + (size_t)b0 * a.ldy;
+        if (a.resid) g.resid = a.resid + (size_t)b0 * a.ldy;
+#define GEMV_CASE(NB)                                                                                        \
+    case NB:                                                                                                 \
+        gemv_kernel<WT, NB, EPI><<<grid, kGemvThreads, (size_t)NB * a.K * sizeof(float), lm->stream>>>(g); \
+        break;
+        const bool prof = lm->profile && lm->prof_used + 2 <= lm->prof_ev.size();
+        if (prof) cudaEventRecord(lm->prof_ev[lm->prof_used], lm->stream);
+        switch (n) {
+            GEMV_CASE(1) GEMV_CASE(2) GEMV_CASE(3) GEMV_CASE(4) GEMV_CASE(5) GEMV_CASE(6) GEMV_CASE(7) GEMV_CASE(8)
+        }
+#undef GEMV_CASE
+        if (prof) {
+            cudaEventRecord(lm->prof_ev[lm->prof_used + 1], lm->stream);
+            lm->prof_used += 2;
+            lm->prof_bytes += (uint64_t)a.rows * a.K * sizeof(WT) * (EPI == EPI_SWIGLU ? 2 : 1);
+        }
+        LAUNCH_CHECK(lm);
+    }
+    return FSB_OK;
+}
+
+// dynamic smem opt-in for every GEMV instantiation (done once, outside graph capture)
+template <typename WT, int EPI>
+static cudaError_t init_gemv_attrs_epi(int bytes) {
+    cudaError_t e = cudaSuccess;
+#define GEMV_ATTR(NB)                                                                                          \
+    if (e == cudaSuccess && (size_t)bytes / 8 * NB > 48 * 1024)                                                \
+        e = cudaFuncSetAttribute(gemv_kernel<WT, NB, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes / 8 * NB);
+    GEMV_ATTR(1) GEMV_ATTR(2) GEMV_ATTR(3) GEMV_ATTR(4) GEMV_ATTR(5) GEMV_ATTR(6) GEMV_ATTR(7) GEMV_ATTR(8)
+#undef GEMV_ATTR
+    return e;
+}
+static cudaError_t init_gemv_attrs(int max_k) {
+    const int bytes = 8 * max_k * (int)sizeof(float);
+    cudaError_t e = init_gemv_attrs_epi<float, EPI_STORE>(bytes);
+    if (e == cudaSuccess) e = init_gemv_attrs_epi<float, EPI_RESID>(bytes);
+    if (e == cudaSuccess) e = init_gemv_attrs_epi<float, EPI_SWIGLU>(bytes);
+    if (e == cudaSuccess) e = init_gemv_attrs_epi<__nv_bfloat16, EPI_STORE>(bytes);
+    if (e == cudaSuccess) e = init_gemv_attrs_epi<__nv_bfloat16, EPI_RESID>(bytes);
+    if (e == cudaSuccess) e = init_gemv_attrs_epi<__nv_bfloat16, EPI_SWIGLU>(bytes);
+    return e;
+}
+
+template <int EPI>
+static int launch_gemv(fsb_lm *lm, const DevTensor &W, const DevTensor *W3, const float *x, int ldx,
+                       const float *norm_w, const float *resid, float *y, int ldy, int rows, int K, int nb,
+                       const int *n_active, int row0 = 0, int rest_base = 1) {
+    GemvArgs a;
+    a.W = W.ptr;
+    a.W3 = W3 ? W3->ptr : nullptr;
+    a.x = x;
+    a.norm_w = norm_w;
+    a.resid = resid;
+    a.y = y;
+    a.rows = rows;
+    a.K = K;
+    a.ldx = ldx;
+    a.ldy = ldy;
+    a.eps = lm->cfg.norm_eps;
+    a.row0 = row0;
+    a.rest_base = rest_base;
+    a.n_active = n_active;
+    if (W.dtype == FSB_F32) return launch_gemv_nb<float, EPI>(lm, a, nb);
+    return launch_gemv_nb<__nv_bfloat16, EPI>(lm, a, nb);
+}
+
+// ---------------------------------------------------------------- one decode step of a block stack
+// x (nb, D) in place.  pos_ptr (device, per row) or pos_imm.
+static int decode_layer(fsb_lm *lm, const LayerW &L, float *x, int nb, float *kc, float *vc, int cache_len,
+                        const int *pos_ptr, int pos_imm, int rope_delta, const int *n_active, int nsplit) {
+    const int D = lm->D, H = lm->H, KV = lm->KV, hd = lm->hd, I = lm->I, QKV = lm->QKV;
+    Scratch &s = lm->s;
+    FSB_TRY(launch_gemv<EPI_STORE>(lm, L.wqkv, nullptr, x, D, (const float *)L.attn_norm.ptr, nullptr, s.qkv, QKV,
+                                   QKV, D, nb, n_active));
+    rope_append_kernel<<<nb, 256, 0, lm->stream>>>(s.qkv, s.q, kc, vc, lm->cosT, lm->sinT, pos_ptr, pos_imm,
+                                                   rope_delta, H, KV, hd, cache_len, n_active);
+    LAUNCH_CHECK(lm);
+    const int n_rep = H / KV;
+    attn_decode_split_kernel<<<dim3(nsplit, KV, nb), n_rep * 32, n_rep * hd * sizeof(float), lm->stream>>>(
+        s.q, kc, vc, pos_ptr, pos_imm, H, KV, hd, cache_len, 1.0f / sqrtf((float)hd), s.partial, n_active);
+    LAUNCH_CHECK(lm);
+    attn_decode_combine_kernel<<<nb * H, hd, 0, lm->stream>>>(s.partial, nsplit, hd, s.att, n_active);
+    LAUNCH_CHECK(lm);
+    FSB_TRY(launch_gemv<EPI_RESID>(lm, L.wo, nullptr, s.att, H * hd, nullptr, x, x, D, D, H * hd, nb, n_active));
+    FSB_TRY(launch_gemv<EPI_SWIGLU>(lm, L.w1, &L.w3, x, D, (const float *)L.ffn_norm.ptr, nullptr, s.g1, I, I, D, nb,
+                                    n_active));
+    FSB_TRY(launch_gemv<EPI_RESID>(lm, L.w2, nullptr, s.g1, I, nullptr, x, x, D, D, I, nb, n_active));
+    return FSB_OK;
+}
+
+template <typename WT>
+static void launch_embed(fsb_lm *lm, const uint32_t *toks, int nrows, int S, float *x, const int *n_active) {
+    embed_sum_kernel<WT><<<nrows, 256, 0, lm->stream>>>(toks, S, lm->C, lm->D, lm->CS, (const WT *)lm->emb.ptr,
+                                                       (const WT *)lm->cb_emb.ptr, lm->tok.semantic_start_id,
+                                                       lm->tok.semantic_end_id, lm->tok.has_semantic_end, x,
+                                                       n_active);
+}
+static int embed(fsb_lm *lm, const uint32_t *toks, int nrows, int S, float *x, const int *n_active) {
+    if (lm->wdt == FSB_F32) launch_embed<float>(lm, toks, nrows, S, x, n_active);
+    else launch_embed<__nv_bfloat16>(lm, toks, nrows, S, x, n_active);
+    LAUNCH_CHECK(lm);
+    return FSB_OK;
+}
+
+static float *slow_k(fsb_lm *lm, int l) { return lm->kc + (size_t)l * lm->max_batch * lm->KV * lm->max_len * lm->hd; }
+static float *slow_v(fsb_lm *lm, int l) { return lm->vc + (size_t)l * lm->max_batch * lm->KV * lm->max_len * lm->hd; }
+static float *fast_k(fsb_lm *lm, int l) { return lm->fkc + (size_t)l * lm->max_batch * lm->KV * lm->fast_len * lm->hd; }
+static float *fast_v(fsb_lm *lm, int l) { return lm->fvc + (size_t)l * lm->max_batch * lm->KV * lm->fast_len * lm->hd; }
+
+// ---------------------------------------------------------------- prefill of one row (S > 1)
+template <typename WT, int EPI>
+static void launch_gemm(fsb_lm *lm, const float *A, const DevTensor &W, const float *resid, float *Cm, int M, int N,
+                        int K) {
+    dim3 grid((N + kGemmBN - 1) / kGemmBN, (M + kGemmBM - 1) / kGemmBM);
+    gemm_nt_kernel<WT, EPI><<<grid, 256, 0, lm->stream>>>(A, (const WT *)W.ptr, resid, Cm, M, N, K);
+}
+template <int EPI>
+static int gemm(fsb_lm *lm, const float *A, const DevTensor &W, const float *resid, float *Cm, int M, int N, int K) {
+    if (W.dtype == FSB_F32) launch_gemm<float, EPI>(lm, A, W, resid, Cm, M, N, K);
+    else launch_gemm<__nv_bfloat16, EPI>(lm, A, W, resid, Cm, M, N, K);
+    LAUNCH_CHECK(lm);
+    return FSB_OK;
+}
+
+// toks_dev: (C+1, S_total) device, columns [c0, c0+S) are processed; KV rows land at pos0.. of row b.
+static int prefill_chunk(fsb_lm *lm, const uint32_t *toks_dev, int S_total, int c0, int S, int b, int pos0,
+                         int rope_delta) {
+    const int D = lm->D, H = lm->H, KV = lm->KV, hd = lm->hd, I = lm->I, QKV = lm->QKV;
+    Scratch &s = lm->s;
+    // embed: token (c, s) at toks_dev[c * S_total + c0 + s]; reuse the kernel with S = S_total, rows offset
+    {
+        // the embed kernel indexes toks[(b*(C+1) + c)*S + s]; feed it a shifted base so that s in [0, S)
+        if (lm->wdt == FSB_F32)
+            embed_sum_kernel<float><<<S, 256, 0, lm->stream>>>(toks_dev + c0, S_total, lm->C, D, lm->CS,
+                                                              (const float *)lm->emb.ptr, (const float *)lm->cb_emb.ptr,
+                                                              lm->tok.semantic_start_id, lm->tok.semantic_end_id,
+                                                              lm->tok.has_semantic_end, s.x, nullptr);
+        else
+            embed_sum_kernel<__nv_bfloat16><<<S, 256, 0, lm->stream>>>(
+                toks_dev + c0, S_total, lm->C, D, lm->CS, (const __nv_bfloat16 *)lm->emb.ptr,
+                (const __nv_bfloat16 *)lm->cb_emb.ptr, lm->tok.semantic_start_id, lm->tok.semantic_end_id,
+                lm->tok.has_semantic_end, s.x, nullptr);
+        LAUNCH_CHECK(lm);
+    }
+    const float scale = 1.0f / sqrtf((float)hd);
+    for (int l = 0; l < lm->NL; ++l) {
+        const LayerW &L = lm->layers[l];
+        rmsnorm_rows_kernel<<<(S + 3) / 4, 128, 0, lm->stream>>>(s.x, (const float *)L.attn_norm.ptr,
+                                                                 lm->cfg.norm_eps, S, D, s.xn);
+        LAUNCH_CHECK(lm);
+        FSB_TRY(gemm<EPI_STORE>(lm, s.xn, L.wqkv, nullptr, s.qkv, S, QKV, D));
+        rope_append_rows_kernel<<<S, 256, 0, lm->stream>>>(s.qkv, s.q, slow_k(lm, l), slow_v(lm, l), lm->cosT,
+                                                           lm->sinT, b, pos0, rope_delta, H, KV, hd, lm->max_len);
+        LAUNCH_CHECK(lm);
+        attn_prefill_kernel<<<dim3((S + 3) / 4, H), 128, 0, lm->stream>>>(s.q, slow_k(lm, l), slow_v(lm, l), b, pos0,
+                                                                          S, H, KV, hd, lm->max_len, scale, s.att);
+        LAUNCH_CHECK(lm);
+        FSB_TRY(gemm<EPI_RESID>(lm, s.att, L.wo, s.x, s.x, S, D, H * hd));
+        rmsnorm_rows_kernel<<<(S + 3) / 4, 128, 0, lm->stream>>>(s.x, (const float *)L.ffn_norm.ptr, lm->cfg.norm_eps,
+                                                                 S, D, s.xn);
+        LAUNCH_CHECK(lm);
+        FSB_TRY(gemm<EPI_STORE>(lm, s.xn, L.w1, nullptr, s.g1, S, I, D));
+        FSB_TRY(gemm<EPI_STORE>(lm, s.xn, L.w3, nullptr, s.g3, S, I, D));
+        const size_t n = (size_t)S * I;
+        swiglu_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, lm->stream>>>(s.g1, s.g3, n, s.g1);
+        LAUNCH_CHECK(lm);
+        FSB_TRY(gemm<EPI_RESID>(lm, s.g1, L.w2, s.x, s.x, S, D, I));
+    }
+    return FSB_OK;
+}
+
+// Prefill `S` prompt columns of row b (chunked to the scratch size); leaves the
+// pre-norm last-position state in s.hidden[b].
+static int prefill_row(fsb_lm *lm, const uint32_t *toks_dev, int S, int b, int pos0, int rope_delta) {
+    for (int c0 = 0; c0 < S; c0 += lm->prefill_rows) {
+        const int n = std::min(lm->prefill_rows, S - c0);
+        FSB_TRY(prefill_chunk(lm, toks_dev, S, c0, n, b, pos0 + c0, rope_delta));
+        if (c0 + n == S)
+            FSB_CUDA_OK(cudaMemcpyAsync(lm->s.hidden + (size_t)b * lm->D, lm->s.x + (size_t)(n - 1) * lm->D,
+                                        lm->D * sizeof(float), cudaMemcpyDeviceToDevice, lm->stream));
+    }
+    return FSB_OK;
+}
+
+// norm + constrained output head on s.hidden -> s.slow_logits (generate/utils.rs:6-33)
+static int slow_head(fsb_lm *lm, int nb, const int *n_active) {
+    return launch_gemv<EPI_STORE>(lm, lm->out_w, nullptr, lm->s.hidden, lm->D, (const float *)lm->norm.ptr, nullptr,
+                                  lm->s.slow_logits, lm->n_slow_logits, lm->n_slow_logits, lm->D, nb, n_active,
+                                  lm->slow_row0, lm->slow_rest_base);
+}
+
+static size_t sample_smem(int n) {
+    int n_pad = 1;
+    while (n_pad < n) n_pad <<= 1;
+    return (size_t)n_pad * 12 + 64 * 4 * 2;
+}
+
+// slow sample + C fast steps + frame bookkeeping (single_batch.rs:126-204)
+static int frame_tail(fsb_lm *lm, int nb) {
+    Scratch &s = lm->s;
+    const int *na = lm->h_st.n_active;
+    FSB_TRY(slow_head(lm, nb, na));
+    sample_slow_kernel<<<nb, kSampleThreads, sample_smem(lm->n_slow_logits), lm->stream>>>(
+        s.slow_logits, lm->n_slow_logits, lm->n_slow_logits, lm->d_st, lm->tok.semantic_start_id, s.hidden, s.fast_x,
+        lm->D);
+    LAUNCH_CHECK(lm);
+    for (int cb = 0; cb < lm->C; ++cb) {
+        for (int l = 0; l < lm->NFL; ++l)
+            FSB_TRY(decode_layer(lm, lm->fast_layers[l], s.fast_x, nb, fast_k(lm, l), fast_v(lm, l), lm->fast_len,
+                                 nullptr, cb, 0, na, 1));
+        FSB_TRY(launch_gemv<EPI_STORE>(lm, lm->fast_out, nullptr, s.fast_x, lm->D, (const float *)lm->fast_norm.ptr,
+                                       nullptr, s.fast_logits, lm->CS, lm->CS, lm->D, nb, na));
+        if (lm->wdt == FSB_F32)
+            sample_fast_kernel<float><<<nb, kSampleThreads, sample_smem(lm->CS), lm->stream>>>(
+                s.fast_logits, lm->CS, cb, lm->d_st, (const float *)lm->fast_emb.ptr, s.fast_x, lm->D);
+        else
+            sample_fast_kernel<__nv_bfloat16><<<nb, kSampleThreads, sample_smem(lm->CS), lm->stream>>>(
+                s.fast_logits, lm->CS, cb, lm->d_st, (const __nv_bfloat16 *)lm->fast_emb.ptr, s.fast_x, lm->D);
+        LAUNCH_CHECK(lm);
+    }
+    return FSB_OK;
+}
+
+// one decode frame for nb rows: slow step on `prev` codes + tail
+static int decode_frame(fsb_lm *lm, int nb) {
+    Scratch &s = lm->s;
+    const int *na = lm->h_st.n_active;
+    FSB_TRY(embed(lm, lm->h_st.prev, nb, 1, s.hidden, na));
+    for (int l = 0; l < lm->NL; ++l)
+        FSB_TRY(decode_layer(lm, lm->layers[l], s.hidden, nb, slow_k(lm, l), slow_v(lm, l), lm->max_len,
+                             lm->h_st.pos, 0, 0, na, lm->nsplit));
+    return frame_tail(lm, nb);
+}
+
+static int get_graph(fsb_lm *lm, std::map<int, cudaGraphExec_t> &cache, int nb, bool with_slow,
+                     cudaGraphExec_t *out) {
+    auto it = cache.find(nb);
+    if (it != cache.end()) {
+        *out = it->second;
+        return FSB_OK;
+    }
+    FSB_CUDA_OK(cudaStreamBeginCapture(lm->stream, cudaStreamCaptureModeThreadLocal));
+    const uint64_t l0 = lm->launches;
+    int st = with_slow ? decode_frame(lm, nb) : frame_tail(lm, nb);
+    cudaGraph_t g = nullptr;
+    cudaError_t e = cudaStreamEndCapture(lm->stream, &g);
+    const uint64_t per_graph = lm->launches - l0;
+    lm->launches = l0;
+    if (st != FSB_OK) {
+        if (g) cudaGraphDestroy(g);
+        return st;
+    }
+    FSB_CUDA_OK(e);
+    cudaGraphExec_t ge = nullptr;
+    FSB_CUDA_OK(cudaGraphInstantiate(&ge, g, 0));
+    cudaGraphDestroy(g);
+    cache[nb] = ge;
+    // remember how many kernels one replay launches
+    cache[-nb - 1] = reinterpret_cast<cudaGraphExec_t>((uintptr_t)per_graph);
+    *out = ge;
+    return FSB_OK;
+}
+static uint64_t graph_launches(std::map<int, cudaGraphExec_t> &cache, int nb) {
+    return (uint64_t)(uintptr_t)cache[-nb - 1];
+}
+
+static void precompute_freqs(const fsb_model_args &c, int max_len, std::vector<float> *cosv, std::vector<float> *sinv) {
+    // dual_ar.rs:168-186: theta_i = 1 / base^(i/n) in f32, idx_theta = pos * theta (f32 product), cos/sin.
+    // Transcendentals in f64 rounded once to f32 (== correctly rounded f32), as in oracle/dual_ar.py.
+    const int n_elem = c.dim / c.n_head;
+    const int half = n_elem / 2;
+    std::vector<float> theta(half);
+    for (int i = 0; i < half; ++i) {
+        const float expo = (float)(2 * i) / (float)n_elem;
+        const float p = (float)std::pow((double)c.rope_base, (double)expo);
+        theta[i] = 1.0f / p;
+    }
+    cosv->resize((size_t)max_len * half);
+    sinv->resize((size_t)max_len * half);
+    for (int pos = 0; pos < max_len; ++pos)
+        for (int i = 0; i < half; ++i) {
+            const float a = (float)pos * theta[i];
+            (*cosv)[(size_t)pos * half + i] = (float)std::cos((double)a);
+            (*sinv)[(size_t)pos * half + i] = (float)std::sin((double)a);
+        }
+}
+
+static int load_block(fsb_lm *lm, const fsb_tensor *w, size_t n, const std::string &p, LayerW *L) {
+    const int D = lm->D, I = lm->I, QKV = lm->QKV, wdt = lm->wdt;
+    cudaStream_t st = lm->stream;
+    FSB_TRY(upload_tensor(w, n, p + "attention.wqkv.weight", {QKV, D}, wdt, st, &L->wqkv, &lm->owned));
+    FSB_TRY(upload_tensor(w, n, p + "attention.wo.weight", {D, lm->H * lm->hd}, wdt, st, &L->wo, &lm->owned));
+    FSB_TRY(upload_tensor(w, n, p + "feed_forward.w1.weight", {I, D}, wdt, st, &L->w1, &lm->owned));
+    FSB_TRY(upload_tensor(w, n, p + "feed_forward.w2.weight", {D, I}, wdt, st, &L->w2, &lm->owned));
+    FSB_TRY(upload_tensor(w, n, p + "feed_forward.w3.weight", {I, D}, wdt, st, &L->w3, &lm->owned));
+    FSB_TRY(upload_tensor(w, n, p + "ffn_norm.weight", {D}, FSB_F32, st, &L->ffn_norm, &lm->owned));
+    FSB_TRY(upload_tensor(w, n, p + "attention_norm.weight", {D}, FSB_F32, st, &L->attn_norm, &lm->owned));
+    return FSB_OK;
+}
+
+static int lm_create_impl(fsb_lm *lm, const fsb_tensor *w, size_t n) {
+    const fsb_model_args &c = lm->cfg;
+    FSB_TRY(select_device(lm->opt.device));
+    if (lm->opt.stream) {
+        lm->stream = (cudaStream_t)lm->opt.stream;
+    } else {
+        FSB_CUDA_OK(cudaStreamCreateWithFlags(&lm->stream, cudaStreamNonBlocking));
+        lm->own_stream = true;
+    }
+    FSB_CUDA_OK(cudaEventCreate(&lm->ev0));
+    FSB_CUDA_OK(cudaEventCreate(&lm->ev1));
+    FSB_CUDA_OK(cudaEventCreate(&lm->ev2));
+    const int D = lm->D, V = lm->V, C = lm->C, CS = lm->CS, wdt = lm->wdt;
+    cudaStream_t st = lm->stream;
+    FSB_TRY(upload_tensor(w, n, "embeddings.weight", {V, D}, wdt, st, &lm->emb, &lm->owned));
+    FSB_TRY(upload_tensor(w, n, "codebook_embeddings.weight", {(int64_t)C * CS, D}, wdt, st, &lm->cb_emb, &lm->owned));
+    lm->layers.resize(lm->NL);
+    for (int l = 0; l < lm->NL; ++l) FSB_TRY(load_block(lm, w, n, "layers." + std::to_string(l) + ".", &lm->layers[l]));
+    FSB_TRY(upload_tensor(w, n, "norm.weight", {D}, FSB_F32, st, &lm->norm, &lm->owned));
+    if (c.tie_word_embeddings) lm->out_w = lm->emb;  // dual_ar.rs:486-490
+    else FSB_TRY(upload_tensor(w, n, "output.weight", {V, D}, wdt, st, &lm->out_w, &lm->owned));
+    FSB_TRY(upload_tensor(w, n, "fast_embeddings.weight", {CS, D}, wdt, st, &lm->fast_emb, &lm->owned));
+    lm->fast_layers.resize(lm->NFL);
+    for (int l = 0; l < lm->NFL; ++l)
+        FSB_TRY(load_block(lm, w, n, "fast_layers." + std::to_string(l) + ".", &lm->fast_layers[l]));
+    FSB_TRY(upload_tensor(w, n, "fast_norm.weight", {D}, FSB_F32, st, &lm->fast_norm, &lm->owned));
+    FSB_TRY(upload_tensor(w, n, "fast_output.weight", {CS, D}, wdt, st, &lm->fast_out, &lm->owned));
+
+    // RoPE tables (dual_ar.rs:168-186), built on the host exactly like the oracle
+    std::vector<float> cosv, sinv;
+    precompute_freqs(c, c.max_seq_len, &cosv, &sinv);
+    FSB_TRY(dev_alloc(lm, &lm->cosT, cosv.size()));
+    FSB_TRY(dev_alloc(lm, &lm->sinT, sinv.size()));
+    FSB_CUDA_OK(cudaMemcpyAsync(lm->cosT, cosv.data(), cosv.size() * 4, cudaMemcpyHostToDevice, st));
+    FSB_CUDA_OK(cudaMemcpyAsync(lm->sinT, sinv.data(), sinv.size() * 4, cudaMemcpyHostToDevice, st));
+    FSB_CUDA_OK(cudaStreamSynchronize(st));
+
+    const int B = lm->max_batch;
+    const size_t kv_per_layer = (size_t)B * lm->KV * lm->max_len * lm->hd;
+    FSB_TRY(dev_alloc(lm, &lm->kc, kv_per_layer * lm->NL));
+    FSB_TRY(dev_alloc(lm, &lm->vc, kv_per_layer * lm->NL));
+    const size_t fkv = (size_t)B * lm->KV * lm->fast_len * lm->hd;
+    FSB_TRY(dev_alloc(lm, &lm->fkc, fkv * lm->NFL));
+    FSB_TRY(dev_alloc(lm, &lm->fvc, fkv * lm->NFL));
+
+    Scratch &s = lm->s;
+    const int M = std::max(lm->prefill_rows, B);
+    FSB_TRY(dev_alloc(lm, &s.x, (size_t)M * D));
+    FSB_TRY(dev_alloc(lm, &s.xn, (size_t)M * D));
+    FSB_TRY(dev_alloc(lm, &s.qkv, (size_t)M * lm->QKV));
+    FSB_TRY(dev_alloc(lm, &s.q, (size_t)M * lm->H * lm->hd));
+    FSB_TRY(dev_alloc(lm, &s.att, (size_t)M * lm->H * lm->hd));
+    FSB_TRY(dev_alloc(lm, &s.g1, (size_t)M * lm->I));
+    FSB_TRY(dev_alloc(lm, &s.g3, (size_t)M * lm->I));
+    FSB_TRY(dev_alloc(lm, &s.partial, (size_t)B * lm->H * lm->nsplit * (lm->hd + 2)));
+    FSB_TRY(dev_alloc(lm, &s.logits, (size_t)B * V));
+    FSB_TRY(dev_alloc(lm, &s.slow_logits, (size_t)B * lm->n_slow_logits));
+    FSB_TRY(dev_alloc(lm, &s.hidden, (size_t)B * D));
+    FSB_TRY(dev_alloc(lm, &s.fast_x, (size_t)B * D));
+    FSB_TRY(dev_alloc(lm, &s.fast_logits, (size_t)B * CS));
+    FSB_TRY(dev_alloc(lm, &s.toks, (size_t)(C + 1) * std::max(lm->max_len, 1)));
+
+    GenState &g = lm->h_st;
+    memset(&g, 0, sizeof(g));
+    FSB_TRY(dev_alloc(lm, &g.pos, B));
+    FSB_TRY(dev_alloc(lm, &g.active, B));
+    FSB_TRY(dev_alloc(lm, &g.eos, B));
+    FSB_TRY(dev_alloc(lm, &g.frame, B));
+    FSB_TRY(dev_alloc(lm, &g.max_frames, B));
+    FSB_TRY(dev_alloc(lm, &g.n_active, 1));
+    FSB_TRY(dev_alloc(lm, &g.cur, (size_t)B * (C + 1)));
+    FSB_TRY(dev_alloc(lm, &g.prev, (size_t)B * (C + 1)));
+    g.out_cap = lm->max_len + 2;
+    FSB_TRY(dev_alloc(lm, &g.out, (size_t)B * g.out_cap * (C + 1)));
+    FSB_TRY(dev_alloc(lm, &g.rep, (size_t)B * C));
+    g.C = C;
+    g.im_end_id = lm->tok.im_end_id;
+    g.pad_id = lm->tok.pad_id;
+    FSB_TRY(dev_alloc(lm, &lm->d_st, 1));
+    FSB_CUDA_OK(cudaMemsetAsync(g.pos, 0, B * sizeof(int), st));
+    FSB_CUDA_OK(cudaMallocHost((void **)&lm->h_pin, sizeof(int) * (4 * B + 16)));
+    lm->kv_len.assign(B, 0);
+    // sampler kernels may need > 48 KB dynamic smem
+    {
+        const int sm = (int)sample_smem(std::max(lm->n_slow_logits, CS));
+        FSB_REQUIRE(std::max(lm->n_slow_logits, CS) <= 2 * kSampleMaxN, FSB_ERR_UNSUPPORTED,
+                    "constrained head of %d rows exceeds the block sampler", lm->n_slow_logits);
+        FSB_CUDA_OK(cudaFuncSetAttribute(sample_slow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+        FSB_CUDA_OK(cudaFuncSetAttribute(sample_fast_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+        FSB_CUDA_OK(
+            cudaFuncSetAttribute(sample_fast_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+    }
+    FSB_REQUIRE(std::max(lm->D, lm->I) * 32 <= 227 * 1024, FSB_ERR_UNSUPPORTED, "dim/intermediate_size too large");
+    FSB_CUDA_OK(init_gemv_attrs(std::max(lm->D, lm->I)));
+    FSB_CUDA_OK(cudaStreamSynchronize(st));
+    return FSB_OK;
+}
+
+static void lm_free(fsb_lm *lm) {
+    if (!lm) return;
+    for (auto &kv : lm->frame_graphs)
+        if (kv.first >= 0 && kv.second) cudaGraphExecDestroy(kv.second);
+    for (auto &kv : lm->tail_graphs)
+        if (kv.first >= 0 && kv.second) cudaGraphExecDestroy(kv.second);
+    for (void *p : lm->owned) cudaFree(p);
+    for (cudaEvent_t e : lm->prof_ev) cudaEventDestroy(e);
+    if (lm->h_pin) cudaFreeHost(lm->h_pin);
+    if (lm->ev0) cudaEventDestroy(lm->ev0);
+    if (lm->ev1) cudaEventDestroy(lm->ev1);
+    if (lm->ev2) cudaEventDestroy(lm->ev2);
+    if (lm->own_stream && lm->stream) cudaStreamDestroy(lm->stream);
+    delete lm;
+}
+
+static int check_handle(fsb_lm *lm) {
+    FSB_REQUIRE(lm != nullptr, FSB_ERR_INVALID, "null fsb_lm handle");
+    FSB_REQUIRE(!lm->poisoned, FSB_ERR_CUDA, "handle poisoned by an earlier sticky CUDA error");
+    cudaError_t e = cudaSetDevice(lm->opt.device);
+    if (e != cudaSuccess) {
+        set_error("cudaSetDevice(%d): %s", lm->opt.device, cudaGetErrorString(e));
+        return FSB_ERR_CUDA;
+    }
+    return FSB_OK;
+}
+
+static int finish(fsb_lm *lm, int st) {
+    if (st == FSB_ERR_CUDA) {
+        // a sticky error (illegal address, launch failure) poisons the context
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess && e != cudaErrorNotReady) lm->poisoned = true;
+        (void)cudaGetLastError();
+    }
+    return st;
+}
+
+static int upload_state(fsb_lm *lm) {
+    FSB_CUDA_OK(cudaMemcpyAsync(lm->d_st, &lm->h_st, sizeof(GenState), cudaMemcpyHostToDevice, lm->stream));
+    return FSB_OK;
+}
+
+static int sync_pos_to_device(fsb_lm *lm, int nb) {
+    for (int b = 0; b < nb; ++b) lm->h_pin[b] = lm->kv_len[b];
+    FSB_CUDA_OK(cudaMemcpyAsync(lm->h_st.pos, lm->h_pin, nb * sizeof(int), cudaMemcpyHostToDevice, lm->stream));
+    return FSB_OK;
+}
+
+// ---------------------------------------------------------------- generate
+static int generate_impl(fsb_lm *lm, const uint32_t *const *prompts, const int32_t *prompt_lens, int bsz,
+                         size_t max_new_tokens, const fsb_sampling_args *sa, uint32_t flags, int32_t fixed_len,
+                         uint32_t *const *out_codes, size_t cap, size_t *out_lens) {
+    FSB_REQUIRE(prompts && prompt_lens && sa && out_codes && out_lens, FSB_ERR_INVALID, "null argument");
+    FSB_REQUIRE(bsz >= 1 && bsz <= lm->max_batch, FSB_ERR_INVALID, "bsz %d outside [1, max_batch=%d]", bsz,
+                lm->max_batch);
+    const int C = lm->C;
+    const bool fixed = (flags & FSB_GEN_FIXED_LEN) != 0;
+    FSB_REQUIRE(!fixed || fixed_len >= 1, FSB_ERR_INVALID, "FSB_GEN_FIXED_LEN needs fixed_len >= 1");
+    if (!(flags & FSB_GEN_KEEP_SLOW_KV))
+        for (int b = 0; b < bsz; ++b) lm->kv_len[b] = 0;
+    std::vector<int> max_frames(bsz);
+    for (int b = 0; b < bsz; ++b) {
+        const int P = prompt_lens[b];
+        FSB_REQUIRE(P >= 1 && prompts[b], FSB_ERR_INVALID, "prompt %d is empty", b);
+        // Q3: `input_pos > max_new_tokens + n_cached` stops the iterator (single_batch.rs:61,77)
+        long long lim = (long long)max_new_tokens - P + 2;
+        if (lim < 1) lim = 1;
+        if (fixed) lim = std::min<long long>(lim, fixed_len);
+        FSB_REQUIRE(lm->kv_len[b] + P + lim - 1 <= lm->max_len, FSB_ERR_STATE,
+                    "row %d: %d cached + %d prompt + %lld frames exceed the KV arena (%d positions)", b, lm->kv_len[b],
+                    P, lim, lm->max_len);
+        FSB_REQUIRE(lim <= lm->h_st.out_cap, FSB_ERR_STATE, "frame budget %lld exceeds the output arena", lim);
+        max_frames[b] = (int)lim;
+    }
+    // ---- state ----
+    GenState &g = lm->h_st;
+    g.fixed_len = fixed ? 1 : 0;
+    g.legacy_slow = (lm->opt.fish_version != FSB_FISH_1_5) ? 1 : 0;
+    g.sp.greedy = sa->temp <= 1e-7 ? 1 : 0;
+    g.sp.inv_temp = g.sp.greedy ? 1.0f : (float)(1.0 / sa->temp);
+    g.sp.top_p = (float)sa->top_p;
+    g.sp.top_k = sa->top_k;
+    g.sp.penalty = sa->repetition_penalty;
+    g.sp.seed = sa->seed;
+    FSB_TRY(upload_state(lm));
+    int *hp = lm->h_pin;
+    for (int b = 0; b < bsz; ++b) {
+        hp[b] = 1;                    // active
+        hp[bsz + b] = max_frames[b];  // max_frames
+        hp[2 * bsz + b] = lm->kv_len[b] + prompt_lens[b];  // pos after prefill
+    }
+    hp[3 * bsz] = bsz;
+    cudaStream_t st = lm->stream;
+    FSB_CUDA_OK(cudaMemcpyAsync(g.active, hp, bsz * sizeof(int), cudaMemcpyHostToDevice, st));
+    FSB_CUDA_OK(cudaMemcpyAsync(g.max_frames, hp + bsz, bsz * sizeof(int), cudaMemcpyHostToDevice, st));
+    FSB_CUDA_OK(cudaMemcpyAsync(g.pos, hp + 2 * bsz, bsz * sizeof(int), cudaMemcpyHostToDevice, st));
+    FSB_CUDA_OK(cudaMemcpyAsync(g.n_active, hp + 3 * bsz, sizeof(int), cudaMemcpyHostToDevice, st));
+    FSB_CUDA_OK(cudaMemsetAsync(g.eos, 0, bsz * sizeof(int), st));
+    FSB_CUDA_OK(cudaMemsetAsync(g.frame, 0, bsz * sizeof(int), st));
+    FSB_CUDA_OK(cudaMemsetAsync(g.rep, 0, (size_t)bsz * C * sizeof(RepPenState), st));
+    FSB_CUDA_OK(cudaStreamSynchronize(st));  // h_pin is reused below
+
+    const uint64_t l0 = lm->launches;
+    uint64_t graph_l = 0;
+    // ---- prefill, row by row (independent utterances) ----
+    FSB_CUDA_OK(cudaEventRecord(lm->ev0, st));
+    for (int b = 0; b < bsz; ++b) {
+        const int P = prompt_lens[b];
+        FSB_CUDA_OK(cudaMemcpyAsync(lm->s.toks, prompts[b], (size_t)(C + 1) * P * sizeof(uint32_t),
+                                    cudaMemcpyHostToDevice, st));
+        FSB_TRY(prefill_row(lm, lm->s.toks, P, b, lm->kv_len[b], 0));
+        // prompts[b] may be pageable: the copy above is synchronous w.r.t. the host for pageable
+        // memory, and s.toks is only reused after the row's kernels are queued on the same stream.
+    }
+    {
+        cudaGraphExec_t tg;
+        FSB_TRY(get_graph(lm, lm->tail_graphs, bsz, false, &tg));
+        FSB_CUDA_OK(cudaGraphLaunch(tg, st));
+        graph_l += graph_launches(lm->tail_graphs, bsz);
+    }
+    FSB_CUDA_OK(cudaEventRecord(lm->ev1, st));
+    // ---- frame loop ----
+    int total_max = 0;
+    for (int b = 0; b < bsz; ++b) total_max = std::max(total_max, max_frames[b]);
+    cudaGraphExec_t fg;
+    FSB_TRY(get_graph(lm, lm->frame_graphs, bsz, true, &fg));
+    const uint64_t per_frame = graph_launches(lm->frame_graphs, bsz);
+    const int kPoll = 16;
+    int launched = 1;
+    if (lm->profile) {
+        // eager frames with per-launch events while the event pool lasts
+        lm->prof_used = 0;
+        lm->prof_bytes = 0;
+        while (launched < total_max && lm->prof_used + 2 * per_frame <= lm->prof_ev.size()) {
+            FSB_TRY(decode_frame(lm, bsz));
+            ++launched;
+        }
+    }
+    volatile int *flag = hp + 3 * bsz + 1;
+    *flag = bsz;
+    while (launched < total_max) {
+        const int n = std::min(kPoll, total_max - launched);
+        for (int i = 0; i < n; ++i) FSB_CUDA_OK(cudaGraphLaunch(fg, st));
+        launched += n;
+        graph_l += per_frame * n;
+        if (fixed) continue;
+        // early exit on EOS: one poll per kPoll frames (kernels no-op once n_active == 0)
+        FSB_CUDA_OK(cudaMemcpyAsync((void *)flag, g.n_active, sizeof(int), cudaMemcpyDeviceToHost, st));
+        FSB_CUDA_OK(cudaStreamSynchronize(st));
+        if (*flag == 0) break;
+    }
+    FSB_CUDA_OK(cudaEventRecord(lm->ev2, st));
+    // ---- results ----
+    std::vector<int> frames(bsz), pos(bsz);
+    FSB_CUDA_OK(cudaMemcpyAsync(hp, g.frame, bsz * sizeof(int), cudaMemcpyDeviceToHost, st));
+    FSB_CUDA_OK(cudaMemcpyAsync(hp + bsz, g.pos, bsz * sizeof(int), cudaMemcpyDeviceToHost, st));
+    FSB_CUDA_OK(cudaStreamSynchronize(st));
+    uint64_t total_frames = 0;
+    std::vector<uint32_t> host_out;
+    for (int b = 0; b < bsz; ++b) {
+        frames[b] = hp[b];
+        lm->kv_len[b] = hp[bsz + b];
+    }
+    for (int b = 0; b < bsz; ++b) {
+        const int nf = frames[b];
+        host_out.resize((size_t)nf * (C + 1));
+        FSB_CUDA_OK(cudaMemcpyAsync(host_out.data(), g.out + (size_t)b * g.out_cap * (C + 1),
+                                    host_out.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        FSB_CUDA_OK(cudaStreamSynchronize(st));
+        // generate_blocking_with_hidden: keep frame 0 always (Q4), drop later <|im_end|> frames
+        // (single_batch.rs:262-266), strip the semantic row (:280-282)
+        size_t T = 0;
+        for (int f = 0; f < nf; ++f) {
+            const uint32_t *fr = &host_out[(size_t)f * (C + 1)];
+            if (f > 0 && fr[0] == lm->tok.im_end_id) continue;
+            FSB_REQUIRE(T < cap, FSB_ERR_INVALID, "row %d: output capacity %zu too small", b, cap);
+            for (int c = 0; c < C; ++c) out_codes[b][(size_t)c * cap + T] = fr[1 + c];
+            ++T;
+        }
+        out_lens[b] = T;
+        total_frames += T;
+    }
+    float ms_pre = 0.f, ms_dec = 0.f;
+    FSB_CUDA_OK(cudaEventElapsedTime(&ms_pre, lm->ev0, lm->ev1));
+    FSB_CUDA_OK(cudaEventElapsedTime(&ms_dec, lm->ev1, lm->ev2));
+    lm->stats.prefill_ms = ms_pre;
+    lm->stats.decode_ms = ms_dec;
+    lm->stats.frames = total_frames;
+    lm->stats.kernel_launches = (lm->launches - l0) + graph_l;
+    lm->stats.dominant_kernel_ms = 0;
+    lm->stats.dominant_kernel_launches = 0;
+    lm->stats.dominant_kernel_bytes = 0;
+    if (lm->profile) {
+        double tot = 0;
+        for (size_t i = 0; i + 1 < lm->prof_used; i += 2) {
+            float ms = 0.f;
+            FSB_CUDA_OK(cudaEventElapsedTime(&ms, lm->prof_ev[i], lm->prof_ev[i + 1]));
+            tot += ms;
+        }
+        lm->stats.dominant_kernel_ms = tot;
+        lm->stats.dominant_kernel_launches = lm->prof_used / 2;
+        lm->stats.dominant_kernel_bytes = lm->prof_bytes;
+    }
+    return FSB_OK;
+}
+
+}  // namespace fsb
+
+// =================================================================== C ABI
+extern "C" {
+
+int fsb_lm_create(const fsb_model_args *args, const fsb_token_config *tok, const fsb_tensor *weights,
+                  size_t n_weights, const fsb_lm_options *opts, fsb_lm **out) {
+    FSB_REQUIRE(args && tok && weights && opts && out, FSB_ERR_INVALID, "fsb_lm_create: null argument");
+    *out = nullptr;
+    FSB_REQUIRE(!args->attention_qkv_bias, FSB_ERR_UNSUPPORTED, "attention_qkv_bias is not supported");
+    FSB_REQUIRE(args->head_dim == 64, FSB_ERR_UNSUPPORTED, "head_dim %d: kernels are specialised for 64",
+                args->head_dim);
+    FSB_REQUIRE(args->n_local_heads > 0 && args->n_head % args->n_local_heads == 0 &&
+                    args->n_head / args->n_local_heads <= kAttnMaxRep,
+                FSB_ERR_UNSUPPORTED, "n_head %d / n_local_heads %d unsupported", args->n_head, args->n_local_heads);
+    FSB_REQUIRE(args->dim % 256 == 0, FSB_ERR_UNSUPPORTED, "dim %d must be a multiple of 256", args->dim);
+    FSB_REQUIRE(args->dim == args->n_head * args->head_dim, FSB_ERR_UNSUPPORTED,
+                "dim must equal n_head * head_dim (RoPE table uses dim / n_head, dual_ar.rs:173)");
+    FSB_REQUIRE(opts->weight_dtype == FSB_F32 || opts->weight_dtype == FSB_BF16, FSB_ERR_INVALID,
+                "weight_dtype must be FSB_F32 or FSB_BF16");
+    FSB_REQUIRE(opts->max_batch >= 1, FSB_ERR_INVALID, "max_batch must be >= 1");
+    FSB_REQUIRE(args->num_codebooks >= 1 && args->num_codebooks <= 16, FSB_ERR_UNSUPPORTED, "num_codebooks");
+    FSB_REQUIRE(args->codebook_size <= 1024, FSB_ERR_UNSUPPORTED, "codebook_size > 1024 (rep-pen bitset)");
+    std::unique_ptr<fsb_lm> lm(new fsb_lm());
+    lm->cfg = *args;
+    lm->tok = *tok;
+    lm->opt = *opts;
+    lm->D = args->dim;
+    lm->I = args->intermediate_size ? args->intermediate_size : args->dim * 4;
+    FSB_REQUIRE(lm->I % 256 == 0, FSB_ERR_UNSUPPORTED, "intermediate_size must be a multiple of 256");
+    lm->H = args->n_head;
+    lm->KV = args->n_local_heads;
+    lm->hd = args->head_dim;
+    lm->V = args->vocab_size;
+    lm->C = args->num_codebooks;
+    lm->CS = args->codebook_size;
+    lm->QKV = (lm->H + 2 * lm->KV) * lm->hd;
+    lm->NL = args->n_layer;
+    lm->NFL = args->n_fast_layer;
+    lm->wdt = opts->weight_dtype;
+    lm->max_batch = opts->max_batch;
+    lm->max_len = opts->max_seq_len > 0 ? std::min(opts->max_seq_len, args->max_seq_len) : args->max_seq_len;
+    lm->fast_len = lm->C;
+    lm->prefill_rows = 1024;
+    lm->nsplit = 16;
+    FSB_REQUIRE(tok->im_end_id < (uint32_t)lm->V && tok->semantic_start_id < (uint32_t)lm->V, FSB_ERR_INVALID,
+                "token ids outside the vocabulary");
+    if (opts->fish_version == FSB_FISH_1_5) {
+        // generate/utils.rs:6-33: [im_end | semantic_start .. V)
+        lm->slow_row0 = (int)tok->im_end_id;
+        lm->slow_rest_base = (int)tok->semantic_start_id;
+        lm->n_slow_logits = 1 + (lm->V - (int)tok->semantic_start_id);
+    } else {
+        // single_batch.rs:104-124: only the <|im_end|> and PAD logits are read
+        lm->slow_row0 = (int)tok->im_end_id;
+        lm->slow_rest_base = (int)tok->pad_id;
+        lm->n_slow_logits = 2;
+    }
+    memset(&lm->stats, 0, sizeof(lm->stats));
+    int st = lm_create_impl(lm.get(), weights, n_weights);
+    if (st != FSB_OK) {
+        lm_free(lm.release());
+        (void)cudaGetLastError();
+        return st;
+    }
+    const size_t es = esize(lm->wdt);
+    const size_t per_layer = (size_t)lm->QKV * lm->D + (size_t)lm->D * lm->H * lm->hd + 3ull * lm->I * lm->D;
+    lm->stats.weight_bytes_per_frame =
+        es * (per_layer * lm->NL + (size_t)lm->n_slow_logits * lm->D +
+              (size_t)lm->C * (per_layer * lm->NFL + (size_t)lm->CS * lm->D));
+    *out = lm.release();
+    return FSB_OK;
+}
+
+int fsb_lm_destroy(fsb_lm *lm) {
+    if (!lm) return FSB_OK;
+    cudaSetDevice(lm->opt.device);
+    if (lm->stream) cudaStreamSynchronize(lm->stream);
+    lm_free(lm);
+    (void)cudaGetLastError();
+    return FSB_OK;
+}
+
+int fsb_lm_forward_generate(fsb_lm *lm, const uint32_t *inp, int32_t bsz, int32_t seq_len, size_t input_pos,
+                            float *logits, float *hidden) {
+    FSB_TRY(check_handle(lm));
+    FSB_REQUIRE(inp && bsz >= 1 && bsz <= lm->max_batch && seq_len >= 1, FSB_ERR_INVALID,
+                "forward_generate: bad arguments (bsz %d, seq_len %d)", bsz, seq_len);
+    const int C = lm->C, D = lm->D, V = lm->V;
+    cudaStream_t st = lm->stream;
+    auto body = [&]() -> int {
+        for (int b = 0; b < bsz; ++b) {
+            FSB_REQUIRE(lm->kv_len[b] + seq_len <= lm->max_len, FSB_ERR_STATE,
+                        "KV overflow: %d cached + %d new > %d", lm->kv_len[b], seq_len, lm->max_len);
+            FSB_REQUIRE(input_pos + seq_len <= (size_t)lm->cfg.max_seq_len, FSB_ERR_STATE,
+                        "input_pos %zu + %d exceeds max_seq_len", input_pos, seq_len);
+        }
+        if (seq_len == 1) {
+            FSB_CUDA_OK(cudaMemcpyAsync(lm->s.toks, inp, (size_t)bsz * (C + 1) * sizeof(uint32_t),
+                                        cudaMemcpyHostToDevice, st));
+            FSB_TRY(sync_pos_to_device(lm, bsz));
+            FSB_TRY(embed(lm, lm->s.toks, bsz, 1, lm->s.hidden, nullptr));
+            // all rows share input_pos (reference semantics); cache slot == rows cached so far
+            for (int b = 1; b < bsz; ++b)
+                FSB_REQUIRE(lm->kv_len[b] == lm->kv_len[0], FSB_ERR_STATE,
+                            "step API needs equal KV lengths across rows");
+            const int delta = (int)input_pos - lm->kv_len[0];
+            for (int l = 0; l < lm->NL; ++l)
+                FSB_TRY(decode_layer(lm, lm->layers[l], lm->s.hidden, bsz, slow_k(lm, l), slow_v(lm, l), lm->max_len,
+                                     lm->h_st.pos, 0, delta, nullptr, lm->nsplit));
+        } else {
+            for (int b = 0; b < bsz; ++b) {
+                FSB_CUDA_OK(cudaMemcpyAsync(lm->s.toks, inp + (size_t)b * (C + 1) * seq_len,
+                                            (size_t)(C + 1) * seq_len * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+                FSB_TRY(prefill_row(lm, lm->s.toks, seq_len, b, lm->kv_len[b], (int)input_pos - lm->kv_len[b]));
+            }
+        }
+        for (int b = 0; b < bsz; ++b) lm->kv_len[b] += seq_len;
+        if (logits) {
+            FSB_TRY(launch_gemv<EPI_STORE>(lm, lm->out_w, nullptr, lm->s.hidden, D, (const float *)lm->norm.ptr,
+                                           nullptr, lm->s.logits, V, V, D, bsz, nullptr));
+            FSB_CUDA_OK(cudaMemcpyAsync(logits, lm->s.logits, (size_t)bsz * V * sizeof(float),
+                                        cudaMemcpyDeviceToHost, st));
+        }
+        if (hidden)
+            FSB_CUDA_OK(cudaMemcpyAsync(hidden, lm->s.hidden, (size_t)bsz * D * sizeof(float),
+                                        cudaMemcpyDeviceToHost, st));
+        FSB_CUDA_OK(cudaStreamSynchronize(st));
+        return FSB_OK;
+    };
+    return finish(lm, body());
+}
+
+int fsb_lm_forward_generate_fast(fsb_lm *lm, const float *x, int32_t bsz, size_t input_pos, float *logits) {
+    FSB_TRY(check_handle(lm));
+    FSB_REQUIRE(x && logits && bsz >= 1 && bsz <= lm->max_batch, FSB_ERR_INVALID, "forward_generate_fast: bad args");
+    FSB_REQUIRE(input_pos < (size_t)lm->fast_len, FSB_ERR_STATE, "fast input_pos %zu >= num_codebooks %d", input_pos,
+                lm->fast_len);
+    cudaStream_t st = lm->stream;
+    auto body = [&]() -> int {
+        FSB_CUDA_OK(cudaMemcpyAsync(lm->s.fast_x, x, (size_t)bsz * lm->D * sizeof(float), cudaMemcpyHostToDevice, st));
+        for (int l = 0; l < lm->NFL; ++l)
+            FSB_TRY(decode_layer(lm, lm->fast_layers[l], lm->s.fast_x, bsz, fast_k(lm, l), fast_v(lm, l),
+                                 lm->fast_len, nullptr, (int)input_pos, 0, nullptr, 1));
+        FSB_TRY(launch_gemv<EPI_STORE>(lm, lm->fast_out, nullptr, lm->s.fast_x, lm->D,
+                                       (const float *)lm->fast_norm.ptr, nullptr, lm->s.fast_logits, lm->CS, lm->CS,
+                                       lm->D, bsz, nullptr));
+        FSB_CUDA_OK(cudaMemcpyAsync(logits, lm->s.fast_logits, (size_t)bsz * lm->CS * sizeof(float),
+                                    cudaMemcpyDeviceToHost, st));
+        FSB_CUDA_OK(cudaStreamSynchronize(st));
+        return FSB_OK;
+    };
+    return finish(lm, body());
+}
+
+int fsb_lm_fast_embeddings(fsb_lm *lm, const uint32_t *ids, int32_t n, float *out) {
+    FSB_TRY(check_handle(lm));
+    FSB_REQUIRE(ids && out && n >= 1, FSB_ERR_INVALID, "fast_embeddings: bad args");
+    const int D = lm->D;
+    const size_t es = esize(lm->wdt);
+    std::vector<uint8_t> row(D * es);
+    for (int i = 0; i < n; ++i) {
+        FSB_REQUIRE(ids[i] < (uint32_t)lm->CS, FSB_ERR_INVALID, "fast_embeddings: id %u out of range", ids[i]);
+        FSB_CUDA_OK(cudaMemcpy(row.data(), (const uint8_t *)lm->fast_emb.ptr + (size_t)ids[i] * D * es, D * es,
+                               cudaMemcpyDeviceToHost));
+        for (int d = 0; d < D; ++d) {
+            if (lm->wdt == FSB_F32) {
+                out[(size_t)i * D + d] = reinterpret_cast<const float *>(row.data())[d];
+            } else {
+                uint32_t u = (uint32_t)reinterpret_cast<const uint16_t *>(row.data())[d] << 16;
+                float f;
+                memcpy(&f, &u, 4);
+                out[(size_t)i * D + d] = f;
+            }
+        }
+    }
+    return FSB_OK;
+}
+
+int fsb_lm_clear_fast_layer_caches(fsb_lm *lm) {
+    FSB_TRY(check_handle(lm));
+    return FSB_OK;  // fast KV slots are addressed by codebook index and always rewritten in order
+}
+int fsb_lm_clear_slow_layer_caches(fsb_lm *lm) {
+    FSB_TRY(check_handle(lm));
+    std::fill(lm->kv_len.begin(), lm->kv_len.end(), 0);
+    return FSB_OK;
+}
+int fsb_lm_clear_slow_caches_until(fsb_lm *lm, size_t pos) {
+    FSB_TRY(check_handle(lm));
+    for (auto &v : lm->kv_len) v = (int)std::min<size_t>((size_t)v, pos);  // dual_ar.rs:392-404: truncate
+    return FSB_OK;
+}
+int fsb_lm_curr_kv_size(fsb_lm *lm, size_t *out) {
+    FSB_TRY(check_handle(lm));
+    FSB_REQUIRE(out, FSB_ERR_INVALID, "null out");
+    *out = (size_t)lm->kv_len[0];
+    return FSB_OK;
+}
+
+int fsb_lm_generate_blocking(fsb_lm *lm, const uint32_t *prompt, int32_t prompt_len, size_t max_new_tokens,
+                             const fsb_sampling_args *sampling, uint32_t flags, int32_t fixed_len,
+                             uint32_t *out_codes, size_t cap, size_t *out_len) {
+    FSB_TRY(check_handle(lm));
+    const uint32_t *prompts[1] = {prompt};
+    uint32_t *outs[1] = {out_codes};
+    return finish(lm, generate_impl(lm, prompts, &prompt_len, 1, max_new_tokens, sampling, flags, fixed_len, outs, cap,
+                                    out_len));
+}
+
+int fsb_lm_generate_static_batch(fsb_lm *lm, const uint32_t *const *prompts, const int32_t *prompt_lens,
+                                 int32_t bsz, size_t max_new_tokens, const fsb_sampling_args *sampling,
+                                 uint32_t flags, int32_t fixed_len, uint32_t *const *out_codes, size_t cap,
+                                 size_t *out_lens) {
+    FSB_TRY(check_handle(lm));
+    return finish(lm, generate_impl(lm, prompts, prompt_lens, bsz, max_new_tokens, sampling, flags, fixed_len,
+                                    out_codes, cap, out_lens));
+}
+
+int fsb_lm_set_profile(fsb_lm *lm, int on) {
+    FSB_TRY(check_handle(lm));
+    lm->profile = on != 0;
+    if (lm->profile && lm->prof_ev.empty()) {
+        lm->prof_ev.resize(2 * 4096);
+        for (auto &e : lm->prof_ev) FSB_CUDA_OK(cudaEventCreate(&e));
+    }
+    return FSB_OK;
+}
+
+int fsb_lm_get_stats(fsb_lm *lm, fsb_lm_stats *out) {
+    FSB_REQUIRE(lm && out, FSB_ERR_INVALID, "null argument");
+    *out = lm->stats;
+    return FSB_OK;
+}
+
+// ---------------------------------------------------------------- operator level
+int fsb_op_repeat_kv(const void *src_dev, void *dst_dev, int32_t dtype, int32_t n_local_heads, int32_t n_rep,
+                     int32_t seqlen, int32_t head_dim, void *stream) {
+    FSB_REQUIRE(src_dev && dst_dev, FSB_ERR_INVALID, "repeat_kv: null pointer");
+    FSB_REQUIRE(n_local_heads > 0 && n_rep > 0 && seqlen > 0 && head_dim > 0, FSB_ERR_INVALID, "repeat_kv: bad dims");
+    cudaStream_t st = (cudaStream_t)stream;
+    dim3 grid(seqlen, n_local_heads);
+    const int threads = std::min(256, ((head_dim + 31) / 32) * 32);
+    switch (dtype) {
+        case FSB_F32:
+        case FSB_U32:
+            repeat_kv_kernel<uint32_t><<<grid, threads, 0, st>>>((const uint32_t *)src_dev, (uint32_t *)dst_dev, n_rep,
+                                                                 seqlen, head_dim);
+            break;
+        case FSB_BF16:
+        case FSB_F16:
+            repeat_kv_kernel<uint16_t><<<grid, threads, 0, st>>>((const uint16_t *)src_dev, (uint16_t *)dst_dev, n_rep,
+                                                                 seqlen, head_dim);
+            break;
+        case FSB_I64:
+        case FSB_F64:
+            repeat_kv_kernel<uint64_t><<<grid, threads, 0, st>>>((const uint64_t *)src_dev, (uint64_t *)dst_dev, n_rep,
+                                                                 seqlen, head_dim);
+            break;
+        case FSB_U8:
+            repeat_kv_kernel<uint8_t><<<grid, threads, 0, st>>>((const uint8_t *)src_dev, (uint8_t *)dst_dev, n_rep,
+                                                                seqlen, head_dim);
+            break;
+        default:
+            set_error("repeat_kv: unsupported dtype %d", dtype);
+            return FSB_ERR_INVALID;
+    }
+    FSB_CUDA_OK(cudaGetLastError());
+    return FSB_OK;
+}
+
+size_t fsb_op_gqa_decode_attn_scratch_bytes(int32_t bsz, int32_t n_head, int32_t head_dim) {
+    return (size_t)bsz * n_head * 16 * (head_dim + 2) * sizeof(float) + (size_t)bsz * n_head * head_dim * sizeof(float);
+}
+
+int fsb_op_gqa_decode_attn(const float *qkv_dev, float *kcache_dev, float *vcache_dev, const float *cos_dev,
+                           const float *sin_dev, const int32_t *pos_dev, int32_t bsz, int32_t n_head,
+                           int32_t n_local_heads, int32_t head_dim, int32_t max_len, float *out_dev,
+                           void *scratch_dev, size_t scratch_bytes, void *stream) {
+    FSB_REQUIRE(qkv_dev && kcache_dev && vcache_dev && cos_dev && sin_dev && pos_dev && out_dev && scratch_dev,
+                FSB_ERR_INVALID, "gqa_decode_attn: null pointer");
+    FSB_REQUIRE(head_dim == 64, FSB_ERR_UNSUPPORTED, "gqa_decode_attn: head_dim must be 64");
+    FSB_REQUIRE(n_local_heads > 0 && n_head % n_local_heads == 0 && n_head / n_local_heads <= kAttnMaxRep,
+                FSB_ERR_UNSUPPORTED, "gqa_decode_attn: unsupported head configuration");
+    FSB_REQUIRE(scratch_bytes >= fsb_op_gqa_decode_attn_scratch_bytes(bsz, n_head, head_dim), FSB_ERR_INVALID,
+                "gqa_decode_attn: scratch too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nsplit = 16, n_rep = n_head / n_local_heads;
+    float *partial = (float *)scratch_dev;
+    float *q = partial + (size_t)bsz * n_head * nsplit * (head_dim + 2);
+    rope_append_kernel<<<bsz, 256, 0, st>>>(qkv_dev, q, kcache_dev, vcache_dev, cos_dev, sin_dev, pos_dev, 0, 0,
+                                            n_head, n_local_heads, head_dim, max_len, nullptr);
+    attn_decode_split_kernel<<<dim3(nsplit, n_local_heads, bsz), n_rep * 32, n_rep * head_dim * sizeof(float), st>>>(
+        q, kcache_dev, vcache_dev, pos_dev, 0, n_head, n_local_heads, head_dim, max_len,
+        1.0f / sqrtf((float)head_dim), partial, nullptr);
+    attn_decode_combine_kernel<<<bsz * n_head, head_dim, 0, st>>>(partial, nsplit, head_dim, out_dev, nullptr);
+    FSB_CUDA_OK(cudaGetLastError());
+    return FSB_OK;
+}
+
+}  // extern "C"

@@ -9,20 +9,26 @@ namespace fsb {
 
 // Device-resident state of the frame loop (single_batch.rs:19-28 fields that the
 // reference keeps on the host: input_pos, previous_codes, prompt/None, rep-pen).
+// The struct itself lives in device memory so that a captured frame graph stays
+// valid across generate calls; kernels read it through a pointer.
 struct GenState {
     int *pos;            // (B) cached positions == position of the next token
     int *active;         // (B) 1 while the row still generates
     int *eos;            // (B) slow token of the current frame was <|im_end|>
     int *frame;          // (B) frames emitted so far
+    int *max_frames;     // (B) frame budget of the row (Q3 / fixed_len)
     int *n_active;       // (1) rows still active; kernels no-op when 0
     uint32_t *cur;       // (B, C+1) codes of the frame being built
     uint32_t *prev;      // (B, C+1) codes of the previous frame (previous_codes)
-    uint32_t *out;       // (B, max_frames, C+1) every emitted frame
+    uint32_t *out;       // (B, out_cap, C+1) every emitted frame
     RepPenState *rep;    // (B, C)
-    int max_frames;
-    int fixed_len;       // FSB_GEN_FIXED_LEN
+    int out_cap;
+    int fixed_len;       // FSB_GEN_FIXED_LEN: <|im_end|> not eligible
+    int legacy_slow;     // Fish <= 1.4: slow token is a 2-way PAD/EOS draw (single_batch.rs:104-124)
     int C;
     uint32_t im_end_id;
+    uint32_t pad_id;
+    SampleParams sp;
 };
 
 // ------------------------------------------------------------------ embed
@@ -485,11 +491,13 @@ __global__ void attn_prefill_kernel(const float *__restrict__ q, const float *__
 // ------------------------------------------------------------------ samplers
 // Slow head: constrained logits (generate/utils.rs:6-33) -> token (utils.rs:36-56),
 // EOS bookkeeping (single_batch.rs:153-156,199-204).  grid B, block 1024.
-// logits (B, ld) holds rows [im_end | semantic_start ..) i.e. n = V' entries.
+// logits (B, ld) holds rows [im_end | semantic_start ..) i.e. n = V' entries
+// (Fish <= 1.4: the two rows [im_end, pad], sampling/mod.rs:8-26).
 __global__ void __launch_bounds__(kSampleThreads) sample_slow_kernel(const float *__restrict__ logits, int ld, int n,
-                                                                      SampleParams sp, GenState st,
+                                                                      const GenState *__restrict__ stp,
                                                                       uint32_t sem_start, const float *hidden,
                                                                       float *fast_x, int D) {
+    const GenState st = *stp;
     if (*st.n_active == 0) return;
     const int b = blockIdx.x;
     if (!st.active[b]) return;
@@ -499,16 +507,26 @@ __global__ void __launch_bounds__(kSampleThreads) sample_slow_kernel(const float
     unsigned long long *keys = reinterpret_cast<unsigned long long *>(smem_raw);
     float *vals = reinterpret_cast<float *>(keys + n_pad);
     float *red = vals + n_pad;
-    for (int i = threadIdx.x; i < n; i += kSampleThreads) {
-        float v = logits[(size_t)b * ld + i];
-        if (i == 0 && st.fixed_len) v = -INFINITY;
-        vals[i] = v;
-    }
-    __syncthreads();
     const int frame = st.frame[b];
-    const float u = philox_uniform(sp.seed, (uint64_t)frame * (st.C + 1), (uint32_t)b);
-    const int idx = block_sample(vals, keys, red, n, n_pad, sp, u);
-    const uint32_t tok = (idx == 0) ? st.im_end_id : (sem_start + (uint32_t)idx - 1);
+    const float u = philox_uniform(st.sp.seed, (uint64_t)frame * (st.C + 1), (uint32_t)b);
+    uint32_t tok;
+    if (st.legacy_slow) {
+        // legacy_softmax_sample(pad, eos): thread_rng replaced by the Philox draw
+        const float eos_l = logits[(size_t)b * ld + 0], pad_l = logits[(size_t)b * ld + 1];
+        const float mx = fmaxf(pad_l, eos_l);
+        const float e_pad = expf(pad_l - mx), e_eos = expf(eos_l - mx);
+        const float p_pad = e_pad / (e_pad + e_eos);
+        tok = (st.fixed_len || u < p_pad) ? st.pad_id : st.im_end_id;
+    } else {
+        for (int i = threadIdx.x; i < n; i += kSampleThreads) {
+            float v = logits[(size_t)b * ld + i];
+            if (i == 0 && st.fixed_len) v = -INFINITY;
+            vals[i] = v;
+        }
+        __syncthreads();
+        const int idx = block_sample(vals, keys, red, n, n_pad, st.sp, u);
+        tok = (idx == 0) ? st.im_end_id : (sem_start + (uint32_t)idx - 1);
+    }
     const bool eos = (tok == st.im_end_id);
     if (threadIdx.x == 0) {
         st.cur[b * (st.C + 1)] = tok;
@@ -525,9 +543,10 @@ __global__ void __launch_bounds__(kSampleThreads) sample_slow_kernel(const float
 // bookkeeping (:193-204).  grid B, block 1024.
 template <typename WT>
 __global__ void __launch_bounds__(kSampleThreads) sample_fast_kernel(const float *__restrict__ logits, int n, int cb,
-                                                                      SampleParams sp, GenState st,
+                                                                      const GenState *__restrict__ stp,
                                                                       const WT *__restrict__ fast_emb,
                                                                       float *fast_x, int D) {
+    const GenState st = *stp;
     if (*st.n_active == 0) return;
     const int b = blockIdx.x;
     if (!st.active[b]) return;
@@ -548,12 +567,12 @@ __global__ void __launch_bounds__(kSampleThreads) sample_fast_kernel(const float
         }
         for (int i = threadIdx.x; i < n; i += kSampleThreads) {
             float v = logits[(size_t)b * n + i];
-            if (frame > 0 && ((rp->seen[i >> 5] >> (i & 31)) & 1u)) v = __fdiv_rn(v, sp.penalty);
+            if (frame > 0 && ((rp->seen[i >> 5] >> (i & 31)) & 1u)) v = __fdiv_rn(v, st.sp.penalty);
             vals[i] = v;
         }
         __syncthreads();
-        const float u = philox_uniform(sp.seed, (uint64_t)frame * (C + 1) + cb + 1, (uint32_t)b);
-        const int a = block_sample(vals, keys, red, n, n_pad, sp, u);
+        const float u = philox_uniform(st.sp.seed, (uint64_t)frame * (C + 1) + cb + 1, (uint32_t)b);
+        const int a = block_sample(vals, keys, red, n, n_pad, st.sp, u);
         if (threadIdx.x == 0) st.cur[b * (C + 1) + 1 + cb] = (uint32_t)a;
         if (cb != C - 1)
             for (int d = threadIdx.x; d < D; d += kSampleThreads)
@@ -562,7 +581,7 @@ __global__ void __launch_bounds__(kSampleThreads) sample_fast_kernel(const float
     if (cb == C - 1) {
         __syncthreads();
         if (threadIdx.x == 0) {
-            uint32_t *o = st.out + ((size_t)b * st.max_frames + frame) * (C + 1);
+            uint32_t *o = st.out + ((size_t)b * st.out_cap + frame) * (C + 1);
             for (int c = 0; c <= C; ++c) {
                 const uint32_t v = st.cur[b * (C + 1) + c];
                 o[c] = v;
@@ -570,18 +589,15 @@ __global__ void __launch_bounds__(kSampleThreads) sample_fast_kernel(const float
             }
             const int nf = frame + 1;
             st.frame[b] = nf;
-            if (eos || nf >= st.max_frames) {
+            // the slow step that consumed the previous frame appended one KV row
+            // (input_pos bookkeeping, single_batch.rs:193-197); prefill sets pos itself
+            if (frame > 0) st.pos[b] += 1;
+            if (eos || nf >= st.max_frames[b]) {
                 st.active[b] = 0;
                 atomicSub(st.n_active, 1);
             }
         }
     }
-}
-
-// pos[b] += 1 for rows that are still active (input_pos bookkeeping, single_batch.rs:193-197).
-__global__ void advance_pos_kernel(GenState st, int B) {
-    const int b = threadIdx.x;
-    if (b < B && st.active[b]) st.pos[b] += 1;
 }
 
 // repeat_kv (candle-gqa-kernels/src/unary.cu:8-58) for callers that still want the copy.

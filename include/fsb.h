@@ -122,6 +122,7 @@ typedef struct fsb_lm_stats {
     double dominant_kernel_ms; /* summed device time of the weight-streaming kernel(s), when FSB_PROFILE=1 */
     uint64_t dominant_kernel_launches;
     uint64_t weight_bytes_per_frame; /* algorithmic bytes one decode frame must stream */
+    uint64_t dominant_kernel_bytes;  /* algorithmic weight bytes the profiled launches streamed */
 } fsb_lm_stats;
 
 typedef struct fsb_lm fsb_lm;
@@ -177,6 +178,11 @@ int fsb_lm_generate_static_batch(fsb_lm *lm, const uint32_t *const *prompts, con
                                  size_t *out_lens);
 
 int fsb_lm_get_stats(fsb_lm *lm, fsb_lm_stats *out);
+/* Profiling switch (the reference's only instrumentation is Instant + println!, single_batch.rs:233-303).
+ * on != 0: generate calls run the frame loop eagerly and bracket every launch of the dominant
+ * (weight-streaming) kernel with CUDA events on the handle's stream, for the first frames of the call;
+ * the sums land in fsb_lm_stats.dominant_kernel_{ms,launches,bytes}.  Off by default (graphs). */
+int fsb_lm_set_profile(fsb_lm *lm, int on);
 
 /* ---- FireflyCodec (fish_speech_core/lib/codec/firefly.rs) --------------- */
 
@@ -189,7 +195,8 @@ typedef struct fsb_codec_options {
 } fsb_codec_options;
 
 typedef struct fsb_codec_stats {
-    double decode_ms;
+    double decode_ms;          /* last decode call, host copies included */
+    double device_ms;          /* same call, kernels only (CUDA events on the handle's stream) */
     uint64_t kernel_launches;
     double dominant_kernel_ms; /* ResBlock conv kernels, when FSB_PROFILE=1 */
     uint64_t dominant_kernel_launches;

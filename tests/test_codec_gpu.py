@@ -1,0 +1,83 @@
+"""GPU parity tests of the Firefly codec against the oracle, through the C ABI.
+Tolerance: PCM max-abs 1e-4 on the tanh-bounded output, fp32 both sides."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from fish_speech_rs_b200 import FireflyCodec
+from fish_speech_rs_b200._ffi import FsbError
+from oracle import codec as ocodec
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+PCM_ATOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def codec(codec_weights):
+    c = FireflyCodec(codec_weights, max_frames=300, with_encoder=True)
+    yield c
+    c.close()
+
+
+@pytest.mark.parametrize("T", [1, 2, 5, 33])
+def test_decode_matches_oracle(codec, codec_weights, T):
+    rng = np.random.default_rng(7 + T)
+    codes = rng.integers(0, 1000, size=(1, 8, T)).astype(np.uint32)
+    with torch.no_grad():
+        exp = ocodec.decode(torch.from_numpy(codes.astype(np.int64)), codec_weights).numpy()
+    got = codec.decode(codes)
+    assert got.shape == (1, 1, 2048 * T)
+    assert np.abs(exp).max() > 0.05 and np.abs(exp).max() < 0.999  # signal present, tanh not saturated
+    err = np.abs(got - exp).max()
+    assert err <= PCM_ATOL, f"max abs PCM error {err}"
+
+
+def test_decode_default_voice_prefix(codec, codec_weights):
+    """Real Fish-1.5 codes (voices-template/default.npy) as vocoder input."""
+    v = np.load(os.path.join(GOLDEN, "default_voice.npy"))[:, :48]
+    with torch.no_grad():
+        exp = ocodec.decode(torch.from_numpy(v)[None], codec_weights).numpy()
+    got = codec.decode(v[None].astype(np.uint32))
+    assert np.abs(got - exp).max() <= PCM_ATOL
+
+
+def test_decode_is_causal_and_chunk_consistent(codec):
+    """Full-size property: decode(codes[:k]) == decode(codes)[:2048 k] (strictly causal stack)."""
+    rng = np.random.default_rng(1)
+    codes = rng.integers(0, 1000, size=(1, 8, 216)).astype(np.uint32)
+    full = codec.decode(codes)
+    part = codec.decode(codes[:, :, :100])
+    np.testing.assert_array_equal(part, full[:, :, : 2048 * 100])
+
+
+def test_decode_batch_equals_single(codec):
+    rng = np.random.default_rng(2)
+    cs = [rng.integers(0, 1000, size=(8, T)).astype(np.uint32) for T in (3, 9, 1)]
+    outs = codec.decode_batch(cs)
+    for c, o in zip(cs, outs):
+        np.testing.assert_array_equal(o, codec.decode(c[None]))
+
+
+def test_invalid_codes_rejected(codec):
+    codes = np.full((1, 8, 4), 1000, np.uint32)  # Q11
+    with pytest.raises(FsbError) as e:
+        codec.decode(codes)
+    assert e.value.status == -1
+    with pytest.raises(FsbError):
+        codec.decode(np.zeros((1, 8, 301), np.uint32))  # > max_frames
+
+
+@pytest.mark.parametrize("Lm", [16, 37, 203])
+def test_encode_mel_matches_oracle(codec, codec_weights, Lm):
+    rng = np.random.default_rng(Lm)
+    mel = (rng.standard_normal((1, 160, Lm)) * 2.0 - 4.0).astype(np.float32)  # log-mel-like range
+    with torch.no_grad():
+        exp = ocodec.encode_mel(torch.from_numpy(mel), codec_weights).numpy()
+    got = codec.encode_mel(mel)
+    assert got.shape == exp.shape == (1, 8, ((Lm - 2) // 2 + 1 - 2) // 2 + 1)
+    # integer indices: exact except where a pre-round value sits within float noise of .5
+    mism = (got != exp).mean()
+    assert mism <= 0.002, f"{mism:.4f} of the indices differ"
