@@ -306,7 +306,12 @@ def main():
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     ap.add_argument("--cpu-sample-frames", type=int, default=16)
+    ap.add_argument("--frames", type=int, default=0, help="override the frame count (profiling runs only)")
     a = ap.parse_args()
+    if a.frames:
+        for c in CONFIGS.values():
+            c["frames"] = a.frames
+            c["desc"] += f" [frames overridden to {a.frames}: NOT the benchmark workload]"
     if a.impl == "reference":
         return run_reference(a)
     world = int(os.environ.get("WORLD_SIZE", "1"))
