@@ -7,6 +7,7 @@
 #include <memory>
 
 #include "fsb_lm_kernels.cuh"
+#include "fsb_lm_mega_params.cuh"
 
 namespace fsb {
 
@@ -60,6 +61,15 @@ struct fsb_lm {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
     fsb_lm_stats stats;
     uint64_t launches = 0;
+    // persistent megakernel (decode_mode 2)
+    MegaParams mp;
+    bool mega_ok = false;
+    int mega_grid = 0;
+    MegaLayer *d_mega_slow = nullptr, *d_mega_fast = nullptr;
+    float *mega_partial = nullptr, *mega_logits = nullptr;
+    unsigned int *mega_bar = nullptr;
+    unsigned long long *mega_dbg = nullptr;
+    cudaEvent_t prof_m0 = nullptr, prof_m1 = nullptr;
     // profile mode: event pairs around the weight-streaming kernel
     bool profile = false;
     std::vector<cudaEvent_t> prof_ev;
@@ -375,6 +385,109 @@ static uint64_t graph_launches(std::map<int, cudaGraphExec_t> &cache, int nb) {
     return (uint64_t)(uintptr_t)cache[-nb - 1];
 }
 
+// ---------------------------------------------------------------- megakernel host side
+static int mega_nb_template(int nb) { return nb <= 1 ? 1 : nb <= 2 ? 2 : nb <= 4 ? 4 : 8; }
+
+static size_t mega_smem_bytes(const fsb_lm *lm, int NB, int *xs_floats, int *val_floats) {
+    const int G = lm->mega_grid;
+    const int NE = lm->wdt == FSB_F32 ? 4 : 8;
+    const int maxK = std::max(std::max(lm->D, lm->I), lm->H * lm->hd);
+    int n_pad = 1;
+    while (n_pad < std::max(lm->n_slow_logits, lm->CS)) n_pad <<= 1;
+    const int samp_floats = (n_pad * 12 + 1024) / 4;
+    *xs_floats = (std::max(NB * maxK, samp_floats) + 3) & ~3;
+    auto tasks = [&](int rows, int K, int mats) {
+        const int upr = K / (32 * NE), ksplit = (upr + kMegaPre - 1) / kMegaPre;
+        return ((rows + G - 1) / G + 2) * ksplit * mats;
+    };
+    int nt = tasks(lm->QKV, lm->D, 1);
+    nt = std::max(nt, tasks(lm->D, lm->H * lm->hd, 1));
+    nt = std::max(nt, tasks(lm->I, lm->D, 2));
+    nt = std::max(nt, tasks(lm->D, lm->I, 1));
+    nt = std::max(nt, tasks(lm->n_slow_logits, lm->D, 1));
+    nt = std::max(nt, tasks(lm->CS, lm->D, 1));
+    *val_floats = (nt * NB + 3) & ~3;
+    return ((size_t)*xs_floats + (size_t)*val_floats + 64 * NB + 2ull * kMegaChunk * kMegaKvStride) * sizeof(float);
+}
+
+static int mega_launch(fsb_lm *lm, int nb, int nframes, bool first_is_tail) {
+    MegaParams mp = lm->mp;
+    mp.nb = nb;
+    mp.nframes = nframes;
+    mp.first_is_tail = first_is_tail ? 1 : 0;
+    const int NB = mega_nb_template(nb);
+    int xs_floats = 0, val_floats = 0;
+    const size_t smem = mega_smem_bytes(lm, NB, &xs_floats, &val_floats);
+    mp.xs_floats = xs_floats;
+    mp.val_floats = val_floats;
+    mp.st = lm->h_st;
+    FSB_CUDA_OK(cudaMemsetAsync(lm->mega_bar, 0, sizeof(unsigned int), lm->stream));
+    FSB_CUDA_OK(lm->wdt == FSB_F32 ? mega_launch_f32(NB, mp, lm->mega_grid, smem, lm->stream)
+                                   : mega_launch_bf16(NB, mp, lm->mega_grid, smem, lm->stream));
+    lm->launches++;
+    return FSB_OK;
+}
+
+static int mega_setup(fsb_lm *lm) {
+    cudaDeviceProp prop;
+    FSB_CUDA_OK(cudaGetDeviceProperties(&prop, lm->opt.device));
+    lm->mega_grid = prop.multiProcessorCount;
+    int coop = 0;
+    FSB_CUDA_OK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, lm->opt.device));
+    auto split_ok = [&](int K) {
+        const int upr = K / (32 * (lm->wdt == FSB_F32 ? 4 : 8)), ksplit = (upr + kMegaPre - 1) / kMegaPre;
+        return upr >= 1 && upr % ksplit == 0;
+    };
+    const int upr_ok = (lm->D % 256 == 0) && (lm->I % 256 == 0) && (lm->hd == 64) && (lm->QKV % 2 == 0) &&
+                       split_ok(lm->D) && split_ok(lm->I) && split_ok(lm->H * lm->hd);
+    int xs_floats, val_floats;
+    const size_t smem8 = mega_smem_bytes(lm, 8, &xs_floats, &val_floats);
+    lm->mega_ok = coop && upr_ok && lm->C <= 8 && smem8 <= (size_t)prop.sharedMemPerBlockOptin && lm->H / lm->KV <= 8;
+    if (!lm->mega_ok) return FSB_OK;
+    std::vector<MegaLayer> hs(lm->NL), hf(lm->NFL);
+    auto fill = [](const LayerW &L, MegaLayer *m) {
+        m->wqkv = L.wqkv.ptr; m->wo = L.wo.ptr; m->w1 = L.w1.ptr; m->w3 = L.w3.ptr; m->w2 = L.w2.ptr;
+        m->attn_norm = (const float *)L.attn_norm.ptr; m->ffn_norm = (const float *)L.ffn_norm.ptr;
+    };
+    for (int l = 0; l < lm->NL; ++l) fill(lm->layers[l], &hs[l]);
+    for (int l = 0; l < lm->NFL; ++l) fill(lm->fast_layers[l], &hf[l]);
+    FSB_TRY(dev_alloc(lm, &lm->d_mega_slow, lm->NL));
+    FSB_TRY(dev_alloc(lm, &lm->d_mega_fast, lm->NFL));
+    FSB_CUDA_OK(cudaMemcpy(lm->d_mega_slow, hs.data(), hs.size() * sizeof(MegaLayer), cudaMemcpyHostToDevice));
+    FSB_CUDA_OK(cudaMemcpy(lm->d_mega_fast, hf.data(), hf.size() * sizeof(MegaLayer), cudaMemcpyHostToDevice));
+    const int B = lm->max_batch;
+    const int ldl = std::max(lm->n_slow_logits, lm->CS);
+    const int n_chunks_max = (lm->max_len + kMegaChunk - 1) / kMegaChunk;
+    FSB_TRY(dev_alloc(lm, &lm->mega_partial, (size_t)B * lm->H * 2 * n_chunks_max * (lm->hd + 4)));
+    FSB_TRY(dev_alloc(lm, &lm->mega_logits, (size_t)B * ldl));
+    FSB_TRY(dev_alloc(lm, &lm->mega_bar, 1));
+    if (getenv("FSB_MEGA_TIMERS")) {
+        FSB_TRY(dev_alloc(lm, &lm->mega_dbg, 64));
+        FSB_CUDA_OK(cudaMemset(lm->mega_dbg, 0, 64 * sizeof(unsigned long long)));
+    }
+    MegaParams &m = lm->mp;
+    memset(&m, 0, sizeof(m));
+    m.slow = lm->d_mega_slow; m.fast = lm->d_mega_fast;
+    m.NL = lm->NL; m.NFL = lm->NFL; m.D = lm->D; m.I = lm->I; m.H = lm->H; m.KV = lm->KV; m.hd = lm->hd;
+    m.QKV = lm->QKV; m.C = lm->C; m.CS = lm->CS;
+    m.n_slow_logits = lm->n_slow_logits; m.slow_row0 = lm->slow_row0; m.slow_rest_base = lm->slow_rest_base;
+    m.emb = lm->emb.ptr; m.cb_emb = lm->cb_emb.ptr; m.out_w = lm->out_w.ptr; m.fast_emb = lm->fast_emb.ptr;
+    m.fast_out = lm->fast_out.ptr;
+    m.norm = (const float *)lm->norm.ptr; m.fast_norm = (const float *)lm->fast_norm.ptr;
+    m.eps = lm->cfg.norm_eps;
+    m.kc = lm->kc; m.vc = lm->vc; m.fkc = lm->fkc; m.fvc = lm->fvc;
+    m.max_len = lm->max_len; m.fast_len = lm->fast_len; m.max_batch = lm->max_batch;
+    m.cosT = lm->cosT; m.sinT = lm->sinT;
+    m.x = lm->s.hidden; m.fx = lm->s.fast_x; m.q = lm->s.q; m.partial = lm->mega_partial; m.h = lm->s.g1;
+    m.logits = lm->mega_logits; m.ldl = ldl;
+    m.n_chunks_max = n_chunks_max;
+    m.bar = lm->mega_bar; m.dbg = lm->mega_dbg;
+    m.sem_start = lm->tok.semantic_start_id; m.sem_end = lm->tok.semantic_end_id; m.has_end = lm->tok.has_semantic_end;
+    FSB_CUDA_OK(cudaEventCreate(&lm->prof_m0));
+    FSB_CUDA_OK(cudaEventCreate(&lm->prof_m1));
+    return FSB_OK;
+}
+
 static void precompute_freqs(const fsb_model_args &c, int max_len, std::vector<float> *cosv, std::vector<float> *sinv) {
     // dual_ar.rs:168-186: theta_i = 1 / base^(i/n) in f32, idx_theta = pos * theta (f32 product), cos/sin.
     // Transcendentals in f64 rounded once to f32 (== correctly rounded f32), as in oracle/dual_ar.py.
@@ -503,6 +616,7 @@ static int lm_create_impl(fsb_lm *lm, const fsb_tensor *w, size_t n) {
     }
     FSB_REQUIRE(std::max(lm->D, lm->I) * 32 <= 227 * 1024, FSB_ERR_UNSUPPORTED, "dim/intermediate_size too large");
     FSB_CUDA_OK(init_gemv_attrs(std::max(lm->D, lm->I)));
+    FSB_TRY(mega_setup(lm));
     FSB_CUDA_OK(cudaStreamSynchronize(st));
     return FSB_OK;
 }
@@ -519,6 +633,8 @@ static void lm_free(fsb_lm *lm) {
     if (lm->ev0) cudaEventDestroy(lm->ev0);
     if (lm->ev1) cudaEventDestroy(lm->ev1);
     if (lm->ev2) cudaEventDestroy(lm->ev2);
+    if (lm->prof_m0) cudaEventDestroy(lm->prof_m0);
+    if (lm->prof_m1) cudaEventDestroy(lm->prof_m1);
     if (lm->own_stream && lm->stream) cudaStreamDestroy(lm->stream);
     delete lm;
 }
@@ -621,42 +737,53 @@ static int generate_impl(fsb_lm *lm, const uint32_t *const *prompts, const int32
         // prompts[b] may be pageable: the copy above is synchronous w.r.t. the host for pageable
         // memory, and s.toks is only reused after the row's kernels are queued on the same stream.
     }
-    {
-        cudaGraphExec_t tg;
-        FSB_TRY(get_graph(lm, lm->tail_graphs, bsz, false, &tg));
-        FSB_CUDA_OK(cudaGraphLaunch(tg, st));
-        graph_l += graph_launches(lm->tail_graphs, bsz);
-    }
-    FSB_CUDA_OK(cudaEventRecord(lm->ev1, st));
-    // ---- frame loop ----
     int total_max = 0;
     for (int b = 0; b < bsz; ++b) total_max = std::max(total_max, max_frames[b]);
-    cudaGraphExec_t fg;
-    FSB_TRY(get_graph(lm, lm->frame_graphs, bsz, true, &fg));
-    const uint64_t per_frame = graph_launches(lm->frame_graphs, bsz);
-    const int kPoll = 16;
-    int launched = 1;
-    if (lm->profile) {
-        // eager frames with per-launch events while the event pool lasts
-        lm->prof_used = 0;
-        lm->prof_bytes = 0;
-        while (launched < total_max && lm->prof_used + 2 * per_frame <= lm->prof_ev.size()) {
-            FSB_TRY(decode_frame(lm, bsz));
-            ++launched;
+    const bool use_mega = lm->mega_ok && bsz <= 8 && lm->opt.decode_mode != 1 && !lm->profile;
+    FSB_REQUIRE(use_mega || lm->opt.decode_mode != 2 || lm->profile, FSB_ERR_UNSUPPORTED,
+                "decode_mode 2 (megakernel) needs bsz <= 8 and cooperative launch support");
+    if (use_mega) {
+        // frame 0 = tail on the prefilled hidden state, then whole frames; the kernel leaves its
+        // loop by itself once every row is finished (no host polling).  The prefill event sits
+        // right before the launch, so frame 0's tail is accounted to the frame loop here.
+        FSB_CUDA_OK(cudaEventRecord(lm->ev1, st));
+        FSB_TRY(mega_launch(lm, bsz, total_max, true));
+    } else {
+        {
+            cudaGraphExec_t tg;
+            FSB_TRY(get_graph(lm, lm->tail_graphs, bsz, false, &tg));
+            FSB_CUDA_OK(cudaGraphLaunch(tg, st));
+            graph_l += graph_launches(lm->tail_graphs, bsz);
         }
-    }
-    volatile int *flag = hp + 3 * bsz + 1;
-    *flag = bsz;
-    while (launched < total_max) {
-        const int n = std::min(kPoll, total_max - launched);
-        for (int i = 0; i < n; ++i) FSB_CUDA_OK(cudaGraphLaunch(fg, st));
-        launched += n;
-        graph_l += per_frame * n;
-        if (fixed) continue;
-        // early exit on EOS: one poll per kPoll frames (kernels no-op once n_active == 0)
-        FSB_CUDA_OK(cudaMemcpyAsync((void *)flag, g.n_active, sizeof(int), cudaMemcpyDeviceToHost, st));
-        FSB_CUDA_OK(cudaStreamSynchronize(st));
-        if (*flag == 0) break;
+        FSB_CUDA_OK(cudaEventRecord(lm->ev1, st));
+        // ---- frame loop ----
+        cudaGraphExec_t fg;
+        FSB_TRY(get_graph(lm, lm->frame_graphs, bsz, true, &fg));
+        const uint64_t per_frame = graph_launches(lm->frame_graphs, bsz);
+        const int kPoll = 16;
+        int launched = 1;
+        if (lm->profile) {
+            // eager frames with per-launch events while the event pool lasts
+            lm->prof_used = 0;
+            lm->prof_bytes = 0;
+            while (launched < total_max && lm->prof_used + 2 * per_frame <= lm->prof_ev.size()) {
+                FSB_TRY(decode_frame(lm, bsz));
+                ++launched;
+            }
+        }
+        volatile int *flag = hp + 3 * bsz + 1;
+        *flag = bsz;
+        while (launched < total_max) {
+            const int n = std::min(kPoll, total_max - launched);
+            for (int i = 0; i < n; ++i) FSB_CUDA_OK(cudaGraphLaunch(fg, st));
+            launched += n;
+            graph_l += per_frame * n;
+            if (fixed) continue;
+            // early exit on EOS: one poll per kPoll frames (kernels no-op once n_active == 0)
+            FSB_CUDA_OK(cudaMemcpyAsync((void *)flag, g.n_active, sizeof(int), cudaMemcpyDeviceToHost, st));
+            FSB_CUDA_OK(cudaStreamSynchronize(st));
+            if (*flag == 0) break;
+        }
     }
     FSB_CUDA_OK(cudaEventRecord(lm->ev2, st));
     // ---- results ----
@@ -699,6 +826,37 @@ static int generate_impl(fsb_lm *lm, const uint32_t *const *prompts, const int32
     lm->stats.dominant_kernel_ms = 0;
     lm->stats.dominant_kernel_launches = 0;
     lm->stats.dominant_kernel_bytes = 0;
+    if (use_mega && lm->mega_dbg) {
+        unsigned long long h[64];
+        FSB_CUDA_OK(cudaMemcpy(h, lm->mega_dbg, sizeof(h), cudaMemcpyDeviceToHost));
+        FSB_CUDA_OK(cudaMemset(lm->mega_dbg, 0, sizeof(h)));
+        static const char *kn[7] = {"qkv", "attn", "wo", "w13", "w2", "head", "sample"};
+        for (int c = 0; c < 2; ++c)
+            for (int k = 0; k < 7; ++k)
+                if (h[c * 32 + k * 3 + 2])
+                    fprintf(stderr, "[mega cta %s] %-6s n=%6llu work %8.2f us/phase  barrier %8.2f us/phase\n",
+                            c ? "last" : "0", kn[k], h[c * 32 + k * 3 + 2],
+                            h[c * 32 + k * 3] / 1e3 / h[c * 32 + k * 3 + 2], h[c * 32 + k * 3 + 1] / 1e3 / h[c * 32 + k * 3 + 2]);
+    }
+    if (use_mega) {
+        // the single persistent launch IS the frame loop: algorithmic bytes = weights streamed per
+        // executed frame (frame 0 runs no slow stack) + the KV rows attention had to read
+        const size_t es = esize(lm->wdt);
+        const size_t per_layer = (size_t)lm->QKV * lm->D + (size_t)lm->D * lm->H * lm->hd + 3ull * lm->I * lm->D;
+        const uint64_t w_slow = es * (per_layer * lm->NL);
+        const uint64_t w_tail = es * ((size_t)lm->n_slow_logits * lm->D +
+                                      (size_t)lm->C * (per_layer * lm->NFL + (size_t)lm->CS * lm->D));
+        int fmax = 0;
+        uint64_t kv_bytes = 0;
+        for (int b = 0; b < bsz; ++b) {
+            fmax = std::max(fmax, frames[b]);
+            for (int f = 1; f < frames[b]; ++f)
+                kv_bytes += (uint64_t)(lm->kv_len[b] - (frames[b] - 1) + f) * lm->NL * 2 * lm->KV * lm->hd * sizeof(float);
+        }
+        lm->stats.dominant_kernel_ms = ms_dec;
+        lm->stats.dominant_kernel_launches = 1;
+        lm->stats.dominant_kernel_bytes = (uint64_t)fmax * w_tail + (uint64_t)std::max(fmax - 1, 0) * w_slow + kv_bytes;
+    }
     if (lm->profile) {
         double tot = 0;
         for (size_t i = 0; i + 1 < lm->prof_used; i += 2) {

@@ -7,30 +7,6 @@
 
 namespace fsb {
 
-// Device-resident state of the frame loop (single_batch.rs:19-28 fields that the
-// reference keeps on the host: input_pos, previous_codes, prompt/None, rep-pen).
-// The struct itself lives in device memory so that a captured frame graph stays
-// valid across generate calls; kernels read it through a pointer.
-struct GenState {
-    int *pos;            // (B) cached positions == position of the next token
-    int *active;         // (B) 1 while the row still generates
-    int *eos;            // (B) slow token of the current frame was <|im_end|>
-    int *frame;          // (B) frames emitted so far
-    int *max_frames;     // (B) frame budget of the row (Q3 / fixed_len)
-    int *n_active;       // (1) rows still active; kernels no-op when 0
-    uint32_t *cur;       // (B, C+1) codes of the frame being built
-    uint32_t *prev;      // (B, C+1) codes of the previous frame (previous_codes)
-    uint32_t *out;       // (B, out_cap, C+1) every emitted frame
-    RepPenState *rep;    // (B, C)
-    int out_cap;
-    int fixed_len;       // FSB_GEN_FIXED_LEN: <|im_end|> not eligible
-    int legacy_slow;     // Fish <= 1.4: slow token is a 2-way PAD/EOS draw (single_batch.rs:104-124)
-    int C;
-    uint32_t im_end_id;
-    uint32_t pad_id;
-    SampleParams sp;
-};
-
 // ------------------------------------------------------------------ embed
 // DualARTransformer::embed, :532-567.  toks(b, c, s) = toks[(b*(C+1) + c)*S + s].
 template <typename WT>
@@ -518,7 +494,7 @@ __global__ void __launch_bounds__(kSampleThreads) sample_slow_kernel(const float
         const float p_pad = e_pad / (e_pad + e_eos);
         tok = (st.fixed_len || u < p_pad) ? st.pad_id : st.im_end_id;
     } else {
-        for (int i = threadIdx.x; i < n; i += kSampleThreads) {
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
             float v = logits[(size_t)b * ld + i];
             if (i == 0 && st.fixed_len) v = -INFINITY;
             vals[i] = v;
@@ -535,7 +511,7 @@ __global__ void __launch_bounds__(kSampleThreads) sample_slow_kernel(const float
             for (int c = 0; c < st.C; ++c) st.cur[b * (st.C + 1) + 1 + c] = 0;
     }
     // fast stack input = pre-norm hidden (Q1, :629-634)
-    for (int d = threadIdx.x; d < D; d += kSampleThreads) fast_x[(size_t)b * D + d] = hidden[(size_t)b * D + d];
+    for (int d = threadIdx.x; d < D; d += blockDim.x) fast_x[(size_t)b * D + d] = hidden[(size_t)b * D + d];
 }
 
 // Fast head for codebook `cb`: rep-pen (from the 2nd frame, single_batch.rs:162-168)
@@ -565,7 +541,7 @@ __global__ void __launch_bounds__(kSampleThreads) sample_fast_kernel(const float
             if (threadIdx.x == 0) rep_pen_update(rp, st.prev[b * (C + 1) + 1 + cb]);
             __syncthreads();
         }
-        for (int i = threadIdx.x; i < n; i += kSampleThreads) {
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
             float v = logits[(size_t)b * n + i];
             if (frame > 0 && ((rp->seen[i >> 5] >> (i & 31)) & 1u)) v = __fdiv_rn(v, st.sp.penalty);
             vals[i] = v;
@@ -575,7 +551,7 @@ __global__ void __launch_bounds__(kSampleThreads) sample_fast_kernel(const float
         const int a = block_sample(vals, keys, red, n, n_pad, st.sp, u);
         if (threadIdx.x == 0) st.cur[b * (C + 1) + 1 + cb] = (uint32_t)a;
         if (cb != C - 1)
-            for (int d = threadIdx.x; d < D; d += kSampleThreads)
+            for (int d = threadIdx.x; d < D; d += blockDim.x)
                 fast_x[(size_t)b * D + d] = to_f32(fast_emb[(size_t)a * D + d]);
     }
     if (cb == C - 1) {

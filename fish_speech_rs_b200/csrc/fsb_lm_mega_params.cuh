@@ -1,0 +1,51 @@
+// Parameters of the persistent decode megakernel (fsb_lm_mega.cuh) shared with the host code.
+#pragma once
+#include "fsb_common.cuh"
+#include "fsb_sample.cuh"
+
+namespace fsb {
+
+constexpr int kMegaThreads = 512;
+constexpr int kMegaWarps = kMegaThreads / 32;
+constexpr int kMegaPre = 4;        // 16-byte weight loads per lane kept in flight across a grid barrier (one task)
+constexpr int kMegaChunk = 128;    // cached positions one attention work item covers (staged in shared memory)
+constexpr int kMegaKvStride = 80;  // floats per staged K/V row (64 + pad: conflict-free LDS.128 for 8 rows at once)
+
+struct MegaLayer {
+    const void *wqkv, *wo, *w1, *w3, *w2;
+    const float *attn_norm, *ffn_norm;
+};
+
+struct MegaParams {
+    const MegaLayer *slow, *fast;
+    int NL, NFL, D, I, H, KV, hd, QKV, C, CS;
+    int n_slow_logits, slow_row0, slow_rest_base;
+    const void *emb, *cb_emb, *out_w, *fast_emb, *fast_out;
+    const float *norm, *fast_norm;
+    float eps;
+    float *kc, *vc, *fkc, *fvc;
+    int max_len, fast_len, max_batch;
+    const float *cosT, *sinT;
+    float *x;        // (B, D) slow residual stream == pre-norm hidden
+    float *fx;       // (B, D) fast residual stream
+    float *q;        // (B, H*hd) roped q
+    float *partial;  // (B, H, 2*n_chunks_max, hd+4): o[hd], m, l, pad (16-byte aligned slots)
+    int n_chunks_max;  // ceil(max_len / kMegaChunk)
+    float *h;        // (B, I)
+    float *logits;   // (B, ldl)
+    int ldl;
+    GenState st;  // by value: every field is launch-constant (the arrays it points to are not)
+    unsigned int *bar;
+    int nb, nframes, first_is_tail;
+    uint32_t sem_start, sem_end;
+    int has_end;
+    int val_floats;  // capacity of the per-task result array (floats)
+    int xs_floats;   // capacity of the activation staging area (floats)
+    unsigned long long *dbg;  // optional (FSB_MEGA_TIMERS=1): per phase kind {work ns, barrier ns, count} of CTA 0 and the last CTA
+};
+
+// Launchers, one translation unit per weight dtype (fsb_lm_mega_{bf16,f32}.cu).  NB in {1,2,4,8}.
+cudaError_t mega_launch_bf16(int NB, const MegaParams &mp, int grid, size_t smem, cudaStream_t st);
+cudaError_t mega_launch_f32(int NB, const MegaParams &mp, int grid, size_t smem, cudaStream_t st);
+
+}  // namespace fsb

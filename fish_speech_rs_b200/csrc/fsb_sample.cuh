@@ -59,16 +59,20 @@ struct SampleParams {
 constexpr int kSampleThreads = 1024;
 constexpr int kSampleMaxN = 4096;
 
-// Block-wide sampler.  `vals` (smem, n_pad floats) holds the adjusted logits;
-// returns the chosen index to every thread.  keys: smem n_pad u64.
-__device__ int block_sample(float *vals, unsigned long long *keys, float *red, int n, int n_pad,
-                            const SampleParams &sp, float u) {
-    const int tid = threadIdx.x;
-    const int lane = tid & 31, warp = tid >> 5;
+// Block-wide sampler (any block size that is a multiple of 32).  `vals` (smem, n_pad floats)
+// holds the adjusted logits; returns the chosen index to every thread.  keys: smem n_pad u64.
+// top-k -> top-p -> multinomial as in sampling/mod.rs:51-75,113-132; the running sums over the
+// sorted candidates are evaluated as a 32-lane segmented scan (each lane sums a contiguous
+// segment sequentially, lane totals are combined by a warp scan) instead of one sequential f32
+// chain: same distribution, differs from a sequential sum only in the last bits of the CDF.
+__device__ inline int block_sample(float *vals, unsigned long long *keys, float *red, int n, int n_pad,
+                                   const SampleParams &sp, float u) {
+    const int tid = threadIdx.x, nthreads = blockDim.x;
+    const int lane = tid & 31, warp = tid >> 5, nwarps = nthreads >> 5;
     // ---- max (and first argmax) ----
     float best = -INFINITY;
     int best_i = 0x7fffffff;
-    for (int i = tid; i < n; i += kSampleThreads) {
+    for (int i = tid; i < n; i += nthreads) {
         float v = vals[i];
         if (v > best || (v == best && i < best_i)) { best = v; best_i = i; }
     }
@@ -82,7 +86,8 @@ __device__ int block_sample(float *vals, unsigned long long *keys, float *red, i
     if (lane == 0) { red[warp] = best; red_i[warp] = best_i; }
     __syncthreads();
     if (warp == 0) {
-        best = red[lane]; best_i = red_i[lane];
+        best = lane < nwarps ? red[lane] : -INFINITY;
+        best_i = lane < nwarps ? red_i[lane] : 0x7fffffff;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             float ov = __shfl_xor_sync(0xffffffffu, best, o);
@@ -99,7 +104,7 @@ __device__ int block_sample(float *vals, unsigned long long *keys, float *red, i
     // ---- softmax(logits * inv_temp) ----
     const float mx = __fmul_rn(best, sp.inv_temp);
     float s = 0.f;
-    for (int i = tid; i < n; i += kSampleThreads) {
+    for (int i = tid; i < n; i += nthreads) {
         float e = expf(__fsub_rn(__fmul_rn(vals[i], sp.inv_temp), mx));
         vals[i] = e;
         s += e;
@@ -108,14 +113,14 @@ __device__ int block_sample(float *vals, unsigned long long *keys, float *red, i
     if (lane == 0) red[warp] = s;
     __syncthreads();
     if (warp == 0) {
-        float t = red[lane];
+        float t = lane < nwarps ? red[lane] : 0.f;
         t = warp_sum(t);
         if (lane == 0) red[0] = t;
     }
     __syncthreads();
     const float denom = red[0];
     // keys: (~prob bits) << 32 | index, ascending sort == prob desc, index asc
-    for (int i = tid; i < n_pad; i += kSampleThreads) {
+    for (int i = tid; i < n_pad; i += nthreads) {
         unsigned long long k = ~0ull;
         if (i < n) {
             float p = vals[i] / denom;
@@ -126,7 +131,7 @@ __device__ int block_sample(float *vals, unsigned long long *keys, float *red, i
     __syncthreads();
     for (int k = 2; k <= n_pad; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = tid; i < n_pad; i += kSampleThreads) {
+            for (int i = tid; i < n_pad; i += nthreads) {
                 int ixj = i ^ j;
                 if (ixj > i) {
                     unsigned long long a = keys[i], b = keys[ixj];
@@ -137,40 +142,94 @@ __device__ int block_sample(float *vals, unsigned long long *keys, float *red, i
             __syncthreads();
         }
     }
-    // ---- top-k -> top-p -> multinomial, sequential f32 like the reference ----
-    if (tid == 0) {
+    // ---- top-k -> top-p -> multinomial on warp 0 ----
+    if (warp == 0) {
+        auto wgt = [&](int i) { return __uint_as_float(~(uint32_t)(keys[i] >> 32)); };
         const int k = (sp.top_k >= (uint32_t)n) ? n : (int)sp.top_k;
-        float sum_p = 0.f;
-        for (int i = 0; i < k; ++i) sum_p += __uint_as_float(~(uint32_t)(keys[i] >> 32));
+        const int seg = (k + 31) / 32;
+        const int i0 = min(k, lane * seg), i1 = min(k, i0 + seg);
+        float local = 0.f;
+        for (int i = i0; i < i1; ++i) local += wgt(i);
+        float incl = local;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const float t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+        if (lane == 0) excl = 0.f;
+        const float sum_p = __shfl_sync(0xffffffffu, incl, 31);
         int kept = k;
         float total = sum_p;
         const bool do_topp = !(sp.top_p <= 0.f || sp.top_p >= sum_p) || (sp.top_k >= (uint32_t)n);
         if (do_topp) {
-            float cumsum = 0.f;
-            kept = 0;
-            for (int i = 0; i < k; ++i) {
-                if (cumsum >= sp.top_p) break;
-                cumsum += __uint_as_float(~(uint32_t)(keys[i] >> 32));
-                kept = i + 1;
+            // an entry survives iff the running sum BEFORE it is still below top_p (mod.rs:119-129)
+            int kl = 0;
+            float tl = 0.f, c = excl;
+            for (int i = i0; i < i1; ++i) {
+                const bool keep = c < sp.top_p;
+                c += wgt(i);
+                if (keep) { kl = i + 1; tl = c; }
             }
-            total = cumsum;  // == sequential sum of the kept weights
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const int ok = __shfl_xor_sync(0xffffffffu, kl, o);
+                const float ot = __shfl_xor_sync(0xffffffffu, tl, o);
+                if (ok > kl) { kl = ok; tl = ot; }
+            }
+            kept = kl;
+            total = tl;
         }
+        // WeightedIndex (rand 0.8.5): first i with cum[i] > u * total
         const float chosen = u * total;
-        float cum = 0.f;
-        int pick = kept - 1;
-        for (int i = 0; i < kept; ++i) {
-            float w = __uint_as_float(~(uint32_t)(keys[i] >> 32));
-            cum += w;
-            if (cum > chosen && w > 0.f) { pick = i; break; }
+        int cand = 0x7fffffff;
+        {
+            float c = excl;
+            for (int i = i0; i < min(i1, kept); ++i) {
+                const float w = wgt(i);
+                c += w;
+                if (c > chosen && w > 0.f) { cand = i; break; }
+            }
         }
-        // last kept entry with non-zero weight if nothing crossed `chosen`
-        while (pick > 0 && __uint_as_float(~(uint32_t)(keys[pick] >> 32)) <= 0.f) --pick;
-        red_i[0] = (int)(keys[pick] & 0xffffffffu);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) cand = min(cand, __shfl_xor_sync(0xffffffffu, cand, o));
+        if (lane == 0) {
+            int pick = cand;
+            if (pick == 0x7fffffff) {  // nothing crossed `chosen`: last kept entry with non-zero weight
+                pick = max(kept - 1, 0);
+                while (pick > 0 && wgt(pick) <= 0.f) --pick;
+            }
+            red_i[0] = (int)(keys[pick] & 0xffffffffu);
+        }
     }
     __syncthreads();
     int r = red_i[0];
     __syncthreads();
     return r;
 }
+
+// Device-resident state of the frame loop (single_batch.rs:19-28 fields that the
+// reference keeps on the host: input_pos, previous_codes, prompt/None, rep-pen).
+// The struct itself lives in device memory so that a captured frame graph stays
+// valid across generate calls; kernels read it through a pointer.
+struct GenState {
+    int *pos;            // (B) cached positions == position of the next token
+    int *active;         // (B) 1 while the row still generates
+    int *eos;            // (B) slow token of the current frame was <|im_end|>
+    int *frame;          // (B) frames emitted so far
+    int *max_frames;     // (B) frame budget of the row (Q3 / fixed_len)
+    int *n_active;       // (1) rows still active; kernels no-op when 0
+    uint32_t *cur;       // (B, C+1) codes of the frame being built
+    uint32_t *prev;      // (B, C+1) codes of the previous frame (previous_codes)
+    uint32_t *out;       // (B, out_cap, C+1) every emitted frame
+    RepPenState *rep;    // (B, C)
+    int out_cap;
+    int fixed_len;       // FSB_GEN_FIXED_LEN: <|im_end|> not eligible
+    int legacy_slow;     // Fish <= 1.4: slow token is a 2-way PAD/EOS draw (single_batch.rs:104-124)
+    int C;
+    uint32_t im_end_id;
+    uint32_t pad_id;
+    SampleParams sp;
+};
 
 }  // namespace fsb

@@ -36,7 +36,9 @@ class DualARTransformer:
     """`DualARTransformer::load(vb, cfg, token_config, model_type)` + methods."""
 
     def __init__(self, weights: Dict[str, "object"], cfg: Dict, token_config: Dict, fish_version: str = "1.5",
-                 device: int = 0, dtype: str = "f32", max_batch: int = 1, max_seq_len: int = 0, stream: int = 0):
+                 device: int = 0, dtype: str = "f32", max_batch: int = 1, max_seq_len: int = 0, stream: int = 0,
+                 decode_mode: int = 0):
+        """decode_mode: 0 auto, 1 per-op kernels replayed from a CUDA graph, 2 persistent megakernel."""
         self.cfg = dict(cfg)
         self.token_config = dict(token_config)
         self.model_type = fish_version
@@ -49,7 +51,7 @@ class DualARTransformer:
         tok = F.fsb_token_config(token_config["im_end_id"], token_config["pad_id"], token_config["semantic_start_id"],
                                  0 if end is None else end, 0 if end is None else 1)
         opts = F.fsb_lm_options(device, stream or None, {"f32": F.FSB_F32, "bf16": F.FSB_BF16}[dtype], max_batch,
-                                max_seq_len, _VERSIONS[fish_version], 0)
+                                max_seq_len, _VERSIONS[fish_version], decode_mode)
         table, keep = F.tensor_table(weights)
         h = C.c_void_p()
         F.check(F.lib().fsb_lm_create(C.byref(args), C.byref(tok), table, len(weights), C.byref(opts), C.byref(h)))

@@ -146,6 +146,24 @@ def test_static_batch_is_independent_rows(models):
         np.testing.assert_array_equal(g.astype(np.int64), e.numpy())
 
 
+@pytest.mark.parametrize("mode", [1, 2])
+def test_decode_modes_agree_with_oracle(tiny_lm, mode):
+    """decode_mode 1 (per-op kernels + CUDA graph) and 2 (persistent megakernel) both match the oracle,
+    greedy and sampled, single row and ragged batch."""
+    cfg, tok, w = tiny_lm
+    gpu = DualARTransformer(w, cfg, tok, max_batch=3, max_seq_len=256, decode_mode=mode)
+    ora = oracle_model(cfg, tok, w)
+    prompts = [synth.make_prompt(cfg, tok, P, seed=50 + i) for i, P in enumerate((30, 17, 44))]
+    for sa, so in ((SamplingArgs(temp=0.0), osamp.SamplingArgs(temp=0.0)),
+                   (SamplingArgs(0.7, 0.8, 256, 1.4, seed=5), osamp.SamplingArgs(0.7, 0.8, 256, 1.4, seed=5))):
+        got = generate_static_batch(gpu, prompts, 400, sa, fixed_len=9)
+        with torch.no_grad():
+            exp = ogen.generate_independent_batch(ora, [t64(p) for p in prompts], 400, so, fixed_len=9)
+        for g, e in zip(got, exp):
+            np.testing.assert_array_equal(g.astype(np.int64), e.numpy())
+    gpu.close()
+
+
 def test_bf16_weights_mode(tiny_lm):
     """weight_dtype bf16: weights stored bf16, fp32 math == oracle run on bf16-rounded weights."""
     cfg, tok, _ = tiny_lm
