@@ -313,7 +313,7 @@ static int slow_head(fsb_lm *lm, int nb, const int *n_active) {
 static size_t sample_smem(int n) {
     int n_pad = 1;
     while (n_pad < n) n_pad <<= 1;
-    return (size_t)n_pad * 12 + 64 * 4 * 2;
+    return (size_t)2 * std::max(n_pad, kSampleThreads) * 8 + (size_t)n_pad * 4 + 64 * 4 * 2;
 }
 
 // slow sample + C fast steps + frame bookkeeping (single_batch.rs:126-204)
@@ -394,7 +394,7 @@ static size_t mega_smem_bytes(const fsb_lm *lm, int NB, int *xs_floats, int *val
     const int maxK = std::max(std::max(lm->D, lm->I), lm->H * lm->hd);
     int n_pad = 1;
     while (n_pad < std::max(lm->n_slow_logits, lm->CS)) n_pad <<= 1;
-    const int samp_floats = (n_pad * 12 + 1024) / 4;
+    const int samp_floats = (2 * std::max(n_pad, kMegaThreads) * 8 + n_pad * 4 + 1024) / 4;
     *xs_floats = (std::max(NB * maxK, samp_floats) + 3) & ~3;
     auto tasks = [&](int rows, int K, int mats) {
         const int upr = K / (32 * NE), ksplit = (upr + kMegaPre - 1) / kMegaPre;
@@ -407,7 +407,10 @@ static size_t mega_smem_bytes(const fsb_lm *lm, int NB, int *xs_floats, int *val
     nt = std::max(nt, tasks(lm->n_slow_logits, lm->D, 1));
     nt = std::max(nt, tasks(lm->CS, lm->D, 1));
     *val_floats = (nt * NB + 3) & ~3;
-    return ((size_t)*xs_floats + (size_t)*val_floats + 64 * NB + 2ull * kMegaChunk * kMegaKvStride) * sizeof(float);
+    // red | rope rows (slow, fast) | positions | sampler state (flags, cur/prev, rep-pen windows)
+    const size_t aux = 64 * NB + NB * 64 + 8 * 64 + 4 * ((NB + 3) / 4) + 4 * NB + 2 * 20 * NB +
+                       (sizeof(RepPenState) / 4) * NB * 8 + 8;
+    return ((size_t)*xs_floats + (size_t)*val_floats + aux + 2ull * kMegaChunk * kMegaKvStride) * sizeof(float);
 }
 
 static int mega_launch(fsb_lm *lm, int nb, int nframes, bool first_is_tail) {
@@ -441,8 +444,8 @@ static int mega_setup(fsb_lm *lm) {
     const int upr_ok = (lm->D % 256 == 0) && (lm->I % 256 == 0) && (lm->hd == 64) && (lm->QKV % 2 == 0) &&
                        split_ok(lm->D) && split_ok(lm->I) && split_ok(lm->H * lm->hd);
     int xs_floats, val_floats;
-    const size_t smem8 = mega_smem_bytes(lm, 8, &xs_floats, &val_floats);
-    lm->mega_ok = coop && upr_ok && lm->C <= 8 && smem8 <= (size_t)prop.sharedMemPerBlockOptin && lm->H / lm->KV <= 8;
+    const size_t smem8 = mega_smem_bytes(lm, 1, &xs_floats, &val_floats);  // per-batch check happens at launch
+    lm->mega_ok = coop && upr_ok && lm->C <= 8 && std::max(lm->D, lm->I) >= 2 * lm->H * lm->hd && smem8 <= (size_t)prop.sharedMemPerBlockOptin && lm->H / lm->KV <= 8;
     if (!lm->mega_ok) return FSB_OK;
     std::vector<MegaLayer> hs(lm->NL), hf(lm->NFL);
     auto fill = [](const LayerW &L, MegaLayer *m) {
@@ -462,8 +465,8 @@ static int mega_setup(fsb_lm *lm) {
     FSB_TRY(dev_alloc(lm, &lm->mega_logits, (size_t)B * ldl));
     FSB_TRY(dev_alloc(lm, &lm->mega_bar, 1));
     if (getenv("FSB_MEGA_TIMERS")) {
-        FSB_TRY(dev_alloc(lm, &lm->mega_dbg, 64));
-        FSB_CUDA_OK(cudaMemset(lm->mega_dbg, 0, 64 * sizeof(unsigned long long)));
+        FSB_TRY(dev_alloc(lm, &lm->mega_dbg, 128));
+        FSB_CUDA_OK(cudaMemset(lm->mega_dbg, 0, 128 * sizeof(unsigned long long)));
     }
     MegaParams &m = lm->mp;
     memset(&m, 0, sizeof(m));
@@ -607,7 +610,7 @@ static int lm_create_impl(fsb_lm *lm, const fsb_tensor *w, size_t n) {
     // sampler kernels may need > 48 KB dynamic smem
     {
         const int sm = (int)sample_smem(std::max(lm->n_slow_logits, CS));
-        FSB_REQUIRE(std::max(lm->n_slow_logits, CS) <= 2 * kSampleMaxN, FSB_ERR_UNSUPPORTED,
+        FSB_REQUIRE(std::max(lm->n_slow_logits, CS) <= kSampleMaxN, FSB_ERR_UNSUPPORTED,
                     "constrained head of %d rows exceeds the block sampler", lm->n_slow_logits);
         FSB_CUDA_OK(cudaFuncSetAttribute(sample_slow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
         FSB_CUDA_OK(cudaFuncSetAttribute(sample_fast_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
@@ -739,7 +742,13 @@ static int generate_impl(fsb_lm *lm, const uint32_t *const *prompts, const int32
     }
     int total_max = 0;
     for (int b = 0; b < bsz; ++b) total_max = std::max(total_max, max_frames[b]);
-    const bool use_mega = lm->mega_ok && bsz <= 8 && lm->opt.decode_mode != 1 && !lm->profile;
+    bool use_mega = lm->mega_ok && bsz <= 8 && lm->opt.decode_mode != 1 && !lm->profile;
+    if (use_mega) {
+        int xf, vf;
+        cudaDeviceProp prop;
+        FSB_CUDA_OK(cudaGetDeviceProperties(&prop, lm->opt.device));
+        use_mega = mega_smem_bytes(lm, mega_nb_template(bsz), &xf, &vf) <= (size_t)prop.sharedMemPerBlockOptin;
+    }
     FSB_REQUIRE(use_mega || lm->opt.decode_mode != 2 || lm->profile, FSB_ERR_UNSUPPORTED,
                 "decode_mode 2 (megakernel) needs bsz <= 8 and cooperative launch support");
     if (use_mega) {
@@ -827,16 +836,22 @@ static int generate_impl(fsb_lm *lm, const uint32_t *const *prompts, const int32
     lm->stats.dominant_kernel_launches = 0;
     lm->stats.dominant_kernel_bytes = 0;
     if (use_mega && lm->mega_dbg) {
-        unsigned long long h[64];
+        unsigned long long h[128];
         FSB_CUDA_OK(cudaMemcpy(h, lm->mega_dbg, sizeof(h), cudaMemcpyDeviceToHost));
         FSB_CUDA_OK(cudaMemset(lm->mega_dbg, 0, sizeof(h)));
         static const char *kn[7] = {"qkv", "attn", "wo", "w13", "w2", "head", "sample"};
         for (int c = 0; c < 2; ++c)
-            for (int k = 0; k < 7; ++k)
-                if (h[c * 32 + k * 3 + 2])
-                    fprintf(stderr, "[mega cta %s] %-6s n=%6llu work %8.2f us/phase  barrier %8.2f us/phase\n",
-                            c ? "last" : "0", kn[k], h[c * 32 + k * 3 + 2],
-                            h[c * 32 + k * 3] / 1e3 / h[c * 32 + k * 3 + 2], h[c * 32 + k * 3 + 1] / 1e3 / h[c * 32 + k * 3 + 2]);
+            for (int k = 0; k < 7; ++k) {
+                const unsigned long long *e = h + c * 32 + k * 4;
+                if (e[3])
+                    fprintf(stderr, "[mega cta %s] %-6s n=%6llu work %7.2f  arrive+prep %7.2f  wait %7.2f us/phase\n",
+                            c ? "last" : "0", kn[k], e[3], e[0] / 1965.0 / e[3], e[1] / 1965.0 / e[3], e[2] / 1965.0 / e[3]);
+                if (c == 0 && e[3] && k != 1 && k != 6) {
+                    const unsigned long long *u = h + 64 + k * 4;
+                    fprintf(stderr, "             %-6s prologue %6.2f  sync %6.2f  norm %6.2f  tasks %6.2f us/phase\n", kn[k],
+                            (double)(long long)u[3] / 1965.0 / e[3], u[0] / 1965.0 / e[3], u[1] / 1965.0 / e[3], u[2] / 1965.0 / e[3]);
+                }
+            }
     }
     if (use_mega) {
         // the single persistent launch IS the frame loop: algorithmic bytes = weights streamed per

@@ -481,7 +481,7 @@ __global__ void __launch_bounds__(kSampleThreads) sample_slow_kernel(const float
     int n_pad = 1;
     while (n_pad < n) n_pad <<= 1;
     unsigned long long *keys = reinterpret_cast<unsigned long long *>(smem_raw);
-    float *vals = reinterpret_cast<float *>(keys + n_pad);
+    float *vals = reinterpret_cast<float *>(keys + 2 * max(n_pad, (int)blockDim.x));
     float *red = vals + n_pad;
     const int frame = st.frame[b];
     const float u = philox_uniform(st.sp.seed, (uint64_t)frame * (st.C + 1), (uint32_t)b);
@@ -532,7 +532,7 @@ __global__ void __launch_bounds__(kSampleThreads) sample_fast_kernel(const float
     int n_pad = 1;
     while (n_pad < n) n_pad <<= 1;
     unsigned long long *keys = reinterpret_cast<unsigned long long *>(smem_raw);
-    float *vals = reinterpret_cast<float *>(keys + n_pad);
+    float *vals = reinterpret_cast<float *>(keys + 2 * max(n_pad, (int)blockDim.x));
     float *red = vals + n_pad;
     const int frame = st.frame[b];
     if (!eos) {

@@ -51,11 +51,8 @@ __device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned *p) {
     asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ unsigned long long globaltimer_ns() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
-}
+// debug timers: SM cycle counter (cheap to read, unlike %globaltimer); reported at 1.965 GHz
+__device__ __forceinline__ unsigned long long globaltimer_ns() { return (unsigned long long)clock64(); }
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
     const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
@@ -70,14 +67,13 @@ __device__ __forceinline__ void grid_arrive(unsigned int *bar, unsigned int &tar
     __syncthreads();
     if (threadIdx.x == 0) {
         target += gridDim.x;
-        __threadfence();
-        atomicAdd(bar, 1u);
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
     }
 }
 __device__ __forceinline__ void grid_wait(unsigned int *bar, unsigned int target) {
     if (threadIdx.x == 0) {
         while ((int)(ld_relaxed_u32(bar) - target) < 0) {}
-        __threadfence();
+        asm volatile("fence.acquire.gpu;" ::: "memory");
     }
     __syncthreads();
 }
@@ -170,11 +166,19 @@ template <typename WT, int NB>
 struct Mega {
     const MegaParams &p;
     float *xs, *val, *red, *kvs;
+    float *cs_s, *csf_s;  // cos|sin rows: per batch row at its slow position; per codebook index (fast stack)
+    int *pos_s;           // slow positions of the current frame
     int tid, lane, warp;
     unsigned int target;
     uint4 pre[kMegaPre];
     int pre_xoff;
+    float gpre[4];   // norm weights of the coming phase (k = tid + i * 512), loaded with the weights
+    int n_staged;    // later tasks of this warp staged in smem by cp.async (same lane writes and reads)
     GemvPlan<WT> plan;
+    // sampler state, authoritative copy in CTA 0's shared memory (global copies are write-through)
+    int *s_active, *s_eos, *s_frame, *s_maxf;
+    uint32_t *s_cur, *s_prev;
+    RepPenState *s_rep;
     // attention item staged for the coming K_ATT phase
     int att_item, att_n;  // item id (or -1), positions staged
 
@@ -182,7 +186,18 @@ struct Mega {
         xs = smem;
         val = smem + pp.xs_floats;
         red = val + pp.val_floats;
-        kvs = red + 64 * NB;
+        cs_s = red + 64 * NB;
+        csf_s = cs_s + NB * 64;
+        pos_s = reinterpret_cast<int *>(csf_s + 8 * 64);
+        s_active = pos_s + 4 * ((NB + 3) / 4);
+        s_eos = s_active + NB;
+        s_frame = s_eos + NB;
+        s_maxf = s_frame + NB;
+        s_cur = reinterpret_cast<uint32_t *>(s_maxf + NB);
+        s_prev = s_cur + NB * 20;
+        s_rep = reinterpret_cast<RepPenState *>(s_prev + NB * 20);
+        kvs = reinterpret_cast<float *>(s_rep + NB * 8);
+        n_staged = 0;
         tid = threadIdx.x;
         lane = tid & 31;
         warp = tid >> 5;
@@ -193,46 +208,69 @@ struct Mega {
     }
 
 
-    // plan + register preload of the next phase's weights; called BEFORE the barrier that precedes the phase
-    __device__ __forceinline__ void prep(const void *W0, const void *W1, int rows, int K, int align = 1,
-                                         int row_a = 0, int row_b = 1) {
+    // plan + register preload of the next phase's weights; called between barrier arrive and wait.
+    // First task of the warp -> registers; later tasks -> this warp's slots of the smem staging area
+    // (cp.async, lane-private: the lane that copies a 16-byte piece is the lane that consumes it);
+    // what does not fit is pulled into L2.  norm_w: rms_norm weights of the phase (or null).
+    __device__ __forceinline__ void prep(const void *W0, const void *W1, int rows, int K, const float *norm_w,
+                                         int align = 1, int row_a = 0, int row_b = 1, bool allow_stage = true) {
+        constexpr int NE = WTraits<WT>::NE;
         plan = make_plan<WT>(W0, W1, rows, K, align, row_a, row_b);
         if (warp < plan.ntasks) {
             const WT *ptr = task_ptr<WT>(plan, warp, lane, &pre_xoff);
             task_load<WT>(plan, ptr, pre);
         }
-        // later tasks of this warp: pull their lines into L2 (4 lanes cover the 4 x 128 B of a unit)
+        if (norm_w) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (tid + i * kMegaThreads < p.D) gpre[i] = __ldg(norm_w + tid + i * kMegaThreads);
+        }
+        // staging capacity per warp: the K/V area split evenly over the warps, in tasks of T units
+        const int cap = (2 * kMegaChunk * kMegaKvStride / 4) / (kMegaWarps * plan.T * 32);  // uint4 slots / (T * 32)
+        uint4 *wst = reinterpret_cast<uint4 *>(kvs) + (size_t)warp * cap * plan.T * 32;
+        n_staged = 0;
         for (int t = warp + kMegaWarps; t < plan.ntasks; t += kMegaWarps) {
             int xo;
             const WT *ptr = task_ptr<WT>(plan, t, lane, &xo);
-            if ((lane & 7) == 0)
-                for (int i = 0; i < plan.T; ++i) prefetch_l2(ptr + (size_t)i * 32 * WTraits<WT>::NE);
+            if (allow_stage && n_staged < cap) {
+                for (int i = 0; i < plan.T; ++i)
+                    cp_async16(wst + ((size_t)n_staged * plan.T + i) * 32 + lane, ptr + (size_t)i * 32 * NE);
+                ++n_staged;
+            } else if ((lane & 7) == 0) {
+                for (int i = 0; i < plan.T; ++i) prefetch_l2(ptr + (size_t)i * 32 * NE);
+            }
         }
+        cp_async_commit();
     }
 
     // all tasks of the CTA: val[t * NB + b] = dot(task t, activation row b)
     __device__ __forceinline__ void run_tasks() {
-        uint4 nxt[kMegaPre];
-        int nxoff = 0;
-        for (int t = warp; t < plan.ntasks; t += kMegaWarps) {
-            const bool more = t + kMegaWarps < plan.ntasks;
-            if (more) {
-                const WT *nptr = task_ptr<WT>(plan, t + kMegaWarps, lane, &nxoff);
-                task_load<WT>(plan, nptr, nxt);
+        constexpr int NE = WTraits<WT>::NE;
+        const int cap = (2 * kMegaChunk * kMegaKvStride / 4) / (kMegaWarps * plan.T * 32);
+        const uint4 *wst = reinterpret_cast<const uint4 *>(kvs) + (size_t)warp * cap * plan.T * 32;
+        if (n_staged > 0) cp_async_wait_all();
+        int round = 0;
+        for (int t = warp; t < plan.ntasks; t += kMegaWarps, ++round) {
+            int xoff = pre_xoff;
+            if (round > 0) {
+                const WT *ptr = task_ptr<WT>(plan, t, lane, &xoff);
+                if (round - 1 < n_staged) {
+#pragma unroll
+                    for (int i = 0; i < kMegaPre; ++i)
+                        if (i < plan.T) pre[i] = wst[((size_t)(round - 1) * plan.T + i) * 32 + lane];
+                } else {
+                    task_load<WT>(plan, ptr, pre);
+                }
             }
             float acc[NB];
-            task_dot<WT, NB>(plan, pre, xs, pre_xoff, acc);
+            task_dot<WT, NB>(plan, pre, xs, xoff, acc);
 #pragma unroll
             for (int b = 0; b < NB; ++b) {
-                const float s = warp_sum(acc[b]);
-                if (lane == 0) val[t * NB + b] = s;
-            }
-            if (more) {
-#pragma unroll
-                for (int i = 0; i < kMegaPre; ++i) pre[i] = nxt[i];
-                pre_xoff = nxoff;
+                const float sres = warp_sum(acc[b]);
+                if (lane == 0) val[t * NB + b] = sres;
             }
         }
+        n_staged = 0;
     }
 
     // value of (matrix m, local row rl, batch row b): slices summed in a fixed order
@@ -243,7 +281,8 @@ struct Mega {
         return s;
     }
 
-    // rms_norm of NB rows staged in xs (row stride K): x / sqrt(mean(x^2) + eps) * g  (candle_nn::RmsNorm)
+    // rms_norm of NB rows staged in xs (row stride D): x / sqrt(mean(x^2) + eps) * g  (candle_nn::RmsNorm);
+    // g comes from the registers `prep` filled (D <= 4 * 512), else from global memory
     __device__ __forceinline__ void norm_in_smem(int K, const float *g) {
         float ss[NB];
 #pragma unroll
@@ -257,14 +296,23 @@ struct Mega {
             if (lane == 0) red[warp * NB + b] = ss[b];
         }
         __syncthreads();
+        const bool in_regs = K <= 4 * kMegaThreads;
 #pragma unroll
         for (int b = 0; b < NB; ++b) {
             float tot = 0.f;
 #pragma unroll
             for (int w = 0; w < kMegaWarps; ++w) tot += red[w * NB + b];
             const float denom = sqrtf(tot / (float)K + p.eps);
-            for (int k = tid; k < K; k += kMegaThreads)
-                xs[b * K + k] = __fmul_rn(__fdiv_rn(xs[b * K + k], denom), g[k]);
+            if (in_regs) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int k = tid + i * kMegaThreads;
+                    if (k < K) xs[b * K + k] = __fmul_rn(__fdiv_rn(xs[b * K + k], denom), gpre[i]);
+                }
+            } else {
+                for (int k = tid; k < K; k += kMegaThreads)
+                    xs[b * K + k] = __fmul_rn(__fdiv_rn(xs[b * K + k], denom), g[k]);
+            }
         }
     }
 
@@ -282,7 +330,7 @@ struct Mega {
         *chunk = item % p.n_chunks_max;
         *kvh = (item / p.n_chunks_max) % p.KV;
         *b = item / (p.n_chunks_max * p.KV);
-        *len = __ldcg(p.st.pos + *b) + 1;
+        *len = pos_s[*b] + 1;
         return *chunk * kMegaChunk < *len;
     }
 
@@ -410,24 +458,44 @@ struct Mega {
         att_item = -1;
     }
 
-    // prologue of wo (slow): combine the chunk partials into xs (row stride H*hd)
+    // prologue of wo (slow): combine the chunk partials into xs (row stride H*hd).  Loads are issued in
+    // batches of 8 slots (m, l, o of every slot in the batch are independent loads: one L2 round trip).
     __device__ __forceinline__ void combine_attn() {
         const int Hhd = p.H * p.hd;
         for (int i = tid; i < NB * Hhd; i += kMegaThreads) {
             const int b = i / Hhd, hd_i = i - b * Hhd, h = hd_i / p.hd, d = hd_i - h * p.hd;
             float v = 0.f;
             if (b < p.nb) {
-                const int len = __ldcg(p.st.pos + b) + 1;
+                const int len = pos_s[b] + 1;
                 const int ns = 2 * ((len + kMegaChunk - 1) / kMegaChunk);
                 const float *pp = p.partial + ((size_t)b * p.H + h) * (2 * p.n_chunks_max) * (p.hd + 4);
-                float M = -INFINITY;
-                for (int s = 0; s < ns; ++s) M = fmaxf(M, __ldcg(pp + s * (p.hd + 4) + p.hd));
-                float Lsum = 0.f, o = 0.f;
-                for (int s = 0; s < ns; ++s) {
-                    const float ms = __ldcg(pp + s * (p.hd + 4) + p.hd);
-                    const float w = (ms == -INFINITY) ? 0.f : expf(ms - M);
-                    Lsum = fmaf(__ldcg(pp + s * (p.hd + 4) + p.hd + 1), w, Lsum);
-                    o = fmaf(__ldcg(pp + s * (p.hd + 4) + d), w, o);
+                float M = -INFINITY, Lsum = 0.f, o = 0.f;
+                for (int s0 = 0; s0 < ns; s0 += 8) {
+                    float ms[8], ls[8], os[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        if (s0 + j < ns) {
+                            const float *sp = pp + (s0 + j) * (p.hd + 4);
+                            ms[j] = __ldcg(sp + p.hd);
+                            ls[j] = __ldcg(sp + p.hd + 1);
+                            os[j] = __ldcg(sp + d);
+                        } else {
+                            ms[j] = -INFINITY; ls[j] = 0.f; os[j] = 0.f;
+                        }
+                    }
+                    float Mn = M;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) Mn = fmaxf(Mn, ms[j]);
+                    const float c0 = (M == -INFINITY) ? 0.f : expf(M - Mn);
+                    Lsum *= c0;
+                    o *= c0;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float w = (ms[j] == -INFINITY) ? 0.f : expf(ms[j] - Mn);
+                        Lsum = fmaf(ls[j], w, Lsum);
+                        o = fmaf(os[j], w, o);
+                    }
+                    M = Mn;
                 }
                 v = o / Lsum;
             }
@@ -436,50 +504,44 @@ struct Mega {
     }
 
     // prologue of wo (fast): the whole attention over <= C cached positions, recomputed by every CTA.
-    // All K/V loads of a head are issued before any of them is used.
+    // q and the cached rows are staged in smem by one coalesced pass (one L2 round trip).
     __device__ __forceinline__ void fast_attn(const float *kcache, const float *vcache, int cb) {
         const int Hhd = p.H * p.hd, n_rep = p.H / p.KV;
         const float scale = 1.0f / sqrtf((float)p.hd);
-        constexpr int MAXP = 8;  // the megakernel is only selected for num_codebooks <= 8
+        const int npos = cb + 1;
+        float *qs = xs + NB * Hhd;                         // NB * Hhd, behind the output rows (max K >= 2 * Hhd)
+        float *kss = kvs;                                  // NB * KV * fast_len * hd
+        float *vss = kss + NB * p.KV * p.fast_len * p.hd;  // same
+        for (int i = tid; i < p.nb * Hhd / 4; i += kMegaThreads)
+            reinterpret_cast<float4 *>(qs)[i] = __ldcg(reinterpret_cast<const float4 *>(p.q) + i);
+        const int rows = p.nb * p.KV;  // (b, kvh) pairs; each holds fast_len rows of hd floats, npos of them valid
+        const int seg = p.hd / 4;
+        for (int i = tid; i < rows * npos * seg; i += kMegaThreads) {
+            const int r = i / (npos * seg), rem = i - r * npos * seg;
+            const size_t off = (size_t)r * p.fast_len * p.hd + rem * 4;
+            *reinterpret_cast<float4 *>(kss + off) = __ldcg(reinterpret_cast<const float4 *>(kcache + off));
+            *reinterpret_cast<float4 *>(vss + off) = __ldcg(reinterpret_cast<const float4 *>(vcache + off));
+        }
+        __syncthreads();
         for (int item = warp; item < NB * p.H; item += kMegaWarps) {
             const int b = item / p.H, h = item - b * p.H;
             float o0 = 0.f, o1 = 0.f;
             if (b < p.nb) {
                 const int kvh = h / n_rep;
-                const float q0 = __ldcg(p.q + (size_t)b * Hhd + h * p.hd + lane);
-                const float q1 = __ldcg(p.q + (size_t)b * Hhd + h * p.hd + lane + 32);
-                const float *kb = kcache + ((size_t)b * p.KV + kvh) * p.fast_len * p.hd;
-                const float *vb = vcache + ((size_t)b * p.KV + kvh) * p.fast_len * p.hd;
-                float k0[MAXP], k1[MAXP], v0[MAXP], v1[MAXP];
-#pragma unroll
-                for (int j = 0; j < MAXP; ++j) {
-                    if (j <= cb) {
-                        k0[j] = __ldcg(kb + j * p.hd + lane);
-                        k1[j] = __ldcg(kb + j * p.hd + lane + 32);
-                        v0[j] = __ldcg(vb + j * p.hd + lane);
-                        v1[j] = __ldcg(vb + j * p.hd + lane + 32);
-                    }
-                }
-                float sc[MAXP];
-                float m = -INFINITY;
-#pragma unroll
-                for (int j = 0; j < MAXP; ++j) {
-                    if (j <= cb) {
-                        float d = q0 * (k0[j] * scale);
-                        d = fmaf(q1, k1[j] * scale, d);
-                        sc[j] = warp_sum(d);
-                        m = fmaxf(m, sc[j]);
-                    }
-                }
-                float l = 0.f;
-#pragma unroll
-                for (int j = 0; j < MAXP; ++j) {
-                    if (j <= cb) {
-                        const float pj = expf(sc[j] - m);
-                        l += pj;
-                        o0 = fmaf(pj, v0[j], o0);
-                        o1 = fmaf(pj, v1[j], o1);
-                    }
+                const float q0 = qs[b * Hhd + h * p.hd + lane], q1 = qs[b * Hhd + h * p.hd + lane + 32];
+                const float *kb = kss + ((size_t)b * p.KV + kvh) * p.fast_len * p.hd;
+                const float *vb = vss + ((size_t)b * p.KV + kvh) * p.fast_len * p.hd;
+                float m = -INFINITY, l = 0.f;
+                for (int j = 0; j < npos; ++j) {
+                    float dd = q0 * (kb[j * p.hd + lane] * scale);
+                    dd = fmaf(q1, kb[j * p.hd + lane + 32] * scale, dd);
+                    dd = warp_sum(dd);
+                    const float m_new = fmaxf(m, dd);
+                    const float corr = expf(m - m_new), pj = expf(dd - m_new);
+                    l = fmaf(l, corr, pj);
+                    o0 = fmaf(o0, corr, pj * vb[j * p.hd + lane]);
+                    o1 = fmaf(o1, corr, pj * vb[j * p.hd + lane + 32]);
+                    m = m_new;
                 }
                 o0 /= l;
                 o1 /= l;
@@ -523,13 +585,15 @@ struct Mega {
     __device__ __forceinline__ void prep_step(const Step &s) {
         const bool slow = s.pass == 0;
         switch (s.kind) {
-            case K_QKV: prep(layer_of(s).wqkv, nullptr, p.QKV, p.D, 2); break;
-            case K_WO: prep(layer_of(s).wo, nullptr, p.D, p.H * p.hd); break;
-            case K_W13: prep(layer_of(s).w1, layer_of(s).w3, p.I, p.D); break;
-            case K_W2: prep(layer_of(s).w2, nullptr, p.D, p.I); break;
+            case K_QKV: prep(layer_of(s).wqkv, nullptr, p.QKV, p.D, layer_of(s).attn_norm, 2); break;
+            case K_WO:  // the fast wo prologue stages K/V in the same smem area: no weight staging there
+                prep(layer_of(s).wo, nullptr, p.D, p.H * p.hd, nullptr, 1, 0, 1, slow);
+                break;
+            case K_W13: prep(layer_of(s).w1, layer_of(s).w3, p.I, p.D, layer_of(s).ffn_norm); break;
+            case K_W2: prep(layer_of(s).w2, nullptr, p.D, p.I, nullptr); break;
             case K_HEAD:
-                if (slow) prep(p.out_w, nullptr, p.n_slow_logits, p.D, 1, p.slow_row0, p.slow_rest_base);
-                else prep(p.fast_out, nullptr, p.CS, p.D);
+                if (slow) prep(p.out_w, nullptr, p.n_slow_logits, p.D, p.norm, 1, p.slow_row0, p.slow_rest_base);
+                else prep(p.fast_out, nullptr, p.CS, p.D, p.fast_norm);
                 break;
             default: break;
         }
@@ -550,6 +614,13 @@ struct Mega {
             if (s.l > 0) {
                 stage_rows(xg, D);
             } else if (slow) {
+                // once per frame: this frame's slow positions and their RoPE rows -> smem
+                for (int i = tid; i < NB * p.hd; i += kMegaThreads) {
+                    const int b = i / p.hd, d = i - b * p.hd, half = p.hd / 2;
+                    const int pos = b < p.nb ? __ldcg(p.st.pos + b) : 0;
+                    cs_s[i] = d < half ? p.cosT[(size_t)pos * half + d] : p.sinT[(size_t)pos * half + d - half];
+                    if (d == 0) pos_s[b] = pos;
+                }
                 // DualARTransformer::embed, dual_ar.rs:532-567, on the previous frame's codes
                 const WT *emb = reinterpret_cast<const WT *>(p.emb), *cbe = reinterpret_cast<const WT *>(p.cb_emb);
                 for (int i = tid; i < NB * D; i += kMegaThreads) {
@@ -596,13 +667,25 @@ struct Mega {
             stage_rows(xg, p.D);
             norm_w = slow ? p.norm : p.fast_norm;
         }
+        const bool sub_timed = p.dbg != nullptr && tid == 0 && blockIdx.x == 0;
+        unsigned long long ta = 0, tb = 0, tc = 0, td = 0;
+        if (sub_timed) ta = globaltimer_ns();
         __syncthreads();
+        if (sub_timed) tb = globaltimer_ns();
         if (norm_w) {
             norm_in_smem(p.D, norm_w);
             __syncthreads();
         }
+        if (sub_timed) tc = globaltimer_ns();
         run_tasks();
         __syncthreads();
+        if (sub_timed) {
+            td = globaltimer_ns();
+            p.dbg[64 + kind * 4 + 0] += tb - ta;
+            p.dbg[64 + kind * 4 + 1] += tc - tb;
+            p.dbg[64 + kind * 4 + 2] += td - tc;
+            p.dbg[64 + kind * 4 + 3] += ta;  // absolute start, combined with the phase start below
+        }
         // ---- epilogue
         if (kind == K_QKV) {
             // pairs of rows -> rope_i (dual_ar.rs:246-247) -> q buffer / K cache; V rows -> V cache (Tensor::cat, :316-324)
@@ -612,10 +695,11 @@ struct Mega {
                 if (b >= p.nb) continue;
                 const int r = plan.r0 + 2 * pr;
                 const float v0 = row_val(0, 2 * pr, b), v1 = row_val(0, 2 * pr + 1, b);
-                const int pos = slow ? __ldcg(p.st.pos + b) : cb;
+                const int pos = slow ? pos_s[b] : cb;
                 if (r < Hhd + KVhd) {
                     const int pi = (r % p.hd) / 2;
-                    const float c = p.cosT[(size_t)pos * half + pi], sn = p.sinT[(size_t)pos * half + pi];
+                    const float *cs = slow ? cs_s + b * p.hd : csf_s + cb * p.hd;
+                    const float c = cs[pi], sn = cs[half + pi];
                     const float o0 = __fsub_rn(__fmul_rn(v0, c), __fmul_rn(v1, sn));
                     const float o1 = __fadd_rn(__fmul_rn(v0, sn), __fmul_rn(v1, c));
                     if (r < Hhd) {
@@ -653,18 +737,41 @@ struct Mega {
         }
     }
 
-    // ------------------------------------------------------------ samplers (CTA 0 only; smem aliased on xs/val)
+    // ------------------------------------------------------------ samplers (CTA 0 only; scratch aliased on xs/val)
+    // The per-row generator state lives in CTA 0's shared memory for the whole launch; every update is
+    // also written through to the global copy (other CTAs read cur / prev / pos / n_active from there,
+    // the host reads frame / pos / out after the launch).
+    __device__ __forceinline__ void load_sampler_state() {
+        const GenState &st = p.st;
+        const int C1 = st.C + 1;
+        for (int i = tid; i < p.nb; i += kMegaThreads) {
+            s_active[i] = st.active[i];
+            s_eos[i] = st.eos[i];
+            s_frame[i] = st.frame[i];
+            s_maxf[i] = st.max_frames[i];
+        }
+        for (int i = tid; i < p.nb * C1; i += kMegaThreads) {
+            const int b = i / C1, c = i - b * C1;
+            s_cur[b * 20 + c] = st.cur[i];
+            s_prev[b * 20 + c] = st.prev[i];
+        }
+        const int words = (int)(sizeof(RepPenState) / 4);
+        for (int i = tid; i < p.nb * st.C * words; i += kMegaThreads)
+            reinterpret_cast<uint32_t *>(s_rep)[i] = reinterpret_cast<const uint32_t *>(st.rep)[i];
+        __syncthreads();
+    }
+
     __device__ __forceinline__ void sample_slow() {
         const GenState &st = p.st;
         const int n = p.n_slow_logits;
         int n_pad = 1;
         while (n_pad < n) n_pad <<= 1;
         unsigned long long *keys = reinterpret_cast<unsigned long long *>(xs);
-        float *vals = reinterpret_cast<float *>(keys + n_pad);
+        float *vals = reinterpret_cast<float *>(keys + 2 * max(n_pad, kMegaThreads));
         float *sred = vals + n_pad;
         for (int b = 0; b < p.nb; ++b) {
-            if (!st.active[b]) continue;
-            const int frame = st.frame[b];
+            if (!s_active[b]) continue;
+            const int frame = s_frame[b];
             const float u = philox_uniform(st.sp.seed, (uint64_t)frame * (st.C + 1), (uint32_t)b);
             uint32_t tok;
             if (st.legacy_slow) {
@@ -684,10 +791,15 @@ struct Mega {
             }
             if (tid == 0) {
                 const bool eos = tok == st.im_end_id;
+                s_cur[b * 20] = tok;
                 st.cur[b * (st.C + 1)] = tok;
+                s_eos[b] = eos ? 1 : 0;
                 st.eos[b] = eos ? 1 : 0;
                 if (eos)
-                    for (int c = 0; c < st.C; ++c) st.cur[b * (st.C + 1) + 1 + c] = 0;
+                    for (int c = 0; c < st.C; ++c) {
+                        s_cur[b * 20 + 1 + c] = 0;
+                        st.cur[b * (st.C + 1) + 1 + c] = 0;
+                    }
             }
             __syncthreads();
         }
@@ -699,16 +811,16 @@ struct Mega {
         int n_pad = 1;
         while (n_pad < n) n_pad <<= 1;
         unsigned long long *keys = reinterpret_cast<unsigned long long *>(xs);
-        float *vals = reinterpret_cast<float *>(keys + n_pad);
+        float *vals = reinterpret_cast<float *>(keys + 2 * max(n_pad, kMegaThreads));
         float *sred = vals + n_pad;
         for (int b = 0; b < p.nb; ++b) {
-            if (!st.active[b]) continue;
-            const bool eos = st.eos[b] != 0;
-            const int frame = st.frame[b];
+            if (!s_active[b]) continue;
+            const bool eos = s_eos[b] != 0;
+            const int frame = s_frame[b];
             if (!eos) {
-                RepPenState *rp = st.rep + (size_t)b * C + cb;
+                RepPenState *rp = s_rep + (size_t)b * C + cb;
                 if (frame > 0) {
-                    if (tid == 0) rep_pen_update(rp, st.prev[b * (C + 1) + 1 + cb]);
+                    if (tid == 0) rep_pen_update(rp, s_prev[b * 20 + 1 + cb]);
                     __syncthreads();
                 }
                 for (int i = tid; i < n; i += kMegaThreads) {
@@ -719,24 +831,40 @@ struct Mega {
                 __syncthreads();
                 const float u = philox_uniform(st.sp.seed, (uint64_t)frame * (C + 1) + cb + 1, (uint32_t)b);
                 const int a = block_sample(vals, keys, sred, n, n_pad, st.sp, u);
-                if (tid == 0) st.cur[b * (C + 1) + 1 + cb] = (uint32_t)a;
+                if (tid == 0) {
+                    s_cur[b * 20 + 1 + cb] = (uint32_t)a;
+                    st.cur[b * (C + 1) + 1 + cb] = (uint32_t)a;
+                }
             }
             if (cb == C - 1) {
                 __syncthreads();
+                // frame bookkeeping (single_batch.rs:193-204), write-through
+                if (tid <= C) {
+                    const uint32_t v = s_cur[b * 20 + tid];
+                    st.out[((size_t)b * st.out_cap + frame) * (C + 1) + tid] = v;
+                    s_prev[b * 20 + tid] = v;
+                    st.prev[b * (C + 1) + tid] = v;
+                }
                 if (tid == 0) {
-                    uint32_t *o = st.out + ((size_t)b * st.out_cap + frame) * (C + 1);
-                    for (int c = 0; c <= C; ++c) {
-                        const uint32_t v = st.cur[b * (C + 1) + c];
-                        o[c] = v;
-                        st.prev[b * (C + 1) + c] = v;
-                    }
                     const int nf = frame + 1;
+                    s_frame[b] = nf;
                     st.frame[b] = nf;
-                    if (frame > 0) st.pos[b] += 1;
-                    if (eos || nf >= st.max_frames[b]) {
+                    if (frame > 0) {
+                        pos_s[b] += 1;  // CTA 0's cached copy is reloaded at the next frame start anyway
+                        st.pos[b] = pos_s[b];
+                    }
+                    if (eos || nf >= s_maxf[b]) {
+                        s_active[b] = 0;
                         st.active[b] = 0;
                         atomicSub(st.n_active, 1);
                     }
+                }
+                // the rep-pen windows only matter to a later launch on the same rows: write them back
+                {
+                    const int words = (int)(sizeof(RepPenState) / 4);
+                    const uint32_t *src = reinterpret_cast<const uint32_t *>(s_rep + (size_t)b * C);
+                    uint32_t *dst = reinterpret_cast<uint32_t *>(st.rep + (size_t)b * C);
+                    for (int i = tid; i < C * words; i += kMegaThreads) dst[i] = src[i];
                 }
             }
             __syncthreads();
@@ -749,12 +877,24 @@ struct Mega {
         cur.frame = 0; cur.pass = 0; cur.l = 0;
         cur.kind = (p.first_is_tail || p.NL == 0) ? K_HEAD : K_QKV;
         if (p.nframes <= 0 || __ldcg(p.st.n_active) == 0) return;
+        for (int i = tid; i < p.C * p.hd; i += kMegaThreads) {
+            const int row = i / p.hd, d = i - row * p.hd, half = p.hd / 2;
+            csf_s[i] = d < half ? p.cosT[(size_t)row * half + d] : p.sinT[(size_t)row * half + d - half];
+        }
+        if (blockIdx.x == 0) {
+            for (int i = tid; i < p.nb; i += kMegaThreads) pos_s[i] = p.st.pos[i];
+            load_sampler_state();
+        }
+        __syncthreads();
         prep_step(cur);
         const bool timed = p.dbg != nullptr && tid == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1);
         unsigned long long *dbg = p.dbg + (blockIdx.x == 0 ? 0 : 32);
         while (cur.kind != K_END) {
             unsigned long long t0 = 0, t1 = 0, t2 = 0;
-            if (timed) t0 = globaltimer_ns();
+            if (timed) {
+                t0 = globaltimer_ns();
+                if (blockIdx.x == 0) p.dbg[64 + cur.kind * 4 + 3] -= t0;  // += (prologue end - phase start)
+            }
             if (cur.kind == K_ATT) phase_attn_slow(cur.l);
             else if (cur.kind == K_SAMPLE) {
                 if (blockIdx.x == 0) {
@@ -771,12 +911,14 @@ struct Mega {
             if (nxt.kind == K_SAMPLE) prep_step(advance(nxt));
             else if (cur.kind != K_SAMPLE) prep_step(nxt);
             if (nxt.kind == K_ATT) att_prefetch(nxt.l);
+            if (timed) t2 = globaltimer_ns();
             grid_wait(p.bar, target);
             if (timed) {
-                t2 = globaltimer_ns();
-                dbg[cur.kind * 3 + 0] += t1 - t0;
-                dbg[cur.kind * 3 + 1] += t2 - t1;
-                dbg[cur.kind * 3 + 2] += 1;
+                const unsigned long long t3 = globaltimer_ns();
+                dbg[cur.kind * 4 + 0] += t1 - t0;
+                dbg[cur.kind * 4 + 1] += t2 - t1;
+                dbg[cur.kind * 4 + 2] += t3 - t2;
+                dbg[cur.kind * 4 + 3] += 1;
             }
             if (nxt.frame != cur.frame && nxt.kind != K_END && __ldcg(p.st.n_active) == 0) break;
             cur = nxt;

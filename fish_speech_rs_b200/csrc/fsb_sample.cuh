@@ -59,22 +59,40 @@ struct SampleParams {
 constexpr int kSampleThreads = 1024;
 constexpr int kSampleMaxN = 4096;
 
-// Block-wide sampler (any block size that is a multiple of 32).  `vals` (smem, n_pad floats)
-// holds the adjusted logits; returns the chosen index to every thread.  keys: smem n_pad u64.
-// top-k -> top-p -> multinomial as in sampling/mod.rs:51-75,113-132; the running sums over the
-// sorted candidates are evaluated as a 32-lane segmented scan (each lane sums a contiguous
-// segment sequentially, lane totals are combined by a warp scan) instead of one sequential f32
-// chain: same distribution, differs from a sequential sum only in the last bits of the CDF.
+// Block-wide sampler (any block size that is a multiple of 32, n_pad <= 8 * blockDim.x).
+// `vals` (smem, n floats) holds the adjusted logits; returns the chosen index to every thread.
+// `keys`: smem scratch of 2 * max(n_pad, blockDim.x) u64.
+// top-k -> top-p -> multinomial as in sampling/mod.rs:51-75,113-132.  The candidates are ordered by a
+// bitonic sort of (~prob bits, index) keys held in REGISTERS: exchange distances >= blockDim.x stay
+// inside a thread, distances < 32 are warp shuffles, only the distances in between go through shared
+// memory (double buffered, one __syncthreads each).  The running sums over the sorted candidates are a
+// 32-lane segmented scan (each lane sums a contiguous segment sequentially, lane totals are combined
+// by a warp scan): same distribution as the reference's sequential f32 chain, last-bit differences
+// in the CDF only.
+constexpr int kSampleMaxE = 8;
+
+__device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned long long v, int m) {
+    unsigned lo = (unsigned)v, hi = (unsigned)(v >> 32);
+    lo = __shfl_xor_sync(0xffffffffu, lo, m);
+    hi = __shfl_xor_sync(0xffffffffu, hi, m);
+    return ((unsigned long long)hi << 32) | lo;
+}
+
 __device__ inline int block_sample(float *vals, unsigned long long *keys, float *red, int n, int n_pad,
                                    const SampleParams &sp, float u) {
     const int tid = threadIdx.x, nthreads = blockDim.x;
     const int lane = tid & 31, warp = tid >> 5, nwarps = nthreads >> 5;
+    const int n_eff = max(n_pad, nthreads);
+    const int E = n_eff / nthreads;  // elements per thread: index e * nthreads + tid
+    float v[kSampleMaxE];
     // ---- max (and first argmax) ----
     float best = -INFINITY;
     int best_i = 0x7fffffff;
-    for (int i = tid; i < n; i += nthreads) {
-        float v = vals[i];
-        if (v > best || (v == best && i < best_i)) { best = v; best_i = i; }
+#pragma unroll
+    for (int e = 0; e < kSampleMaxE; ++e) {
+        const int i = e * nthreads + tid;
+        v[e] = (e < E && i < n) ? vals[i] : -INFINITY;
+        if (v[e] > best) { best = v[e]; best_i = i; }  // ascending i: the first maximum wins
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -85,62 +103,108 @@ __device__ inline int block_sample(float *vals, unsigned long long *keys, float 
     int *red_i = reinterpret_cast<int *>(red + 32);
     if (lane == 0) { red[warp] = best; red_i[warp] = best_i; }
     __syncthreads();
-    if (warp == 0) {
-        best = lane < nwarps ? red[lane] : -INFINITY;
-        best_i = lane < nwarps ? red_i[lane] : 0x7fffffff;
+    {
+        float b2 = lane < nwarps ? red[lane] : -INFINITY;
+        int i2 = lane < nwarps ? red_i[lane] : 0x7fffffff;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
-            float ov = __shfl_xor_sync(0xffffffffu, best, o);
-            int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
-            if (ov > best || (ov == best && oi < best_i)) { best = ov; best_i = oi; }
+            float ov = __shfl_xor_sync(0xffffffffu, b2, o);
+            int oi = __shfl_xor_sync(0xffffffffu, i2, o);
+            if (ov > b2 || (ov == b2 && oi < i2)) { b2 = ov; i2 = oi; }
         }
-        if (lane == 0) { red[0] = best; red_i[0] = best_i; }
+        best = b2;
+        best_i = i2;
     }
-    __syncthreads();
-    best = red[0]; best_i = red_i[0];
-    __syncthreads();
-    if (sp.greedy) return best_i;
-
+    if (sp.greedy) {
+        __syncthreads();
+        return best_i;
+    }
     // ---- softmax(logits * inv_temp) ----
     const float mx = __fmul_rn(best, sp.inv_temp);
     float s = 0.f;
-    for (int i = tid; i < n; i += nthreads) {
-        float e = expf(__fsub_rn(__fmul_rn(vals[i], sp.inv_temp), mx));
-        vals[i] = e;
-        s += e;
+#pragma unroll
+    for (int e = 0; e < kSampleMaxE; ++e) {
+        if (e < E) {
+            v[e] = (e * nthreads + tid < n) ? expf(__fsub_rn(__fmul_rn(v[e], sp.inv_temp), mx)) : 0.f;
+            s += v[e];
+        }
     }
     s = warp_sum(s);
+    __syncthreads();  // red[] reads above are done
     if (lane == 0) red[warp] = s;
     __syncthreads();
-    if (warp == 0) {
-        float t = lane < nwarps ? red[lane] : 0.f;
-        t = warp_sum(t);
-        if (lane == 0) red[0] = t;
-    }
-    __syncthreads();
-    const float denom = red[0];
-    // keys: (~prob bits) << 32 | index, ascending sort == prob desc, index asc
-    for (int i = tid; i < n_pad; i += nthreads) {
-        unsigned long long k = ~0ull;
-        if (i < n) {
-            float p = vals[i] / denom;
-            k = ((unsigned long long)(~__float_as_uint(p)) << 32) | (unsigned)i;
+    float denom = lane < nwarps ? red[lane] : 0.f;
+    denom = warp_sum(denom);
+    // keys: (~prob bits) << 32 | index; ascending sort == prob desc, index asc
+    unsigned long long key[kSampleMaxE];
+#pragma unroll
+    for (int e = 0; e < kSampleMaxE; ++e) {
+        const int i = e * nthreads + tid;
+        key[e] = ~0ull;
+        if (e < E && i < n) {
+            const float p = v[e] / denom;
+            key[e] = ((unsigned long long)(~__float_as_uint(p)) << 32) | (unsigned)i;
         }
-        keys[i] = k;
     }
-    __syncthreads();
-    for (int k = 2; k <= n_pad; k <<= 1) {
+    // ---- bitonic sort over n_eff keys ----
+    int buf = 0;
+    for (int k = 2; k <= n_eff; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = tid; i < n_pad; i += nthreads) {
-                int ixj = i ^ j;
-                if (ixj > i) {
-                    unsigned long long a = keys[i], b = keys[ixj];
-                    bool up = ((i & k) == 0);
-                    if ((a > b) == up) { keys[i] = b; keys[ixj] = a; }
+            if (j >= nthreads) {
+                const int je = j / nthreads;  // partner element inside the same thread
+#pragma unroll
+                for (int jj = 1; jj < kSampleMaxE; jj <<= 1) {  // compile-time register indices
+                    if (je == jj) {
+#pragma unroll
+                        for (int e = 0; e < kSampleMaxE; ++e) {
+                            if ((e & jj) == 0 && (e | jj) < E) {
+                                const int i = e * nthreads + tid;
+                                const bool up = (i & k) == 0;
+                                const unsigned long long a = key[e], b = key[e | jj];
+                                if ((a > b) == up) { key[e] = b; key[e | jj] = a; }
+                            }
+                        }
+                    }
+                }
+            } else if (j >= 32) {
+                unsigned long long *kb = keys + (size_t)buf * n_eff;
+#pragma unroll
+                for (int e = 0; e < kSampleMaxE; ++e)
+                    if (e < E) kb[e * nthreads + tid] = key[e];
+                __syncthreads();
+#pragma unroll
+                for (int e = 0; e < kSampleMaxE; ++e) {
+                    if (e < E) {
+                        const int i = e * nthreads + tid;
+                        const unsigned long long o = kb[i ^ j];
+                        const bool up = (i & k) == 0, lower = (i & j) == 0;
+                        const bool take_min = up == lower;
+                        key[e] = take_min ? (o < key[e] ? o : key[e]) : (o > key[e] ? o : key[e]);
+                    }
+                }
+                buf ^= 1;
+            } else {
+#pragma unroll
+                for (int e = 0; e < kSampleMaxE; ++e) {
+                    if (e < E) {
+                        const int i = e * nthreads + tid;
+                        const unsigned long long o = shfl_xor_u64(key[e], j);
+                        const bool up = (i & k) == 0, lower = (i & j) == 0;
+                        const bool take_min = up == lower;
+                        key[e] = take_min ? (o < key[e] ? o : key[e]) : (o > key[e] ? o : key[e]);
+                    }
                 }
             }
-            __syncthreads();
         }
+    }
+    // sorted position of key[e] is e * nthreads + tid; the scan below only walks the first <= n entries
+    {
+        unsigned long long *kb = keys + (size_t)buf * n_eff;
+#pragma unroll
+        for (int e = 0; e < kSampleMaxE; ++e)
+            if (e < E) kb[e * nthreads + tid] = key[e];
+        __syncthreads();
+        keys = kb;
     }
     // ---- top-k -> top-p -> multinomial on warp 0 ----
     if (warp == 0) {
