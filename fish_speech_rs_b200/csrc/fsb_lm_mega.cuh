@@ -101,11 +101,10 @@ __device__ __forceinline__ GemvPlan<WT> make_plan(const void *W0, const void *W1
     const int upr = K / (32 * WTraits<WT>::NE);
     pl.ksplit = (upr + kMegaPre - 1) / kMegaPre;
     pl.T = upr / pl.ksplit;  // host guarantees divisibility
-    const int groups = rows_total / align;
-    const int g0 = (int)(((long long)blockIdx.x * groups) / gridDim.x);
-    const int g1 = (int)(((long long)(blockIdx.x + 1) * groups) / gridDim.x);
-    pl.r0 = g0 * align;
-    pl.nrows = (blockIdx.x + 1 == gridDim.x ? rows_total : g1 * align) - pl.r0;
+    const unsigned groups = rows_total / align;  // blockIdx * groups < 2^32 for any vocabulary
+    const unsigned g0 = (blockIdx.x * groups) / gridDim.x, g1 = ((blockIdx.x + 1) * groups) / gridDim.x;
+    pl.r0 = (int)g0 * align;
+    pl.nrows = (blockIdx.x + 1 == gridDim.x ? rows_total : (int)g1 * align) - pl.r0;
     pl.row_a = row_a;
     pl.row_b = row_b;
     pl.ntasks = pl.nrows * pl.ksplit * (W1 ? 2 : 1);
