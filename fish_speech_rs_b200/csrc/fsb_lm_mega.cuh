@@ -224,52 +224,54 @@ struct Mega {
             for (int i = 0; i < 4; ++i)
                 if (tid + i * kMegaThreads < p.D) gpre[i] = __ldg(norm_w + tid + i * kMegaThreads);
         }
-        // staging capacity per warp: the K/V area split evenly over the warps, in tasks of T units
-        const int cap = (2 * kMegaChunk * kMegaKvStride / 4) / (kMegaWarps * plan.T * 32);  // uint4 slots / (T * 32)
-        uint4 *wst = reinterpret_cast<uint4 *>(kvs) + (size_t)warp * cap * plan.T * 32;
         n_staged = 0;
-        for (int t = warp + kMegaWarps; t < plan.ntasks; t += kMegaWarps) {
-            int xo;
-            const WT *ptr = task_ptr<WT>(plan, t, lane, &xo);
-            if (allow_stage && n_staged < cap) {
-                for (int i = 0; i < plan.T; ++i)
-                    cp_async16(wst + ((size_t)n_staged * plan.T + i) * 32 + lane, ptr + (size_t)i * 32 * NE);
-                ++n_staged;
-            } else if ((lane & 7) == 0) {
-                for (int i = 0; i < plan.T; ++i) prefetch_l2(ptr + (size_t)i * 32 * NE);
-            }
-        }
-        cp_async_commit();
+        (void)allow_stage;
+        // later tasks of the phase are NOT requested here: their lines were pulled into L2 one phase
+        // earlier (l2_prefetch_rows), and anything outstanding towards this SM would delay the
+        // activation reload that follows the barrier (the SM's return path is a FIFO)
     }
 
-    // all tasks of the CTA: val[t * NB + b] = dot(task t, activation row b)
+    // Pull this CTA's whole weight slice of a FUTURE phase into L2 (prefetch.global.L2 returns no data to
+    // the SM).  Issued two weight phases ahead, so HBM streams in the background while the CTA computes,
+    // sits in barriers or reloads activations; the loads that finally feed the FMAs are L2 hits.
+    __device__ __forceinline__ void l2_prefetch_rows(const void *W0, const void *W1, int rows, int K, int align,
+                                                     int row_a, int row_b) {
+        const GemvPlan<WT> pl = make_plan<WT>(W0, W1, rows, K, align, row_a, row_b);
+        const int lines = K * (int)sizeof(WT) / 128;
+        const int nr = pl.nrows * (W1 ? 2 : 1);
+        for (int fr = warp; fr < nr; fr += kMegaWarps) {
+            const WT *W = fr < pl.nrows ? pl.W0 : pl.W1;
+            const int r = pl.r0 + (fr < pl.nrows ? fr : fr - pl.nrows);
+            const size_t wrow = (size_t)(r == 0 ? pl.row_a : pl.row_b + r - 1);
+            const char *base = reinterpret_cast<const char *>(W + wrow * K);
+            for (int ln = lane; ln < lines; ln += 32) prefetch_l2(base + (size_t)ln * 128);
+        }
+    }
+
+    // all tasks of the CTA: val[t * NB + b] = dot(task t, activation row b); the next task's loads are
+    // issued before the current one is consumed
     __device__ __forceinline__ void run_tasks() {
-        constexpr int NE = WTraits<WT>::NE;
-        const int cap = (2 * kMegaChunk * kMegaKvStride / 4) / (kMegaWarps * plan.T * 32);
-        const uint4 *wst = reinterpret_cast<const uint4 *>(kvs) + (size_t)warp * cap * plan.T * 32;
-        if (n_staged > 0) cp_async_wait_all();
-        int round = 0;
-        for (int t = warp; t < plan.ntasks; t += kMegaWarps, ++round) {
-            int xoff = pre_xoff;
-            if (round > 0) {
-                const WT *ptr = task_ptr<WT>(plan, t, lane, &xoff);
-                if (round - 1 < n_staged) {
-#pragma unroll
-                    for (int i = 0; i < kMegaPre; ++i)
-                        if (i < plan.T) pre[i] = wst[((size_t)(round - 1) * plan.T + i) * 32 + lane];
-                } else {
-                    task_load<WT>(plan, ptr, pre);
-                }
+        uint4 nxt[kMegaPre];
+        int nxoff = 0;
+        for (int t = warp; t < plan.ntasks; t += kMegaWarps) {
+            const bool more = t + kMegaWarps < plan.ntasks;
+            if (more) {
+                const WT *nptr = task_ptr<WT>(plan, t + kMegaWarps, lane, &nxoff);
+                task_load<WT>(plan, nptr, nxt);
             }
             float acc[NB];
-            task_dot<WT, NB>(plan, pre, xs, xoff, acc);
+            task_dot<WT, NB>(plan, pre, xs, pre_xoff, acc);
 #pragma unroll
             for (int b = 0; b < NB; ++b) {
                 const float sres = warp_sum(acc[b]);
                 if (lane == 0) val[t * NB + b] = sres;
             }
+            if (more) {
+#pragma unroll
+                for (int i = 0; i < kMegaPre; ++i) pre[i] = nxt[i];
+                pre_xoff = nxoff;
+            }
         }
-        n_staged = 0;
     }
 
     // value of (matrix m, local row rl, batch row b): slices summed in a fixed order
@@ -598,6 +600,26 @@ struct Mega {
         }
     }
 
+    __device__ __forceinline__ void l2_prefetch_step(const Step &s) {
+        const bool slow = s.pass == 0;
+        switch (s.kind) {
+            case K_QKV: l2_prefetch_rows(layer_of(s).wqkv, nullptr, p.QKV, p.D, 2, 0, 1); break;
+            case K_WO: l2_prefetch_rows(layer_of(s).wo, nullptr, p.D, p.H * p.hd, 1, 0, 1); break;
+            case K_W13: l2_prefetch_rows(layer_of(s).w1, layer_of(s).w3, p.I, p.D, 1, 0, 1); break;
+            case K_W2: l2_prefetch_rows(layer_of(s).w2, nullptr, p.D, p.I, 1, 0, 1); break;
+            case K_HEAD:
+                if (slow) l2_prefetch_rows(p.out_w, nullptr, p.n_slow_logits, p.D, 1, p.slow_row0, p.slow_rest_base);
+                else l2_prefetch_rows(p.fast_out, nullptr, p.CS, p.D, 1, 0, 1);
+                break;
+            default: break;
+        }
+    }
+    // the next step (after s) that streams weights, or K_END
+    __device__ __forceinline__ Step next_weight_step(Step s) const {
+        do { s = advance(s); } while (s.kind == K_ATT || s.kind == K_SAMPLE);
+        return s;
+    }
+
     __device__ __forceinline__ void gemv_phase(const Step &s) {
         const bool slow = s.pass == 0;
         const int cb = s.pass - 1;
@@ -885,6 +907,8 @@ struct Mega {
             load_sampler_state();
         }
         __syncthreads();
+        l2_prefetch_step(cur);
+        l2_prefetch_step(next_weight_step(cur));
         prep_step(cur);
         const bool timed = p.dbg != nullptr && tid == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1);
         unsigned long long *dbg = p.dbg + (blockIdx.x == 0 ? 0 : 32);
@@ -909,6 +933,8 @@ struct Mega {
             // K/V rows of the next attention phase likewise
             if (nxt.kind == K_SAMPLE) prep_step(advance(nxt));
             else if (cur.kind != K_SAMPLE) prep_step(nxt);
+            // HBM -> L2 for the weight phase after the one just prepped (once per weight phase)
+            if (cur.kind != K_ATT && cur.kind != K_SAMPLE) l2_prefetch_step(next_weight_step(next_weight_step(cur)));
             if (nxt.kind == K_ATT) att_prefetch(nxt.l);
             if (timed) t2 = globaltimer_ns();
             grid_wait(p.bar, target);
