@@ -840,6 +840,12 @@ static int generate_impl(fsb_lm *lm, const uint32_t *const *prompts, const int32
         FSB_CUDA_OK(cudaMemcpy(h, lm->mega_dbg, sizeof(h), cudaMemcpyDeviceToHost));
         FSB_CUDA_OK(cudaMemset(lm->mega_dbg, 0, sizeof(h)));
         static const char *kn[7] = {"qkv", "attn", "wo", "w13", "w2", "head", "sample"};
+        if (h[103])
+            fprintf(stderr, "[sample_fast] rep-pen %.2f  logits %.2f  block_sample %.2f us (n=%llu)\n", h[100] / 1965.0 / h[103],
+                    h[101] / 1965.0 / h[103], h[102] / 1965.0 / h[103], h[103]);
+        if (h[107])
+            fprintf(stderr, "[block_sample] max+softmax+keys %.2f  sort %.2f  scan %.2f us (n=%llu)\n", h[104] / 1965.0 / h[107],
+                    h[105] / 1965.0 / h[107], h[106] / 1965.0 / h[107], h[107]);
         for (int c = 0; c < 2; ++c)
             for (int k = 0; k < 7; ++k) {
                 const unsigned long long *e = h + c * 32 + k * 4;

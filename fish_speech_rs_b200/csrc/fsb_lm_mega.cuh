@@ -524,31 +524,57 @@ struct Mega {
             *reinterpret_cast<float4 *>(vss + off) = __ldcg(reinterpret_cast<const float4 *>(vcache + off));
         }
         __syncthreads();
+        // one warp per (row, head): lane = (position j = lane / 4, 16 of the 64 dims); all positions at once
+        const int j = lane >> 2, sub = lane & 3;
+        const bool valid = j < npos;
         for (int item = warp; item < NB * p.H; item += kMegaWarps) {
             const int b = item / p.H, h = item - b * p.H;
-            float o0 = 0.f, o1 = 0.f;
-            if (b < p.nb) {
-                const int kvh = h / n_rep;
-                const float q0 = qs[b * Hhd + h * p.hd + lane], q1 = qs[b * Hhd + h * p.hd + lane + 32];
-                const float *kb = kss + ((size_t)b * p.KV + kvh) * p.fast_len * p.hd;
-                const float *vb = vss + ((size_t)b * p.KV + kvh) * p.fast_len * p.hd;
-                float m = -INFINITY, l = 0.f;
-                for (int j = 0; j < npos; ++j) {
-                    float dd = q0 * (kb[j * p.hd + lane] * scale);
-                    dd = fmaf(q1, kb[j * p.hd + lane + 32] * scale, dd);
-                    dd = warp_sum(dd);
-                    const float m_new = fmaxf(m, dd);
-                    const float corr = expf(m - m_new), pj = expf(dd - m_new);
-                    l = fmaf(l, corr, pj);
-                    o0 = fmaf(o0, corr, pj * vb[j * p.hd + lane]);
-                    o1 = fmaf(o1, corr, pj * vb[j * p.hd + lane + 32]);
-                    m = m_new;
-                }
-                o0 /= l;
-                o1 /= l;
+            if (b >= p.nb) {
+                xs[b * Hhd + h * p.hd + lane] = 0.f;
+                xs[b * Hhd + h * p.hd + lane + 32] = 0.f;
+                continue;
             }
-            xs[b * Hhd + h * p.hd + lane] = o0;
-            xs[b * Hhd + h * p.hd + lane + 32] = o1;
+            const int kvh = h / n_rep;
+            const float *qp = qs + b * Hhd + h * p.hd + sub * 4;
+            const float *kr = kss + (((size_t)b * p.KV + kvh) * p.fast_len + (valid ? j : 0)) * p.hd + sub * 4;
+            const float *vr = vss + (((size_t)b * p.KV + kvh) * p.fast_len + (valid ? j : 0)) * p.hd + sub * 4;
+            float dot = 0.f;
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+                const float4 qv = *reinterpret_cast<const float4 *>(qp + jj * 16);
+                const float4 kk = *reinterpret_cast<const float4 *>(kr + jj * 16);
+                dot = fmaf(qv.x, kk.x * scale, dot);
+                dot = fmaf(qv.y, kk.y * scale, dot);
+                dot = fmaf(qv.z, kk.z * scale, dot);
+                dot = fmaf(qv.w, kk.w * scale, dot);
+            }
+            dot += __shfl_xor_sync(0xffffffffu, dot, 1);
+            dot += __shfl_xor_sync(0xffffffffu, dot, 2);
+            const float sc = valid ? dot : -INFINITY;
+            float m = sc;
+#pragma unroll
+            for (int off = 4; off < 32; off <<= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+            const float pj = valid ? expf(sc - m) : 0.f;
+            float l = pj;
+#pragma unroll
+            for (int off = 4; off < 32; off <<= 1) l += __shfl_xor_sync(0xffffffffu, l, off);
+            float o[16];
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+                const float4 vv = *reinterpret_cast<const float4 *>(vr + jj * 16);
+                o[jj * 4 + 0] = pj * vv.x; o[jj * 4 + 1] = pj * vv.y; o[jj * 4 + 2] = pj * vv.z; o[jj * 4 + 3] = pj * vv.w;
+            }
+#pragma unroll
+            for (int off = 4; off < 32; off <<= 1)
+#pragma unroll
+                for (int i = 0; i < 16; ++i) o[i] += __shfl_xor_sync(0xffffffffu, o[i], off);
+            if (j == 0) {
+                float *dst = xs + b * Hhd + h * p.hd + sub * 4;
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj)
+                    *reinterpret_cast<float4 *>(dst + jj * 16) =
+                        make_float4(o[jj * 4 + 0] / l, o[jj * 4 + 1] / l, o[jj * 4 + 2] / l, o[jj * 4 + 3] / l);
+            }
         }
     }
 
@@ -839,19 +865,27 @@ struct Mega {
             const bool eos = s_eos[b] != 0;
             const int frame = s_frame[b];
             if (!eos) {
+                const bool tm = p.dbg != nullptr && tid == 0;
+                const long long c0 = tm ? clock64() : 0;
                 RepPenState *rp = s_rep + (size_t)b * C + cb;
                 if (frame > 0) {
                     if (tid == 0) rep_pen_update(rp, s_prev[b * 20 + 1 + cb]);
                     __syncthreads();
                 }
+                const long long c1 = tm ? clock64() : 0;
                 for (int i = tid; i < n; i += kMegaThreads) {
                     float v = __ldcg(p.logits + (size_t)b * p.ldl + i);
                     if (frame > 0 && ((rp->seen[i >> 5] >> (i & 31)) & 1u)) v = __fdiv_rn(v, st.sp.penalty);
                     vals[i] = v;
                 }
                 __syncthreads();
+                const long long c2 = tm ? clock64() : 0;
                 const float u = philox_uniform(st.sp.seed, (uint64_t)frame * (C + 1) + cb + 1, (uint32_t)b);
                 const int a = block_sample(vals, keys, sred, n, n_pad, st.sp, u);
+                if (tm) {
+                    const long long c3 = clock64();
+                    p.dbg[100] += c1 - c0; p.dbg[101] += c2 - c1; p.dbg[102] += c3 - c2; p.dbg[103] += 1;
+                }
                 if (tid == 0) {
                     s_cur[b * 20 + 1 + cb] = (uint32_t)a;
                     st.cur[b * (C + 1) + 1 + cb] = (uint32_t)a;
@@ -902,6 +936,7 @@ struct Mega {
             const int row = i / p.hd, d = i - row * p.hd, half = p.hd / 2;
             csf_s[i] = d < half ? p.cosT[(size_t)row * half + d] : p.sinT[(size_t)row * half + d - half];
         }
+        if (blockIdx.x == 0 && tid == 0 && p.dbg) g_sample_dbg = p.dbg + 104;
         if (blockIdx.x == 0) {
             for (int i = tid; i < p.nb; i += kMegaThreads) pos_s[i] = p.st.pos[i];
             load_sampler_state();

@@ -78,20 +78,24 @@ __device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned long long v,
     return ((unsigned long long)hi << 32) | lo;
 }
 
-__device__ inline int block_sample(float *vals, unsigned long long *keys, float *red, int n, int n_pad,
-                                   const SampleParams &sp, float u) {
+__device__ unsigned long long *g_sample_dbg = nullptr;  // optional cycle counters (debug builds of the megakernel)
+
+template <int E>
+__device__ __forceinline__ int block_sample_t(float *vals, unsigned long long *keys, float *red, int n, int n_pad,
+                                              const SampleParams &sp, float u) {
+    const bool tm_ = g_sample_dbg != nullptr && threadIdx.x == 0;
+    const long long q0 = tm_ ? clock64() : 0;
     const int tid = threadIdx.x, nthreads = blockDim.x;
     const int lane = tid & 31, warp = tid >> 5, nwarps = nthreads >> 5;
-    const int n_eff = max(n_pad, nthreads);
-    const int E = n_eff / nthreads;  // elements per thread: index e * nthreads + tid
-    float v[kSampleMaxE];
+    const int n_eff = E * nthreads;  // elements per thread E: index e * nthreads + tid
+    float v[E];
     // ---- max (and first argmax) ----
     float best = -INFINITY;
     int best_i = 0x7fffffff;
 #pragma unroll
-    for (int e = 0; e < kSampleMaxE; ++e) {
+    for (int e = 0; e < E; ++e) {
         const int i = e * nthreads + tid;
-        v[e] = (e < E && i < n) ? vals[i] : -INFINITY;
+        v[e] = (i < n) ? vals[i] : -INFINITY;
         if (v[e] > best) { best = v[e]; best_i = i; }  // ascending i: the first maximum wins
     }
 #pragma unroll
@@ -123,11 +127,9 @@ __device__ inline int block_sample(float *vals, unsigned long long *keys, float 
     const float mx = __fmul_rn(best, sp.inv_temp);
     float s = 0.f;
 #pragma unroll
-    for (int e = 0; e < kSampleMaxE; ++e) {
-        if (e < E) {
-            v[e] = (e * nthreads + tid < n) ? expf(__fsub_rn(__fmul_rn(v[e], sp.inv_temp), mx)) : 0.f;
-            s += v[e];
-        }
+    for (int e = 0; e < E; ++e) {
+        v[e] = (e * nthreads + tid < n) ? expf(__fsub_rn(__fmul_rn(v[e], sp.inv_temp), mx)) : 0.f;
+        s += v[e];
     }
     s = warp_sum(s);
     __syncthreads();  // red[] reads above are done
@@ -136,16 +138,17 @@ __device__ inline int block_sample(float *vals, unsigned long long *keys, float 
     float denom = lane < nwarps ? red[lane] : 0.f;
     denom = warp_sum(denom);
     // keys: (~prob bits) << 32 | index; ascending sort == prob desc, index asc
-    unsigned long long key[kSampleMaxE];
+    unsigned long long key[E];
 #pragma unroll
-    for (int e = 0; e < kSampleMaxE; ++e) {
+    for (int e = 0; e < E; ++e) {
         const int i = e * nthreads + tid;
         key[e] = ~0ull;
-        if (e < E && i < n) {
+        if (i < n) {
             const float p = v[e] / denom;
             key[e] = ((unsigned long long)(~__float_as_uint(p)) << 32) | (unsigned)i;
         }
     }
+    const long long q1 = tm_ ? clock64() : 0;
     // ---- bitonic sort over n_eff keys ----
     int buf = 0;
     for (int k = 2; k <= n_eff; k <<= 1) {
@@ -153,11 +156,11 @@ __device__ inline int block_sample(float *vals, unsigned long long *keys, float 
             if (j >= nthreads) {
                 const int je = j / nthreads;  // partner element inside the same thread
 #pragma unroll
-                for (int jj = 1; jj < kSampleMaxE; jj <<= 1) {  // compile-time register indices
+                for (int jj = 1; jj < E; jj <<= 1) {  // compile-time register indices
                     if (je == jj) {
 #pragma unroll
-                        for (int e = 0; e < kSampleMaxE; ++e) {
-                            if ((e & jj) == 0 && (e | jj) < E) {
+                        for (int e = 0; e < E; ++e) {
+                            if ((e & jj) == 0) {
                                 const int i = e * nthreads + tid;
                                 const bool up = (i & k) == 0;
                                 const unsigned long long a = key[e], b = key[e | jj];
@@ -169,30 +172,25 @@ __device__ inline int block_sample(float *vals, unsigned long long *keys, float 
             } else if (j >= 32) {
                 unsigned long long *kb = keys + (size_t)buf * n_eff;
 #pragma unroll
-                for (int e = 0; e < kSampleMaxE; ++e)
-                    if (e < E) kb[e * nthreads + tid] = key[e];
+                for (int e = 0; e < E; ++e) kb[e * nthreads + tid] = key[e];
                 __syncthreads();
 #pragma unroll
-                for (int e = 0; e < kSampleMaxE; ++e) {
-                    if (e < E) {
-                        const int i = e * nthreads + tid;
-                        const unsigned long long o = kb[i ^ j];
-                        const bool up = (i & k) == 0, lower = (i & j) == 0;
-                        const bool take_min = up == lower;
-                        key[e] = take_min ? (o < key[e] ? o : key[e]) : (o > key[e] ? o : key[e]);
-                    }
+                for (int e = 0; e < E; ++e) {
+                    const int i = e * nthreads + tid;
+                    const unsigned long long o = kb[i ^ j];
+                    const bool up = (i & k) == 0, lower = (i & j) == 0;
+                    const bool take_min = up == lower;
+                    key[e] = take_min ? (o < key[e] ? o : key[e]) : (o > key[e] ? o : key[e]);
                 }
                 buf ^= 1;
             } else {
 #pragma unroll
-                for (int e = 0; e < kSampleMaxE; ++e) {
-                    if (e < E) {
-                        const int i = e * nthreads + tid;
-                        const unsigned long long o = shfl_xor_u64(key[e], j);
-                        const bool up = (i & k) == 0, lower = (i & j) == 0;
-                        const bool take_min = up == lower;
-                        key[e] = take_min ? (o < key[e] ? o : key[e]) : (o > key[e] ? o : key[e]);
-                    }
+                for (int e = 0; e < E; ++e) {
+                    const int i = e * nthreads + tid;
+                    const unsigned long long o = shfl_xor_u64(key[e], j);
+                    const bool up = (i & k) == 0, lower = (i & j) == 0;
+                    const bool take_min = up == lower;
+                    key[e] = take_min ? (o < key[e] ? o : key[e]) : (o > key[e] ? o : key[e]);
                 }
             }
         }
@@ -201,11 +199,11 @@ __device__ inline int block_sample(float *vals, unsigned long long *keys, float 
     {
         unsigned long long *kb = keys + (size_t)buf * n_eff;
 #pragma unroll
-        for (int e = 0; e < kSampleMaxE; ++e)
-            if (e < E) kb[e * nthreads + tid] = key[e];
+        for (int e = 0; e < E; ++e) kb[e * nthreads + tid] = key[e];
         __syncthreads();
         keys = kb;
     }
+    const long long q2 = tm_ ? clock64() : 0;
     // ---- top-k -> top-p -> multinomial on warp 0 ----
     if (warp == 0) {
         auto wgt = [&](int i) { return __uint_as_float(~(uint32_t)(keys[i] >> 32)); };
@@ -269,7 +267,24 @@ __device__ inline int block_sample(float *vals, unsigned long long *keys, float 
     __syncthreads();
     int r = red_i[0];
     __syncthreads();
+    if (tm_) {
+        const long long q3 = clock64();
+        g_sample_dbg[0] += q1 - q0; g_sample_dbg[1] += q2 - q1; g_sample_dbg[2] += q3 - q2; g_sample_dbg[3] += 1;
+    }
     return r;
+}
+
+// elements per thread is a compile-time constant of the sort network (a generic loop over "up to 8"
+// slots made the sampler issue-bound: 17 us of a 21 us draw)
+__device__ inline int block_sample(float *vals, unsigned long long *keys, float *red, int n, int n_pad,
+                                   const SampleParams &sp, float u) {
+    const int E = max(n_pad, (int)blockDim.x) / (int)blockDim.x;
+    switch (E) {
+        case 1: return block_sample_t<1>(vals, keys, red, n, n_pad, sp, u);
+        case 2: return block_sample_t<2>(vals, keys, red, n, n_pad, sp, u);
+        case 4: return block_sample_t<4>(vals, keys, red, n, n_pad, sp, u);
+        default: return block_sample_t<8>(vals, keys, red, n, n_pad, sp, u);
+    }
 }
 
 // Device-resident state of the frame loop (single_batch.rs:19-28 fields that the
