@@ -268,6 +268,15 @@ def run_ours(a):
         peaks, peak_kind = measured_peaks()
         value = frames_all / (dev_ms_max / 1e3)
         e2e = frames_all / (wall_ms_max / 1e3)
+        traffic, traffic_note = None, None
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_mega_traffic.json")))
+            if dom_n > 0 and a.dtype == "bf16":
+                # DRAM bytes per frame from the committed ncu capture x frames in this launch
+                traffic = (tr["dram_bytes_read"] + tr["dram_bytes_write"]) / tr["frames_in_launch"] * N
+                traffic_note = "ncu dram bytes per frame (%s) x %d frames; below the algorithmic bytes: fast-stack weights partly L2-resident (lts hit %.0f%%)" % (tr["source"], N, tr["lts_hit_rate_pct"])
+        except Exception:
+            pass
         n_l = max(dom_n, 1)
         avg_ms = dom_ms / n_l
         bytes_per_launch = dom_bytes / n_l
@@ -287,7 +296,7 @@ def run_ours(a):
             "gpu_launches": int(launches_all),
             "roofline": {"bound": "hbm", "kernel": dom_kernel,
                          "achieved": achieved, "peak": peaks["hbm_gbs"], "peak_kind": peak_kind, "unit": "GB/s",
-                         "frac": achieved / peaks["hbm_gbs"], "traffic": None,
+                         "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "traffic_note": traffic_note,
                          "launches_timed": int(dom_n),
                          "avg_launch_us": avg_ms * 1e3, "algorithmic_bytes_per_launch": bytes_per_launch,
                          "frame_bytes": wb,
