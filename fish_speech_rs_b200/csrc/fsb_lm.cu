@@ -8,11 +8,13 @@
 
 #include "fsb_lm_kernels.cuh"
 #include "fsb_lm_mega_params.cuh"
+#include "fsb_tc_gemm.cuh"
 
 namespace fsb {
 
 struct LayerW {
     DevTensor wqkv, wo, w1, w2, w3;
+    TcMap m_wqkv, m_wo, m_w1, m_w2, m_w3;  // TMA maps of the bf16 matrices (tcgen05 prefill)
     DevTensor attn_norm, ffn_norm;  // always f32
 };
 
@@ -61,6 +63,10 @@ struct fsb_lm {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
     fsb_lm_stats stats;
     uint64_t launches = 0;
+    // tcgen05 prefill (bf16 weights): split-activation buffers (hi | mid | lo) and their TMA maps per N tile
+    bool tc_ok = false;
+    __nv_bfloat16 *sp_xn = nullptr, *sp_att = nullptr, *sp_h = nullptr;
+    TcMap mx_xn[3], mx_att[3], mx_h[3];  // index: bn 32 / 64 / 128
     // persistent megakernel (decode_mode 2)
     MegaParams mp;
     bool mega_ok = false;
@@ -264,28 +270,57 @@ static int prefill_chunk(fsb_lm *lm, const uint32_t *toks_dev, int S_total, int 
         LAUNCH_CHECK(lm);
     }
     const float scale = 1.0f / sqrtf((float)hd);
+    const bool tc = lm->tc_ok;
+    const int bn = tc_pick_bn(S), bi = bn == 32 ? 0 : (bn == 64 ? 1 : 2);
+    const int seg = lm->prefill_rows;
+    cudaStream_t st = lm->stream;
     for (int l = 0; l < lm->NL; ++l) {
         const LayerW &L = lm->layers[l];
         rmsnorm_rows_kernel<<<(S + 3) / 4, 128, 0, lm->stream>>>(s.x, (const float *)L.attn_norm.ptr,
                                                                  lm->cfg.norm_eps, S, D, s.xn);
         LAUNCH_CHECK(lm);
-        FSB_TRY(gemm<EPI_STORE>(lm, s.xn, L.wqkv, nullptr, s.qkv, S, QKV, D));
+        if (tc) {
+            FSB_TRY(tc_split3(s.xn, lm->sp_xn, (size_t)S * D, (size_t)seg * D, st));
+            FSB_TRY(tc_gemm(L.m_wqkv, lm->mx_xn[bi], bn, s.qkv, nullptr, S, QKV, D, seg, QKV, st));
+            lm->launches += 2;
+        } else {
+            FSB_TRY(gemm<EPI_STORE>(lm, s.xn, L.wqkv, nullptr, s.qkv, S, QKV, D));
+        }
         rope_append_rows_kernel<<<S, 256, 0, lm->stream>>>(s.qkv, s.q, slow_k(lm, l), slow_v(lm, l), lm->cosT,
                                                            lm->sinT, b, pos0, rope_delta, H, KV, hd, lm->max_len);
         LAUNCH_CHECK(lm);
         attn_prefill_kernel<<<dim3((S + 3) / 4, H), 128, 0, lm->stream>>>(s.q, slow_k(lm, l), slow_v(lm, l), b, pos0,
                                                                           S, H, KV, hd, lm->max_len, scale, s.att);
         LAUNCH_CHECK(lm);
-        FSB_TRY(gemm<EPI_RESID>(lm, s.att, L.wo, s.x, s.x, S, D, H * hd));
+        if (tc) {
+            FSB_TRY(tc_split3(s.att, lm->sp_att, (size_t)S * H * hd, (size_t)seg * H * hd, st));
+            FSB_TRY(tc_gemm(L.m_wo, lm->mx_att[bi], bn, s.x, s.x, S, D, H * hd, seg, D, st));
+            lm->launches += 2;
+        } else {
+            FSB_TRY(gemm<EPI_RESID>(lm, s.att, L.wo, s.x, s.x, S, D, H * hd));
+        }
         rmsnorm_rows_kernel<<<(S + 3) / 4, 128, 0, lm->stream>>>(s.x, (const float *)L.ffn_norm.ptr, lm->cfg.norm_eps,
                                                                  S, D, s.xn);
         LAUNCH_CHECK(lm);
-        FSB_TRY(gemm<EPI_STORE>(lm, s.xn, L.w1, nullptr, s.g1, S, I, D));
-        FSB_TRY(gemm<EPI_STORE>(lm, s.xn, L.w3, nullptr, s.g3, S, I, D));
+        if (tc) {
+            FSB_TRY(tc_split3(s.xn, lm->sp_xn, (size_t)S * D, (size_t)seg * D, st));
+            FSB_TRY(tc_gemm(L.m_w1, lm->mx_xn[bi], bn, s.g1, nullptr, S, I, D, seg, I, st));
+            FSB_TRY(tc_gemm(L.m_w3, lm->mx_xn[bi], bn, s.g3, nullptr, S, I, D, seg, I, st));
+            lm->launches += 3;
+        } else {
+            FSB_TRY(gemm<EPI_STORE>(lm, s.xn, L.w1, nullptr, s.g1, S, I, D));
+            FSB_TRY(gemm<EPI_STORE>(lm, s.xn, L.w3, nullptr, s.g3, S, I, D));
+        }
         const size_t n = (size_t)S * I;
         swiglu_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, lm->stream>>>(s.g1, s.g3, n, s.g1);
         LAUNCH_CHECK(lm);
-        FSB_TRY(gemm<EPI_RESID>(lm, s.g1, L.w2, s.x, s.x, S, D, I));
+        if (tc) {
+            FSB_TRY(tc_split3(s.g1, lm->sp_h, n, (size_t)seg * I, st));
+            FSB_TRY(tc_gemm(L.m_w2, lm->mx_h[bi], bn, s.x, s.x, S, D, I, seg, D, st));
+            lm->launches += 2;
+        } else {
+            FSB_TRY(gemm<EPI_RESID>(lm, s.g1, L.w2, s.x, s.x, S, D, I));
+        }
     }
     return FSB_OK;
 }
@@ -491,6 +526,35 @@ static int mega_setup(fsb_lm *lm) {
     return FSB_OK;
 }
 
+// tcgen05 prefill: bf16 weights only (fp32 weights keep the CUDA-core GEMM: parity mode)
+static int tc_setup(fsb_lm *lm) {
+    lm->tc_ok = false;
+    if (lm->wdt != FSB_BF16 || getenv("FSB_NO_TCGEN05")) return FSB_OK;
+    const int D = lm->D, I = lm->I, Hhd = lm->H * lm->hd, QKV = lm->QKV, M = lm->prefill_rows;
+    if (D % 64 || I % 64 || Hhd % 64 || QKV % 128 || D % 128 || I % 128) return FSB_OK;
+    FSB_TRY(dev_alloc(lm, &lm->sp_xn, (size_t)3 * M * D));
+    FSB_TRY(dev_alloc(lm, &lm->sp_att, (size_t)3 * M * Hhd));
+    FSB_TRY(dev_alloc(lm, &lm->sp_h, (size_t)3 * M * I));
+    FSB_CUDA_OK(cudaMemset(lm->sp_xn, 0, (size_t)3 * M * D * 2));
+    FSB_CUDA_OK(cudaMemset(lm->sp_att, 0, (size_t)3 * M * Hhd * 2));
+    FSB_CUDA_OK(cudaMemset(lm->sp_h, 0, (size_t)3 * M * I * 2));
+    const int bns[3] = {32, 64, 128};
+    for (int i = 0; i < 3; ++i) {
+        FSB_TRY(tc_make_map_bf16(&lm->mx_xn[i], lm->sp_xn, 3 * M, D, bns[i]));
+        FSB_TRY(tc_make_map_bf16(&lm->mx_att[i], lm->sp_att, 3 * M, Hhd, bns[i]));
+        FSB_TRY(tc_make_map_bf16(&lm->mx_h[i], lm->sp_h, 3 * M, I, bns[i]));
+    }
+    for (auto &L : lm->layers) {
+        FSB_TRY(tc_make_map_bf16(&L.m_wqkv, L.wqkv.ptr, QKV, D, 128));
+        FSB_TRY(tc_make_map_bf16(&L.m_wo, L.wo.ptr, D, Hhd, 128));
+        FSB_TRY(tc_make_map_bf16(&L.m_w1, L.w1.ptr, I, D, 128));
+        FSB_TRY(tc_make_map_bf16(&L.m_w3, L.w3.ptr, I, D, 128));
+        FSB_TRY(tc_make_map_bf16(&L.m_w2, L.w2.ptr, D, I, 128));
+    }
+    lm->tc_ok = true;
+    return FSB_OK;
+}
+
 static void precompute_freqs(const fsb_model_args &c, int max_len, std::vector<float> *cosv, std::vector<float> *sinv) {
     // dual_ar.rs:168-186: theta_i = 1 / base^(i/n) in f32, idx_theta = pos * theta (f32 product), cos/sin.
     // Transcendentals in f64 rounded once to f32 (== correctly rounded f32), as in oracle/dual_ar.py.
@@ -620,6 +684,7 @@ static int lm_create_impl(fsb_lm *lm, const fsb_tensor *w, size_t n) {
     FSB_REQUIRE(std::max(lm->D, lm->I) * 32 <= 227 * 1024, FSB_ERR_UNSUPPORTED, "dim/intermediate_size too large");
     FSB_CUDA_OK(init_gemv_attrs(std::max(lm->D, lm->I)));
     FSB_TRY(mega_setup(lm));
+    FSB_TRY(tc_setup(lm));
     FSB_CUDA_OK(cudaStreamSynchronize(st));
     return FSB_OK;
 }

@@ -1,0 +1,278 @@
+// tcgen05 + TMA + TMEM GEMM for the backbone's dense QKV / O / FFN projections at S > 1 (prefill).
+//
+//   C[p, n] = sum_k W[n, k] * X[p, k]  (+ resid[p, n])        W: (N, K) bf16 row-major (the checkpoint layout)
+//
+// replaces the `Linear` call sites of dual_ar.rs:160-165,289,383 when seq_len > 1.
+//
+// Operands are SWAPPED with respect to the textbook form: the weight rows fill the MMA M dimension
+// (128 per CTA) and the prompt positions are the MMA N dimension (BN = 32 / 64 / 128), so the same
+// kernel shape serves short prompts without wasting the 128-row datapath.
+//
+// Precision: the activations stay fp32-accurate.  X arrives split into three bf16 terms
+// (x = hi + mid + lo, each the bf16 rounding of the remaining residual: 24 mantissa bits in total) and
+// the three partial products are accumulated into the same TMEM tile.  A bf16 x bf16 product is exact in
+// fp32, so the result equals the fp32-activation FMA path up to accumulation order -- the parity
+// tests against the oracle keep their 1e-3 tolerance, and greedy token ids are unchanged.
+//
+// Structure (one CTA = one 128 x BN output tile, 192 threads):
+//   warp 0 / lane 0 : TMA producer   cp.async.bulk.tensor.2d (128B swizzle) -> 4-stage smem ring, mbarrier expect_tx
+//   warp 1 / lane 0 : MMA issuer     tcgen05.mma.cta_group::1.kind::f16, accumulators in TMEM, tcgen05.commit -> mbarrier
+//   warps 2..5      : epilogue       tcgen05.ld 32x32b -> registers -> (+ residual) -> coalesced fp32 stores
+#include <cuda.h>
+
+#include "fsb_tc_gemm.cuh"
+
+namespace fsb {
+
+namespace {
+
+constexpr int kBM = 128, kBK = 64, kTcThreads = 192;
+constexpr int stages_for(int bn) { return bn >= 128 ? 3 : 4; }
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void *smem, const CUtensorMap *map, uint64_t *bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            smem_u32(smem)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+// K-major operand tile [rows][64 bf16] with the 128-byte swizzle: 8-row x 128 B atoms, 1024 B between atoms
+__device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);       // start address
+    d |= (uint64_t)0 << 16;                           // leading byte offset: one swizzle atom along K
+    d |= (uint64_t)((1024 >> 4) & 0x3FFF) << 32;      // stride byte offset between 8-row groups
+    d |= (uint64_t)1 << 46;                           // descriptor version (sm_100)
+    d |= (uint64_t)2 << 61;                           // SWIZZLE_128B
+    return d;
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kTcThreads, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmX, float *__restrict__ C,
+               const float *resid, int P, int N, int K, int x_seg_rows, int ldc) {
+    constexpr int A_BYTES = kBM * kBK * 2, B_BYTES = BN * kBK * 2, STAGE = A_BYTES + 3 * B_BYTES;
+    constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+    constexpr int kStages = stages_for(BN);
+    extern __shared__ uint8_t tc_smem_raw[];
+    // the 128-byte swizzle atoms need 1024-byte aligned tiles
+    uint8_t *tc_smem = tc_smem_raw + ((1024u - (smem_u32(tc_smem_raw) & 1023u)) & 1023u);
+    uint64_t *full = reinterpret_cast<uint64_t *>(tc_smem + kStages * STAGE);
+    uint64_t *empty = full + kStages;
+    uint64_t *tmem_full = empty + kStages;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_full + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n0 = blockIdx.x * kBM, p0 = blockIdx.y * BN;
+    const int nk = K / kBK;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(full + s, 1);
+            mbar_init(empty + s, 1);
+        }
+        mbar_init(tmem_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "n"(TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0 && lane == 0) {
+        // ---- TMA producer
+        for (int kb = 0; kb < nk; ++kb) {
+            const int s = kb % kStages;
+            mbar_wait(empty + s, ((kb / kStages) & 1) ^ 1);
+            uint8_t *st = tc_smem + (size_t)s * STAGE;
+            mbar_expect_tx(full + s, STAGE);
+            tma_load_2d(st, &tmW, full + s, kb * kBK, n0);
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+                tma_load_2d(st + A_BYTES + i * B_BYTES, &tmX, full + s, kb * kBK, i * x_seg_rows + p0);
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ---- MMA issuer: D (TMEM, 128 lanes x BN fp32 columns) += W_tile (M = 128) x X_tile^T (N = BN), K = 16 per instruction
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+        for (int kb = 0; kb < nk; ++kb) {
+            const int s = kb % kStages;
+            mbar_wait(full + s, (kb / kStages) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t a_addr = smem_u32(tc_smem + (size_t)s * STAGE);
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                const uint32_t b_addr = a_addr + A_BYTES + i * B_BYTES;
+#pragma unroll
+                for (int k = 0; k < kBK / 16; ++k)
+                    umma_bf16(tmem_base, umma_desc_k_sw128(a_addr + k * 32), umma_desc_k_sw128(b_addr + k * 32), idesc,
+                              (kb | i | k) != 0 ? 1u : 0u);
+            }
+            umma_commit(empty + s);  // frees the smem stage once these MMAs have read it
+        }
+        umma_commit(tmem_full);
+    } else if (warp >= 2) {
+        // ---- epilogue: warp (w % 4) owns TMEM lanes [32 (w % 4), +32) == weight rows of the tile
+        mbar_wait(tmem_full, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int q = warp & 3;
+        const int n = n0 + q * 32 + lane;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 16) {
+            uint32_t r[16];
+            tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+            if (n < N) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int pp = p0 + c0 + j;
+                    if (pp < P) {
+                        float v = __uint_as_float(r[j]);
+                        if (resid) v = __fadd_rn(resid[(size_t)pp * ldc + n], v);
+                        C[(size_t)pp * ldc + n] = v;
+                    }
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    }
+}
+
+// x (M, K) f32 -> three stacked bf16 matrices (hi | mid | lo), segment stride seg_rows
+__global__ void split3_rows_kernel(const float *__restrict__ x, __nv_bfloat16 *__restrict__ out, size_t n, size_t seg_elems) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float v = x[i];
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    const float r1 = v - __bfloat162float(hi);
+    const __nv_bfloat16 mid = __float2bfloat16_rn(r1);
+    const float r2 = r1 - __bfloat162float(mid);
+    out[i] = hi;
+    out[seg_elems + i] = mid;
+    out[2 * seg_elems + i] = __float2bfloat16_rn(r2);
+}
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_encodeTiled get_encode() {
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_encodeTiled>(p);
+    }
+    return fn;
+}
+
+}  // namespace
+
+int tc_make_map_bf16(TcMap *out, const void *base, int rows, int K, int box_rows) {
+    PFN_encodeTiled enc = get_encode();
+    FSB_REQUIRE(enc != nullptr, FSB_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+    FSB_REQUIRE(K % kBK == 0, FSB_ERR_UNSUPPORTED, "tcgen05 GEMM needs K %% 64 == 0 (K = %d)", K);
+    static_assert(sizeof(TcMap) >= sizeof(CUtensorMap), "TcMap too small");
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+    cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(reinterpret_cast<CUtensorMap *>(out), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), dims,
+                     strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    FSB_REQUIRE(r == CUDA_SUCCESS, FSB_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return FSB_OK;
+}
+
+int tc_pick_bn(int P) { return P <= 32 ? 32 : (P <= 256 ? 64 : 128); }
+
+int tc_split3(const float *x, __nv_bfloat16 *out, size_t n, size_t seg_elems, cudaStream_t st) {
+    if (n == 0) return FSB_OK;
+    split3_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, out, n, seg_elems);
+    FSB_CUDA_OK(cudaGetLastError());
+    return FSB_OK;
+}
+
+template <int BN>
+static int launch_bn(const TcMap &mw, const TcMap &mx, float *C, const float *resid, int P, int N, int K, int x_seg_rows,
+                     int ldc, cudaStream_t st) {
+    constexpr int STAGE = kBM * kBK * 2 + 3 * BN * kBK * 2;
+    const size_t smem = (size_t)stages_for(BN) * STAGE + 256 + 1024;  // + barriers + alignment slack
+    static bool attr_done = false;
+    if (!attr_done) {
+        FSB_CUDA_OK(cudaFuncSetAttribute(tc_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done = true;
+    }
+    dim3 grid((N + kBM - 1) / kBM, (P + BN - 1) / BN);
+    tc_gemm_kernel<BN><<<grid, kTcThreads, smem, st>>>(*reinterpret_cast<const CUtensorMap *>(&mw),
+                                                      *reinterpret_cast<const CUtensorMap *>(&mx), C, resid, P, N, K,
+                                                      x_seg_rows, ldc);
+    FSB_CUDA_OK(cudaGetLastError());
+    return FSB_OK;
+}
+
+int tc_gemm(const TcMap &mw, const TcMap &mx, int bn, float *C, const float *resid, int P, int N, int K, int x_seg_rows,
+            int ldc, cudaStream_t st) {
+    switch (bn) {
+        case 32: return launch_bn<32>(mw, mx, C, resid, P, N, K, x_seg_rows, ldc, st);
+        case 64: return launch_bn<64>(mw, mx, C, resid, P, N, K, x_seg_rows, ldc, st);
+        case 128: return launch_bn<128>(mw, mx, C, resid, P, N, K, x_seg_rows, ldc, st);
+        default: set_error("tc_gemm: unsupported BN %d", bn); return FSB_ERR_INVALID;
+    }
+}
+
+}  // namespace fsb

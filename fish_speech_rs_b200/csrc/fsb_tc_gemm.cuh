@@ -1,0 +1,22 @@
+// tcgen05 / TMA / TMEM GEMM used by prefill (fsb_tc_gemm.cu).
+#pragma once
+#include "fsb_common.cuh"
+
+namespace fsb {
+
+// opaque, 64-byte aligned storage for a CUtensorMap (128 B)
+struct alignas(64) TcMap {
+    unsigned char bytes[128];
+};
+
+// tensor map of a row-major (rows, K) bf16 matrix, box = (64 k, box_rows), 128-byte swizzle
+int tc_make_map_bf16(TcMap *out, const void *base, int rows, int K, int box_rows);
+// N tile (prompt positions per CTA) for a prompt chunk of P rows
+int tc_pick_bn(int P);
+// x (n elements, f32) -> hi | mid | lo bf16 copies at element offsets 0, seg_elems, 2 * seg_elems
+int tc_split3(const float *x, __nv_bfloat16 *out, size_t n, size_t seg_elems, cudaStream_t st);
+// C[p, n] = sum_k W[n, k] * (hi + mid + lo)[p, k] (+ resid[p, n]); mx built with box_rows == bn
+int tc_gemm(const TcMap &mw, const TcMap &mx, int bn, float *C, const float *resid, int P, int N, int K, int x_seg_rows,
+            int ldc, cudaStream_t st);
+
+}  // namespace fsb

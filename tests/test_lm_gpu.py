@@ -184,6 +184,30 @@ def test_bf16_weights_mode(tiny_lm):
     gpu.close()
 
 
+@pytest.mark.parametrize("P", [30, 200, 300])  # N tiles of 32, 64 and 128 prompt positions
+def test_tcgen05_prefill_matches_fma_prefill_and_oracle(tiny_lm, P, monkeypatch):
+    """bf16-weight prefill runs the dense projections on tcgen05 (TMA + TMEM, activations split into three
+    bf16 terms): same hidden state / logits as the CUDA-core FMA prefill (1e-4) and as the oracle (1e-3)."""
+    cfg, tok, _ = tiny_lm
+    w = synth.make_lm_weights(cfg, seed=1234, round_bf16=True)
+    prompt = synth.make_prompt(cfg, tok, P, seed=8)
+    tc = DualARTransformer(w, cfg, tok, dtype="bf16", max_seq_len=512)
+    l_tc, h_tc = tc.forward_generate(prompt[None], 0)
+    tc.close()
+    monkeypatch.setenv("FSB_NO_TCGEN05", "1")
+    fma = DualARTransformer(w, cfg, tok, dtype="bf16", max_seq_len=512)
+    l_fma, h_fma = fma.forward_generate(prompt[None], 0)
+    fma.close()
+    assert not np.array_equal(h_tc, h_fma)  # really two different code paths
+    np.testing.assert_allclose(h_tc, h_fma, atol=1e-4, rtol=0)
+    np.testing.assert_allclose(l_tc, l_fma, atol=1e-4, rtol=0)
+    ora = oracle_model(cfg, tok, w)
+    with torch.no_grad():
+        lo, ho = ora.forward_generate(t64(prompt)[None], 0)
+    np.testing.assert_allclose(h_tc, ho.numpy(), atol=ATOL, rtol=0)
+    np.testing.assert_allclose(l_tc, lo.numpy(), atol=ATOL, rtol=0)
+
+
 def test_fish14_legacy_slow_token(tiny_lm):
     """Fish <= 1.4 (Q8): slow token is PAD until the budget ends (fixed_len), fast codes greedy."""
     cfg, _, w = tiny_lm
