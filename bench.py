@@ -36,6 +36,12 @@ CONFIGS = {
                  desc="Fish 1.5 B=1 temp=0.7 top_p=0.8 10 s utterance (P=384, N=216)"),
     "cfg3": dict(version="1.5", batch=16, prompt_lens=lambda b: [300 + 28 * i for i in range(b)], frames=216,
                  temp=0.7, top_p=0.8, desc="Fish 1.5 B=16 mixed prompts 300..720, N=216 each"),
+    "b2": dict(version="1.5", batch=2, prompt_lens=lambda b: [384] * b, frames=64, temp=0.7, top_p=0.8,
+               desc="tuning probe: B=2, P=384, N=64"),
+    "b4": dict(version="1.5", batch=4, prompt_lens=lambda b: [384] * b, frames=64, temp=0.7, top_p=0.8,
+               desc="tuning probe: B=4, P=384, N=64"),
+    "b8": dict(version="1.5", batch=8, prompt_lens=lambda b: [384] * b, frames=64, temp=0.7, top_p=0.8,
+               desc="tuning probe: B=8, P=384, N=64"),
     "cfg5": dict(version="1.5", batch=32, prompt_lens=lambda b: [384] * b, frames=1292, temp=0.7, top_p=0.8,
                  desc="Fish 1.5 B=32/GPU long-form 60 s (P=384, N=1292)"),
 }
@@ -189,7 +195,7 @@ def run_ours(a):
     lm_w, codec_w = make_weights(c["version"])
     max_len = max(p.shape[1] for p in prompts) + N + 8
     lm = DualARTransformer(lm_w, mcfg, tok, fish_version=c["version"], device=local, dtype=a.dtype, max_batch=B,
-                           max_seq_len=max_len)
+                           max_seq_len=max_len, decode_mode=a.decode_mode)
     codec = FireflyCodec(codec_w, fish_version=c["version"], device=local, max_frames=N)
     if not (a.cpu_baseline and rank == 0):
         del lm_w
@@ -325,6 +331,7 @@ def main():
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     ap.add_argument("--cpu-sample-frames", type=int, default=16)
+    ap.add_argument("--decode-mode", type=int, default=0, help="0 auto, 1 per-op kernels + CUDA graph, 2 megakernel")
     ap.add_argument("--frames", type=int, default=0, help="override the frame count (profiling runs only)")
     a = ap.parse_args()
     if a.frames:

@@ -448,17 +448,29 @@ static size_t mega_smem_bytes(const fsb_lm *lm, int NB, int *xs_floats, int *val
     return ((size_t)*xs_floats + (size_t)*val_floats + aux + 2ull * kMegaChunk * kMegaKvStride) * sizeof(float);
 }
 
-static int mega_launch(fsb_lm *lm, int nb, int nframes, bool first_is_tail) {
+// rows [row0, row0 + nb) of the current batch: every per-row buffer is addressed relative to row0
+static int mega_launch(fsb_lm *lm, int row0, int group_index, int nb, int nframes, bool first_is_tail) {
     MegaParams mp = lm->mp;
     mp.nb = nb;
     mp.nframes = nframes;
     mp.first_is_tail = first_is_tail ? 1 : 0;
+    mp.row0 = row0;
     const int NB = mega_nb_template(nb);
     int xs_floats = 0, val_floats = 0;
     const size_t smem = mega_smem_bytes(lm, NB, &xs_floats, &val_floats);
     mp.xs_floats = xs_floats;
     mp.val_floats = val_floats;
     mp.st = lm->h_st;
+    const int C1 = lm->C + 1;
+    const size_t r = (size_t)row0;
+    mp.x += r * lm->D; mp.fx += r * lm->D; mp.q += r * lm->H * lm->hd; mp.h += r * lm->I;
+    mp.partial += r * lm->H * 2 * mp.n_chunks_max * (lm->hd + 4);
+    mp.logits += r * mp.ldl;
+    mp.kc += r * lm->KV * lm->max_len * lm->hd; mp.vc += r * lm->KV * lm->max_len * lm->hd;
+    mp.fkc += r * lm->KV * lm->fast_len * lm->hd; mp.fvc += r * lm->KV * lm->fast_len * lm->hd;
+    mp.st.pos += r; mp.st.active += r; mp.st.eos += r; mp.st.frame += r; mp.st.max_frames += r;
+    mp.st.cur += r * C1; mp.st.prev += r * C1; mp.st.out += r * mp.st.out_cap * C1; mp.st.rep += r * lm->C;
+    mp.st.n_active += group_index;  // one live-row counter per group
     FSB_CUDA_OK(cudaMemsetAsync(lm->mega_bar, 0, sizeof(unsigned int), lm->stream));
     FSB_CUDA_OK(lm->wdt == FSB_F32 ? mega_launch_f32(NB, mp, lm->mega_grid, smem, lm->stream)
                                    : mega_launch_bf16(NB, mp, lm->mega_grid, smem, lm->stream));
@@ -658,7 +670,7 @@ static int lm_create_impl(fsb_lm *lm, const fsb_tensor *w, size_t n) {
     FSB_TRY(dev_alloc(lm, &g.eos, B));
     FSB_TRY(dev_alloc(lm, &g.frame, B));
     FSB_TRY(dev_alloc(lm, &g.max_frames, B));
-    FSB_TRY(dev_alloc(lm, &g.n_active, 1));
+    FSB_TRY(dev_alloc(lm, &g.n_active, B));  // [0]: whole batch (per-op path); [g]: group g of 8 rows (megakernel)
     FSB_TRY(dev_alloc(lm, &g.cur, (size_t)B * (C + 1)));
     FSB_TRY(dev_alloc(lm, &g.prev, (size_t)B * (C + 1)));
     g.out_cap = lm->max_len + 2;
@@ -807,12 +819,16 @@ static int generate_impl(fsb_lm *lm, const uint32_t *const *prompts, const int32
     }
     int total_max = 0;
     for (int b = 0; b < bsz; ++b) total_max = std::max(total_max, max_frames[b]);
-    bool use_mega = lm->mega_ok && bsz <= 8 && lm->opt.decode_mode != 1 && !lm->profile;
+    bool use_mega = lm->mega_ok && lm->opt.decode_mode != 1 && !lm->profile;
+    int group = 8;  // rows per megakernel launch: the largest batch template whose shared memory fits
     if (use_mega) {
-        int xf, vf;
         cudaDeviceProp prop;
         FSB_CUDA_OK(cudaGetDeviceProperties(&prop, lm->opt.device));
-        use_mega = mega_smem_bytes(lm, mega_nb_template(bsz), &xf, &vf) <= (size_t)prop.sharedMemPerBlockOptin;
+        int xf, vf;
+        while (group > 1 && mega_smem_bytes(lm, group, &xf, &vf) > (size_t)prop.sharedMemPerBlockOptin) group /= 2;
+        use_mega = mega_smem_bytes(lm, group, &xf, &vf) <= (size_t)prop.sharedMemPerBlockOptin;
+        // auto mode: one launch only (rows beyond a group are better served by the per-op GEMV path)
+        if (lm->opt.decode_mode == 0 && bsz > group) use_mega = false;
     }
     FSB_REQUIRE(use_mega || lm->opt.decode_mode != 2 || lm->profile, FSB_ERR_UNSUPPORTED,
                 "decode_mode 2 (megakernel) needs bsz <= 8 and cooperative launch support");
@@ -821,7 +837,17 @@ static int generate_impl(fsb_lm *lm, const uint32_t *const *prompts, const int32
         // loop by itself once every row is finished (no host polling).  The prefill event sits
         // right before the launch, so frame 0's tail is accounted to the frame loop here.
         FSB_CUDA_OK(cudaEventRecord(lm->ev1, st));
-        FSB_TRY(mega_launch(lm, bsz, total_max, true));
+        // batches above 8 rows run as consecutive launches over groups of 8 rows (the kernel keeps one
+        // activation row per batch row in shared memory); each group has its own live-row counter
+        for (int r0 = 0, gi = 0; r0 < bsz; r0 += group, ++gi) {
+            const int nbg = std::min(group, bsz - r0);
+            int fmax_g = 0;
+            for (int b = r0; b < r0 + nbg; ++b) fmax_g = std::max(fmax_g, max_frames[b]);
+            hp[0] = nbg;
+            FSB_CUDA_OK(cudaMemcpyAsync(g.n_active + gi, hp, sizeof(int), cudaMemcpyHostToDevice, st));
+            FSB_CUDA_OK(cudaStreamSynchronize(st));  // hp is reused
+            FSB_TRY(mega_launch(lm, r0, gi, nbg, fmax_g, true));
+        }
     } else {
         {
             cudaGraphExec_t tg;
@@ -932,16 +958,19 @@ static int generate_impl(fsb_lm *lm, const uint32_t *const *prompts, const int32
         const uint64_t w_slow = es * (per_layer * lm->NL);
         const uint64_t w_tail = es * ((size_t)lm->n_slow_logits * lm->D +
                                       (size_t)lm->C * (per_layer * lm->NFL + (size_t)lm->CS * lm->D));
-        int fmax = 0;
-        uint64_t kv_bytes = 0;
-        for (int b = 0; b < bsz; ++b) {
-            fmax = std::max(fmax, frames[b]);
-            for (int f = 1; f < frames[b]; ++f)
-                kv_bytes += (uint64_t)(lm->kv_len[b] - (frames[b] - 1) + f) * lm->NL * 2 * lm->KV * lm->hd * sizeof(float);
+        uint64_t kv_bytes = 0, weight_bytes = 0;
+        for (int r0 = 0; r0 < bsz; r0 += group) {  // every group streams the weights once per frame it runs
+            int fmax = 0;
+            for (int b = r0; b < std::min(bsz, r0 + group); ++b) {
+                fmax = std::max(fmax, frames[b]);
+                for (int f = 1; f < frames[b]; ++f)
+                    kv_bytes += (uint64_t)(lm->kv_len[b] - (frames[b] - 1) + f) * lm->NL * 2 * lm->KV * lm->hd * sizeof(float);
+            }
+            weight_bytes += (uint64_t)fmax * w_tail + (uint64_t)std::max(fmax - 1, 0) * w_slow;
         }
         lm->stats.dominant_kernel_ms = ms_dec;
-        lm->stats.dominant_kernel_launches = 1;
-        lm->stats.dominant_kernel_bytes = (uint64_t)fmax * w_tail + (uint64_t)std::max(fmax - 1, 0) * w_slow + kv_bytes;
+        lm->stats.dominant_kernel_launches = (bsz + group - 1) / group;
+        lm->stats.dominant_kernel_bytes = weight_bytes + kv_bytes;
     }
     if (lm->profile) {
         double tot = 0;

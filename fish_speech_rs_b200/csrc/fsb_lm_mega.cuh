@@ -819,7 +819,7 @@ struct Mega {
         for (int b = 0; b < p.nb; ++b) {
             if (!s_active[b]) continue;
             const int frame = s_frame[b];
-            const float u = philox_uniform(st.sp.seed, (uint64_t)frame * (st.C + 1), (uint32_t)b);
+            const float u = philox_uniform(st.sp.seed, (uint64_t)frame * (st.C + 1), (uint32_t)(p.row0 + b));
             uint32_t tok;
             if (st.legacy_slow) {
                 const float eos_l = __ldcg(p.logits + (size_t)b * p.ldl), pad_l = __ldcg(p.logits + (size_t)b * p.ldl + 1);
@@ -880,7 +880,7 @@ struct Mega {
                 }
                 __syncthreads();
                 const long long c2 = tm ? clock64() : 0;
-                const float u = philox_uniform(st.sp.seed, (uint64_t)frame * (C + 1) + cb + 1, (uint32_t)b);
+                const float u = philox_uniform(st.sp.seed, (uint64_t)frame * (C + 1) + cb + 1, (uint32_t)(p.row0 + b));
                 const int a = block_sample(vals, keys, sred, n, n_pad, st.sp, u);
                 if (tm) {
                     const long long c3 = clock64();

@@ -37,6 +37,7 @@ struct MegaParams {
     GenState st;  // by value: every field is launch-constant (the arrays it points to are not)
     unsigned int *bar;
     int nb, nframes, first_is_tail;
+    int row0;  // global index of local row 0 (groups of <= 8 rows of a larger batch): Philox row = row0 + b
     uint32_t sem_start, sem_end;
     int has_end;
     int val_floats;  // capacity of the per-task result array (floats)

@@ -164,6 +164,23 @@ def test_decode_modes_agree_with_oracle(tiny_lm, mode):
     gpu.close()
 
 
+@pytest.mark.parametrize("mode", [0, 1])
+def test_batch_above_eight_rows(tiny_lm, mode):
+    """11 ragged rows: the megakernel runs them as groups of 8 + 3 (mode 0), the per-op path as two GEMV
+    groups (mode 1); every row must equal its bs=1 oracle generation (Philox row index = global row)."""
+    cfg, tok, w = tiny_lm
+    gpu = DualARTransformer(w, cfg, tok, max_batch=11, max_seq_len=128, decode_mode=mode)
+    ora = oracle_model(cfg, tok, w)
+    prompts = [synth.make_prompt(cfg, tok, 12 + 5 * i, seed=300 + i) for i in range(11)]
+    sa, so = SamplingArgs(0.7, 0.8, 256, 1.4, seed=9), osamp.SamplingArgs(0.7, 0.8, 256, 1.4, seed=9)
+    got = generate_static_batch(gpu, prompts, 400, sa, fixed_len=5)
+    with torch.no_grad():
+        exp = ogen.generate_independent_batch(ora, [t64(p) for p in prompts], 400, so, fixed_len=5)
+    for g, e in zip(got, exp):
+        np.testing.assert_array_equal(g.astype(np.int64), e.numpy())
+    gpu.close()
+
+
 def test_bf16_weights_mode(tiny_lm):
     """weight_dtype bf16: weights stored bf16, fp32 math == oracle run on bf16-rounded weights."""
     cfg, tok, _ = tiny_lm
