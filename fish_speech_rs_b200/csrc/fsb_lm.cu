@@ -66,6 +66,8 @@ struct fsb_lm {
     // tcgen05 prefill (bf16 weights): split-activation buffers (hi | mid | lo) and their TMA maps per N tile
     bool tc_ok = false;
     __nv_bfloat16 *sp_xn = nullptr, *sp_att = nullptr, *sp_h = nullptr;
+    float *tc_ws = nullptr;  // split-K workspace of the decode-sized GEMMs
+    size_t tc_ws_floats = 0;
     TcMap mx_xn[3], mx_att[3], mx_h[3];  // index: bn 32 / 64 / 128
     // persistent megakernel (decode_mode 2)
     MegaParams mp;
@@ -215,6 +217,46 @@ static int decode_layer(fsb_lm *lm, const LayerW &L, float *x, int nb, float *kc
     return FSB_OK;
 }
 
+// Same block step for wide batches (nb > 8, bf16 weights): the five projections run on tcgen05 with the batch
+// rows as the MMA N dimension (weights stream once per layer instead of once per 8 rows); attention, RoPE
+// and the KV append are the per-op kernels above.
+static int decode_layer_tc(fsb_lm *lm, const LayerW &L, float *x, int nb, float *kc, float *vc, int cache_len,
+                           const int *pos_ptr, int pos_imm, int rope_delta, const int *n_active, int nsplit) {
+    const int D = lm->D, H = lm->H, KV = lm->KV, hd = lm->hd, I = lm->I, QKV = lm->QKV;
+    Scratch &s = lm->s;
+    cudaStream_t st = lm->stream;
+    const int bn = tc_pick_bn(nb), bi = bn == 32 ? 0 : (bn == 64 ? 1 : 2);
+    const int seg = lm->prefill_rows;
+    const float eps = lm->cfg.norm_eps;
+    FSB_TRY(tc_rmsnorm_split3(x, (const float *)L.attn_norm.ptr, eps, nb, D, lm->sp_xn, (size_t)seg * D, st));
+    FSB_TRY(tc_gemm(L.m_wqkv, lm->mx_xn[bi], bn, s.qkv, nullptr, nb, QKV, D, seg, QKV, st, lm->tc_ws, lm->tc_ws_floats));
+    rope_append_kernel<<<nb, 256, 0, st>>>(s.qkv, s.q, kc, vc, lm->cosT, lm->sinT, pos_ptr, pos_imm, rope_delta, H, KV, hd,
+                                           cache_len, n_active);
+    LAUNCH_CHECK(lm);
+    const int n_rep = H / KV;
+    attn_decode_split_kernel<<<dim3(nsplit, KV, nb), n_rep * 32, n_rep * hd * sizeof(float), st>>>(
+        s.q, kc, vc, pos_ptr, pos_imm, H, KV, hd, cache_len, 1.0f / sqrtf((float)hd), s.partial, n_active);
+    LAUNCH_CHECK(lm);
+    attn_decode_combine_kernel<<<nb * H, hd, 0, st>>>(s.partial, nsplit, hd, s.att, n_active);
+    LAUNCH_CHECK(lm);
+    FSB_TRY(tc_split3(s.att, lm->sp_att, (size_t)nb * H * hd, (size_t)seg * H * hd, st));
+    FSB_TRY(tc_gemm(L.m_wo, lm->mx_att[bi], bn, x, x, nb, D, H * hd, seg, D, st, lm->tc_ws, lm->tc_ws_floats));
+    FSB_TRY(tc_rmsnorm_split3(x, (const float *)L.ffn_norm.ptr, eps, nb, D, lm->sp_xn, (size_t)seg * D, st));
+    FSB_TRY(tc_gemm(L.m_w1, lm->mx_xn[bi], bn, s.g1, nullptr, nb, I, D, seg, I, st, lm->tc_ws, lm->tc_ws_floats));
+    FSB_TRY(tc_gemm(L.m_w3, lm->mx_xn[bi], bn, s.g3, nullptr, nb, I, D, seg, I, st, lm->tc_ws, lm->tc_ws_floats));
+    FSB_TRY(tc_swiglu_split3(s.g1, s.g3, (size_t)nb * I, lm->sp_h, (size_t)seg * I, st));
+    FSB_TRY(tc_gemm(L.m_w2, lm->mx_h[bi], bn, x, x, nb, D, I, seg, D, st, lm->tc_ws, lm->tc_ws_floats));
+    lm->launches += 9;
+    return FSB_OK;
+}
+
+static int decode_layer_any(fsb_lm *lm, const LayerW &L, float *x, int nb, float *kc, float *vc, int cache_len,
+                            const int *pos_ptr, int pos_imm, int rope_delta, const int *n_active, int nsplit) {
+    if (lm->tc_ok && nb > 8)
+        return decode_layer_tc(lm, L, x, nb, kc, vc, cache_len, pos_ptr, pos_imm, rope_delta, n_active, nsplit);
+    return decode_layer(lm, L, x, nb, kc, vc, cache_len, pos_ptr, pos_imm, rope_delta, n_active, nsplit);
+}
+
 template <typename WT>
 static void launch_embed(fsb_lm *lm, const uint32_t *toks, int nrows, int S, float *x, const int *n_active) {
     embed_sum_kernel<WT><<<nrows, 256, 0, lm->stream>>>(toks, S, lm->C, lm->D, lm->CS, (const WT *)lm->emb.ptr,
@@ -276,14 +318,14 @@ static int prefill_chunk(fsb_lm *lm, const uint32_t *toks_dev, int S_total, int 
     cudaStream_t st = lm->stream;
     for (int l = 0; l < lm->NL; ++l) {
         const LayerW &L = lm->layers[l];
-        rmsnorm_rows_kernel<<<(S + 3) / 4, 128, 0, lm->stream>>>(s.x, (const float *)L.attn_norm.ptr,
-                                                                 lm->cfg.norm_eps, S, D, s.xn);
-        LAUNCH_CHECK(lm);
         if (tc) {
-            FSB_TRY(tc_split3(s.xn, lm->sp_xn, (size_t)S * D, (size_t)seg * D, st));
+            FSB_TRY(tc_rmsnorm_split3(s.x, (const float *)L.attn_norm.ptr, lm->cfg.norm_eps, S, D, lm->sp_xn, (size_t)seg * D, st));
             FSB_TRY(tc_gemm(L.m_wqkv, lm->mx_xn[bi], bn, s.qkv, nullptr, S, QKV, D, seg, QKV, st));
             lm->launches += 2;
         } else {
+            rmsnorm_rows_kernel<<<(S + 3) / 4, 128, 0, lm->stream>>>(s.x, (const float *)L.attn_norm.ptr,
+                                                                     lm->cfg.norm_eps, S, D, s.xn);
+            LAUNCH_CHECK(lm);
             FSB_TRY(gemm<EPI_STORE>(lm, s.xn, L.wqkv, nullptr, s.qkv, S, QKV, D));
         }
         rope_append_rows_kernel<<<S, 256, 0, lm->stream>>>(s.qkv, s.q, slow_k(lm, l), slow_v(lm, l), lm->cosT,
@@ -299,26 +341,22 @@ static int prefill_chunk(fsb_lm *lm, const uint32_t *toks_dev, int S_total, int 
         } else {
             FSB_TRY(gemm<EPI_RESID>(lm, s.att, L.wo, s.x, s.x, S, D, H * hd));
         }
-        rmsnorm_rows_kernel<<<(S + 3) / 4, 128, 0, lm->stream>>>(s.x, (const float *)L.ffn_norm.ptr, lm->cfg.norm_eps,
-                                                                 S, D, s.xn);
-        LAUNCH_CHECK(lm);
+        const size_t n = (size_t)S * I;
         if (tc) {
-            FSB_TRY(tc_split3(s.xn, lm->sp_xn, (size_t)S * D, (size_t)seg * D, st));
+            FSB_TRY(tc_rmsnorm_split3(s.x, (const float *)L.ffn_norm.ptr, lm->cfg.norm_eps, S, D, lm->sp_xn, (size_t)seg * D, st));
             FSB_TRY(tc_gemm(L.m_w1, lm->mx_xn[bi], bn, s.g1, nullptr, S, I, D, seg, I, st));
             FSB_TRY(tc_gemm(L.m_w3, lm->mx_xn[bi], bn, s.g3, nullptr, S, I, D, seg, I, st));
-            lm->launches += 3;
+            FSB_TRY(tc_swiglu_split3(s.g1, s.g3, n, lm->sp_h, (size_t)seg * I, st));
+            FSB_TRY(tc_gemm(L.m_w2, lm->mx_h[bi], bn, s.x, s.x, S, D, I, seg, D, st));
+            lm->launches += 5;
         } else {
+            rmsnorm_rows_kernel<<<(S + 3) / 4, 128, 0, lm->stream>>>(s.x, (const float *)L.ffn_norm.ptr, lm->cfg.norm_eps,
+                                                                     S, D, s.xn);
+            LAUNCH_CHECK(lm);
             FSB_TRY(gemm<EPI_STORE>(lm, s.xn, L.w1, nullptr, s.g1, S, I, D));
             FSB_TRY(gemm<EPI_STORE>(lm, s.xn, L.w3, nullptr, s.g3, S, I, D));
-        }
-        const size_t n = (size_t)S * I;
-        swiglu_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, lm->stream>>>(s.g1, s.g3, n, s.g1);
-        LAUNCH_CHECK(lm);
-        if (tc) {
-            FSB_TRY(tc_split3(s.g1, lm->sp_h, n, (size_t)seg * I, st));
-            FSB_TRY(tc_gemm(L.m_w2, lm->mx_h[bi], bn, s.x, s.x, S, D, I, seg, D, st));
-            lm->launches += 2;
-        } else {
+            swiglu_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, lm->stream>>>(s.g1, s.g3, n, s.g1);
+            LAUNCH_CHECK(lm);
             FSB_TRY(gemm<EPI_RESID>(lm, s.g1, L.w2, s.x, s.x, S, D, I));
         }
     }
@@ -362,8 +400,8 @@ static int frame_tail(fsb_lm *lm, int nb) {
     LAUNCH_CHECK(lm);
     for (int cb = 0; cb < lm->C; ++cb) {
         for (int l = 0; l < lm->NFL; ++l)
-            FSB_TRY(decode_layer(lm, lm->fast_layers[l], s.fast_x, nb, fast_k(lm, l), fast_v(lm, l), lm->fast_len,
-                                 nullptr, cb, 0, na, 1));
+            FSB_TRY(decode_layer_any(lm, lm->fast_layers[l], s.fast_x, nb, fast_k(lm, l), fast_v(lm, l), lm->fast_len,
+                                     nullptr, cb, 0, na, 1));
         FSB_TRY(launch_gemv<EPI_STORE>(lm, lm->fast_out, nullptr, s.fast_x, lm->D, (const float *)lm->fast_norm.ptr,
                                        nullptr, s.fast_logits, lm->CS, lm->CS, lm->D, nb, na));
         if (lm->wdt == FSB_F32)
@@ -383,8 +421,8 @@ static int decode_frame(fsb_lm *lm, int nb) {
     const int *na = lm->h_st.n_active;
     FSB_TRY(embed(lm, lm->h_st.prev, nb, 1, s.hidden, na));
     for (int l = 0; l < lm->NL; ++l)
-        FSB_TRY(decode_layer(lm, lm->layers[l], s.hidden, nb, slow_k(lm, l), slow_v(lm, l), lm->max_len,
-                             lm->h_st.pos, 0, 0, na, lm->nsplit));
+        FSB_TRY(decode_layer_any(lm, lm->layers[l], s.hidden, nb, slow_k(lm, l), slow_v(lm, l), lm->max_len,
+                                 lm->h_st.pos, 0, 0, na, lm->nsplit));
     return frame_tail(lm, nb);
 }
 
@@ -547,6 +585,8 @@ static int tc_setup(fsb_lm *lm) {
     FSB_TRY(dev_alloc(lm, &lm->sp_xn, (size_t)3 * M * D));
     FSB_TRY(dev_alloc(lm, &lm->sp_att, (size_t)3 * M * Hhd));
     FSB_TRY(dev_alloc(lm, &lm->sp_h, (size_t)3 * M * I));
+    lm->tc_ws_floats = (size_t)16 * 64 * std::max(std::max(I, QKV), D);  // up to 16 splits of a 64-row batch
+    FSB_TRY(dev_alloc(lm, &lm->tc_ws, lm->tc_ws_floats));
     FSB_CUDA_OK(cudaMemset(lm->sp_xn, 0, (size_t)3 * M * D * 2));
     FSB_CUDA_OK(cudaMemset(lm->sp_att, 0, (size_t)3 * M * Hhd * 2));
     FSB_CUDA_OK(cudaMemset(lm->sp_h, 0, (size_t)3 * M * I * 2));
@@ -556,13 +596,15 @@ static int tc_setup(fsb_lm *lm) {
         FSB_TRY(tc_make_map_bf16(&lm->mx_att[i], lm->sp_att, 3 * M, Hhd, bns[i]));
         FSB_TRY(tc_make_map_bf16(&lm->mx_h[i], lm->sp_h, 3 * M, I, bns[i]));
     }
-    for (auto &L : lm->layers) {
-        FSB_TRY(tc_make_map_bf16(&L.m_wqkv, L.wqkv.ptr, QKV, D, 128));
-        FSB_TRY(tc_make_map_bf16(&L.m_wo, L.wo.ptr, D, Hhd, 128));
-        FSB_TRY(tc_make_map_bf16(&L.m_w1, L.w1.ptr, I, D, 128));
-        FSB_TRY(tc_make_map_bf16(&L.m_w3, L.w3.ptr, I, D, 128));
-        FSB_TRY(tc_make_map_bf16(&L.m_w2, L.w2.ptr, D, I, 128));
-    }
+    for (auto *stack : {&lm->layers, &lm->fast_layers})
+        for (auto &L : *stack) {
+            FSB_TRY(tc_make_map_bf16(&L.m_wqkv, L.wqkv.ptr, QKV, D, 128));
+            FSB_TRY(tc_make_map_bf16(&L.m_wo, L.wo.ptr, D, Hhd, 128));
+            FSB_TRY(tc_make_map_bf16(&L.m_w1, L.w1.ptr, I, D, 128));
+            FSB_TRY(tc_make_map_bf16(&L.m_w3, L.w3.ptr, I, D, 128));
+            FSB_TRY(tc_make_map_bf16(&L.m_w2, L.w2.ptr, D, I, 128));
+        }
+    FSB_TRY(tc_init());
     lm->tc_ok = true;
     return FSB_OK;
 }

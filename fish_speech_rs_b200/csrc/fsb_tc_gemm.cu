@@ -93,7 +93,7 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 template <int BN>
 __global__ void __launch_bounds__(kTcThreads, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmX, float *__restrict__ C,
-               const float *resid, int P, int N, int K, int x_seg_rows, int ldc) {
+               const float *resid, int P, int N, int K, int x_seg_rows, int ldc, float *__restrict__ ws) {
     constexpr int A_BYTES = kBM * kBK * 2, B_BYTES = BN * kBK * 2, STAGE = A_BYTES + 3 * B_BYTES;
     constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
     constexpr int kStages = stages_for(BN);
@@ -106,7 +106,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_full + 1);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n0 = blockIdx.x * kBM, p0 = blockIdx.y * BN;
-    const int nk = K / kBK;
+    // split-K over blockIdx.z (decode-sized N: too few output tiles to fill the GPU otherwise); partial
+    // tiles go to the workspace ws[z][p][n] and are summed in a fixed order by splitk_reduce_kernel
+    const int nk_total = K / kBK;
+    const int kb0 = (int)(((long long)blockIdx.z * nk_total) / gridDim.z);
+    const int nk = (int)(((long long)(blockIdx.z + 1) * nk_total) / gridDim.z) - kb0;
+    if (gridDim.z > 1) {
+        C = ws + (size_t)blockIdx.z * P * ldc;
+        resid = nullptr;
+    }
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) {
@@ -136,10 +144,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
             mbar_wait(empty + s, ((kb / kStages) & 1) ^ 1);
             uint8_t *st = tc_smem + (size_t)s * STAGE;
             mbar_expect_tx(full + s, STAGE);
-            tma_load_2d(st, &tmW, full + s, kb * kBK, n0);
+            tma_load_2d(st, &tmW, full + s, (kb0 + kb) * kBK, n0);
 #pragma unroll
             for (int i = 0; i < 3; ++i)
-                tma_load_2d(st + A_BYTES + i * B_BYTES, &tmX, full + s, kb * kBK, i * x_seg_rows + p0);
+                tma_load_2d(st + A_BYTES + i * B_BYTES, &tmX, full + s, (kb0 + kb) * kBK, i * x_seg_rows + p0);
         }
     } else if (warp == 1 && lane == 0) {
         // ---- MMA issuer: D (TMEM, 128 lanes x BN fp32 columns) += W_tile (M = 128) x X_tile^T (N = BN), K = 16 per instruction
@@ -204,6 +212,55 @@ __global__ void split3_rows_kernel(const float *__restrict__ x, __nv_bfloat16 *_
     out[2 * seg_elems + i] = __float2bfloat16_rn(r2);
 }
 
+// rms_norm of each row (candle_nn::RmsNorm: x / sqrt(mean(x^2) + eps) * g) written directly as the three
+// bf16 terms the GEMM consumes; one warp per row
+__global__ void rmsnorm_split3_kernel(const float *__restrict__ x, const float *__restrict__ g, float eps, int M, int D,
+                                      __nv_bfloat16 *__restrict__ out, size_t seg_elems) {
+    const int row = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= M) return;
+    const float *xr = x + (size_t)row * D;
+    float ss = 0.f;
+    for (int k = lane; k < D; k += 32) ss += xr[k] * xr[k];
+    ss = warp_sum(ss);
+    const float denom = sqrtf(ss / (float)D + eps);
+    for (int k = lane; k < D; k += 32) {
+        const float v = __fmul_rn(__fdiv_rn(xr[k], denom), g[k]);
+        const size_t i = (size_t)row * D + k;
+        const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+        const float r1 = v - __bfloat162float(hi);
+        const __nv_bfloat16 mid = __float2bfloat16_rn(r1);
+        out[i] = hi;
+        out[seg_elems + i] = mid;
+        out[2 * seg_elems + i] = __float2bfloat16_rn(r1 - __bfloat162float(mid));
+    }
+}
+
+// h = silu(g1) * g3 (dual_ar.rs:160-165) written as the three bf16 terms
+__global__ void swiglu_split3_kernel(const float *__restrict__ g1, const float *__restrict__ g3, size_t n,
+                                     __nv_bfloat16 *__restrict__ out, size_t seg_elems) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float v = __fmul_rn(silu_f(g1[i]), g3[i]);
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    const float r1 = v - __bfloat162float(hi);
+    const __nv_bfloat16 mid = __float2bfloat16_rn(r1);
+    out[i] = hi;
+    out[seg_elems + i] = mid;
+    out[2 * seg_elems + i] = __float2bfloat16_rn(r1 - __bfloat162float(mid));
+}
+
+// C[i] = (resid[i]) + sum_z ws[z][i], z ascending (deterministic)
+__global__ void splitk_reduce_kernel(const float *__restrict__ ws, int ksplit, size_t n, const float *resid,
+                                     float *__restrict__ C) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float acc = ws[i];
+    for (int z = 1; z < ksplit; ++z) acc += ws[(size_t)z * n + i];
+    if (resid) acc = __fadd_rn(resid[i], acc);
+    C[i] = acc;
+}
+
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                     const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -247,30 +304,61 @@ int tc_split3(const float *x, __nv_bfloat16 *out, size_t n, size_t seg_elems, cu
     return FSB_OK;
 }
 
-template <int BN>
-static int launch_bn(const TcMap &mw, const TcMap &mx, float *C, const float *resid, int P, int N, int K, int x_seg_rows,
-                     int ldc, cudaStream_t st) {
-    constexpr int STAGE = kBM * kBK * 2 + 3 * BN * kBK * 2;
-    const size_t smem = (size_t)stages_for(BN) * STAGE + 256 + 1024;  // + barriers + alignment slack
-    static bool attr_done = false;
-    if (!attr_done) {
-        FSB_CUDA_OK(cudaFuncSetAttribute(tc_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_done = true;
-    }
-    dim3 grid((N + kBM - 1) / kBM, (P + BN - 1) / BN);
-    tc_gemm_kernel<BN><<<grid, kTcThreads, smem, st>>>(*reinterpret_cast<const CUtensorMap *>(&mw),
-                                                      *reinterpret_cast<const CUtensorMap *>(&mx), C, resid, P, N, K,
-                                                      x_seg_rows, ldc);
+int tc_rmsnorm_split3(const float *x, const float *g, float eps, int M, int D, __nv_bfloat16 *out, size_t seg_elems,
+                      cudaStream_t st) {
+    rmsnorm_split3_kernel<<<(M + 3) / 4, 128, 0, st>>>(x, g, eps, M, D, out, seg_elems);
     FSB_CUDA_OK(cudaGetLastError());
     return FSB_OK;
 }
 
+int tc_swiglu_split3(const float *g1, const float *g3, size_t n, __nv_bfloat16 *out, size_t seg_elems, cudaStream_t st) {
+    swiglu_split3_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(g1, g3, n, out, seg_elems);
+    FSB_CUDA_OK(cudaGetLastError());
+    return FSB_OK;
+}
+
+template <int BN>
+static size_t tc_smem_bytes() {
+    return (size_t)stages_for(BN) * (kBM * kBK * 2 + 3 * BN * kBK * 2) + 256 + 1024;
+}
+
+// opt every tile shape into its dynamic shared memory once, outside any stream capture
+int tc_init() {
+    FSB_CUDA_OK(cudaFuncSetAttribute(tc_gemm_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes<32>()));
+    FSB_CUDA_OK(cudaFuncSetAttribute(tc_gemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes<64>()));
+    FSB_CUDA_OK(cudaFuncSetAttribute(tc_gemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes<128>()));
+    return FSB_OK;
+}
+
+template <int BN>
+static int launch_bn(const TcMap &mw, const TcMap &mx, float *C, const float *resid, int P, int N, int K, int x_seg_rows,
+                     int ldc, float *ws, size_t ws_floats, cudaStream_t st) {
+    const size_t smem = tc_smem_bytes<BN>();
+    const int tiles = ((N + kBM - 1) / kBM) * ((P + BN - 1) / BN);
+    int ksplit = 1;
+    if (ws && ldc == N && tiles < 96) {  // fill the 148 SMs; every split keeps >= 2 k-blocks
+        const int nk = K / kBK;
+        while (ksplit * 2 * tiles <= 160 && nk / (ksplit * 2) >= 2 && (size_t)(ksplit * 2) * P * N <= ws_floats) ksplit *= 2;
+    }
+    dim3 grid((N + kBM - 1) / kBM, (P + BN - 1) / BN, ksplit);
+    tc_gemm_kernel<BN><<<grid, kTcThreads, smem, st>>>(*reinterpret_cast<const CUtensorMap *>(&mw),
+                                                      *reinterpret_cast<const CUtensorMap *>(&mx), C, resid, P, N, K,
+                                                      x_seg_rows, ldc, ws);
+    FSB_CUDA_OK(cudaGetLastError());
+    if (ksplit > 1) {
+        const size_t n = (size_t)P * N;
+        splitk_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ws, ksplit, n, resid, C);
+        FSB_CUDA_OK(cudaGetLastError());
+    }
+    return FSB_OK;
+}
+
 int tc_gemm(const TcMap &mw, const TcMap &mx, int bn, float *C, const float *resid, int P, int N, int K, int x_seg_rows,
-            int ldc, cudaStream_t st) {
+            int ldc, cudaStream_t st, float *ws, size_t ws_floats) {
     switch (bn) {
-        case 32: return launch_bn<32>(mw, mx, C, resid, P, N, K, x_seg_rows, ldc, st);
-        case 64: return launch_bn<64>(mw, mx, C, resid, P, N, K, x_seg_rows, ldc, st);
-        case 128: return launch_bn<128>(mw, mx, C, resid, P, N, K, x_seg_rows, ldc, st);
+        case 32: return launch_bn<32>(mw, mx, C, resid, P, N, K, x_seg_rows, ldc, ws, ws_floats, st);
+        case 64: return launch_bn<64>(mw, mx, C, resid, P, N, K, x_seg_rows, ldc, ws, ws_floats, st);
+        case 128: return launch_bn<128>(mw, mx, C, resid, P, N, K, x_seg_rows, ldc, ws, ws_floats, st);
         default: set_error("tc_gemm: unsupported BN %d", bn); return FSB_ERR_INVALID;
     }
 }

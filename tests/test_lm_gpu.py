@@ -164,12 +164,15 @@ def test_decode_modes_agree_with_oracle(tiny_lm, mode):
     gpu.close()
 
 
-@pytest.mark.parametrize("mode", [0, 1])
-def test_batch_above_eight_rows(tiny_lm, mode):
-    """11 ragged rows: the megakernel runs them as groups of 8 + 3 (mode 0), the per-op path as two GEMV
-    groups (mode 1); every row must equal its bs=1 oracle generation (Philox row index = global row)."""
+@pytest.mark.parametrize("mode,dtype", [(0, "f32"), (1, "f32"), (1, "bf16")])
+def test_batch_above_eight_rows(tiny_lm, mode, dtype):
+    """11 ragged rows.  f32: the per-op path runs two GEMV groups (auto mode falls back to it above one
+    megakernel group).  bf16: the block projections run on tcgen05 with the batch as the MMA N dimension.
+    Every row must equal its bs=1 oracle generation (Philox row index = global row)."""
     cfg, tok, w = tiny_lm
-    gpu = DualARTransformer(w, cfg, tok, max_batch=11, max_seq_len=128, decode_mode=mode)
+    if dtype == "bf16":
+        w = synth.make_lm_weights(cfg, seed=1234, round_bf16=True)
+    gpu = DualARTransformer(w, cfg, tok, max_batch=11, max_seq_len=128, decode_mode=mode, dtype=dtype)
     ora = oracle_model(cfg, tok, w)
     prompts = [synth.make_prompt(cfg, tok, 12 + 5 * i, seed=300 + i) for i in range(11)]
     sa, so = SamplingArgs(0.7, 0.8, 256, 1.4, seed=9), osamp.SamplingArgs(0.7, 0.8, 256, 1.4, seed=9)
