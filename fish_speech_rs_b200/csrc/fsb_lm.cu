@@ -65,6 +65,7 @@ struct fsb_lm {
     uint64_t launches = 0;
     // tcgen05 prefill (bf16 weights): split-activation buffers (hi | mid | lo) and their TMA maps per N tile
     bool tc_ok = false;
+    size_t smem_optin = 0;  // cudaDevAttrMaxSharedMemoryPerBlockOptin, cached by mega_setup
     __nv_bfloat16 *sp_xn = nullptr, *sp_att = nullptr, *sp_h = nullptr;
     float *tc_ws = nullptr;  // split-K workspace of the decode-sized GEMMs
     size_t tc_ws_floats = 0;
@@ -520,6 +521,7 @@ static int mega_setup(fsb_lm *lm) {
     cudaDeviceProp prop;
     FSB_CUDA_OK(cudaGetDeviceProperties(&prop, lm->opt.device));
     lm->mega_grid = prop.multiProcessorCount;
+    lm->smem_optin = (size_t)prop.sharedMemPerBlockOptin;
     int coop = 0;
     FSB_CUDA_OK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, lm->opt.device));
     auto split_ok = [&](int K) {
@@ -864,11 +866,9 @@ static int generate_impl(fsb_lm *lm, const uint32_t *const *prompts, const int32
     bool use_mega = lm->mega_ok && lm->opt.decode_mode != 1 && !lm->profile;
     int group = 8;  // rows per megakernel launch: the largest batch template whose shared memory fits
     if (use_mega) {
-        cudaDeviceProp prop;
-        FSB_CUDA_OK(cudaGetDeviceProperties(&prop, lm->opt.device));
-        int xf, vf;
-        while (group > 1 && mega_smem_bytes(lm, group, &xf, &vf) > (size_t)prop.sharedMemPerBlockOptin) group /= 2;
-        use_mega = mega_smem_bytes(lm, group, &xf, &vf) <= (size_t)prop.sharedMemPerBlockOptin;
+        int xf, vf;  // (the opt-in limit is cached at setup: cudaGetDeviceProperties costs ~200 ms per call)
+        while (group > 1 && mega_smem_bytes(lm, group, &xf, &vf) > lm->smem_optin) group /= 2;
+        use_mega = mega_smem_bytes(lm, group, &xf, &vf) <= lm->smem_optin;
         // auto mode: one launch only (rows beyond a group are better served by the per-op GEMV path)
         if (lm->opt.decode_mode == 0 && bsz > group) use_mega = false;
     }
