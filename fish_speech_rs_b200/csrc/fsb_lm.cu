@@ -487,6 +487,25 @@ static size_t mega_smem_bytes(const fsb_lm *lm, int NB, int *xs_floats, int *val
     return ((size_t)*xs_floats + (size_t)*val_floats + aux + 2ull * kMegaChunk * kMegaKvStride) * sizeof(float);
 }
 
+// ---- single-row kernel (fsb_lm_mega1.cuh): shared-memory carve-up mirrored from Mega1's constructor
+static bool mega1_eligible(const fsb_lm *lm) {
+    if (getenv("FSB_MEGA_V1")) return false;  // A/B switch: keep the register-prefetch kernel for one row too
+    const int Hhd = lm->H * lm->hd;
+    const SampleParams &sp = lm->h_st.sp;  // the single-row kernel carries the selection sampler only
+    if (!sp.greedy && (sp.top_k > (uint32_t)kSelMaxK || std::max(lm->n_slow_logits, lm->CS) > (1 << kSelIdxBits))) return false;
+    return lm->mega_ok && lm->D == kM1Slice && lm->I % kM1Slice == 0 && Hhd == kM1Slice && lm->I / kM1Slice <= 8 &&
+           8 % (lm->I / kM1Slice) == 0 && lm->hd == 64 && lm->QKV % 2 == 0;
+}
+static size_t mega1_smem_bytes(const fsb_lm *lm, int depth, int *xs_floats, int *kvs_floats) {
+    const int n_max = std::max(lm->n_slow_logits, lm->CS);
+    const int samp_floats = (sel_scratch_bytes(kM1Threads) + 15) / 16 * 4 + ((n_max + 3) & ~3) + 64;
+    *xs_floats = (std::max(lm->I, 2 * lm->H * lm->hd) + 3) & ~3;
+    *kvs_floats = (std::max(2 * kM1AttChunk * kM1KvStride, samp_floats) + 3) & ~3;
+    const size_t fl = (size_t)*xs_floats + lm->D + kM1ValFloats + 64 + 64 + 8 * 64 + 8 * 68 + *kvs_floats + 4 + 12 + 4 + 20 + 20 +
+                      (sizeof(RepPenState) / 4) * 8 + 4 * kM1MaxDepth + 2;
+    return (size_t)depth * kM1ChunkBytes + fl * sizeof(float) + 16;
+}
+
 // rows [row0, row0 + nb) of the current batch: every per-row buffer is addressed relative to row0
 static int mega_launch(fsb_lm *lm, int row0, int group_index, int nb, int nframes, bool first_is_tail) {
     MegaParams mp = lm->mp;
@@ -510,7 +529,22 @@ static int mega_launch(fsb_lm *lm, int row0, int group_index, int nb, int nframe
     mp.st.pos += r; mp.st.active += r; mp.st.eos += r; mp.st.frame += r; mp.st.max_frames += r;
     mp.st.cur += r * C1; mp.st.prev += r * C1; mp.st.out += r * mp.st.out_cap * C1; mp.st.rep += r * lm->C;
     mp.st.n_active += group_index;  // one live-row counter per group
-    FSB_CUDA_OK(cudaMemsetAsync(lm->mega_bar, 0, sizeof(unsigned int), lm->stream));
+    FSB_CUDA_OK(cudaMemsetAsync(lm->mega_bar, 0, 4 * sizeof(unsigned int), lm->stream));
+    if (nb == 1 && mega1_eligible(lm)) {
+        int depth = kM1MaxDepth, xf = 0, kf = 0;
+        while (depth > 2 && mega1_smem_bytes(lm, depth, &xf, &kf) > lm->smem_optin) --depth;
+        const size_t smem1 = mega1_smem_bytes(lm, depth, &xf, &kf);
+        if (smem1 <= lm->smem_optin) {
+            mp.ring_depth = depth;
+            mp.xs_floats = xf;
+            mp.kvs_floats = kf;
+            mp.sampler_cta = getenv("FSB_MEGA_SAMPLER_CTA") ? lm->mega_grid - 1 : -1;
+            FSB_CUDA_OK(lm->wdt == FSB_F32 ? mega1_launch_f32(mp, lm->mega_grid, smem1, lm->stream)
+                                           : mega1_launch_bf16(mp, lm->mega_grid, smem1, lm->stream));
+            lm->launches++;
+            return FSB_OK;
+        }
+    }
     FSB_CUDA_OK(lm->wdt == FSB_F32 ? mega_launch_f32(NB, mp, lm->mega_grid, smem, lm->stream)
                                    : mega_launch_bf16(NB, mp, lm->mega_grid, smem, lm->stream));
     lm->launches++;
@@ -550,7 +584,7 @@ static int mega_setup(fsb_lm *lm) {
     const int n_chunks_max = (lm->max_len + kMegaChunk - 1) / kMegaChunk;
     FSB_TRY(dev_alloc(lm, &lm->mega_partial, (size_t)B * lm->H * 2 * n_chunks_max * (lm->hd + 4)));
     FSB_TRY(dev_alloc(lm, &lm->mega_logits, (size_t)B * ldl));
-    FSB_TRY(dev_alloc(lm, &lm->mega_bar, 1));
+    FSB_TRY(dev_alloc(lm, &lm->mega_bar, 4));  // [0] grid barrier, [1] frames confirmed (single-row kernel)
     if (getenv("FSB_MEGA_TIMERS")) {
         FSB_TRY(dev_alloc(lm, &lm->mega_dbg, 128));
         FSB_CUDA_OK(cudaMemset(lm->mega_dbg, 0, 128 * sizeof(unsigned long long)));
@@ -977,8 +1011,8 @@ static int generate_impl(fsb_lm *lm, const uint32_t *const *prompts, const int32
             fprintf(stderr, "[sample_fast] rep-pen %.2f  logits %.2f  block_sample %.2f us (n=%llu)\n", h[100] / 1965.0 / h[103],
                     h[101] / 1965.0 / h[103], h[102] / 1965.0 / h[103], h[103]);
         if (h[107])
-            fprintf(stderr, "[block_sample] max+softmax+keys %.2f  sort %.2f  scan %.2f us (n=%llu)\n", h[104] / 1965.0 / h[107],
-                    h[105] / 1965.0 / h[107], h[106] / 1965.0 / h[107], h[107]);
+            fprintf(stderr, "[block_sample] max+softmax+keys %.2f  sort|select %.2f  scan|rank %.2f  (walk %.2f) us (n=%llu)\n",
+                    h[104] / 1965.0 / h[107], h[105] / 1965.0 / h[107], h[106] / 1965.0 / h[107], h[108] / 1965.0 / h[107], h[107]);
         for (int c = 0; c < 2; ++c)
             for (int k = 0; k < 7; ++k) {
                 const unsigned long long *e = h + c * 32 + k * 4;

@@ -11,6 +11,17 @@ constexpr int kMegaPre = 4;        // 16-byte weight loads per lane kept in flig
 constexpr int kMegaChunk = 128;    // cached positions one attention work item covers (staged in shared memory)
 constexpr int kMegaKvStride = 80;  // floats per staged K/V row (64 + pad: conflict-free LDS.128 for 8 rows at once)
 
+// single-row kernel (fsb_lm_mega1.cuh)
+constexpr int kM1Warps = 16;                      // compute warps
+constexpr int kM1Threads = kM1Warps * 32;         // compute threads (named barrier 1)
+constexpr int kM1AllThreads = kM1Threads + 32;    // + the TMA producer warp
+constexpr int kM1Slice = 1024;                    // K elements of one task
+constexpr int kM1ChunkBytes = 32768;              // one ring slot
+constexpr int kM1MaxDepth = 6;
+constexpr int kM1AttChunk = 64;                   // cached positions per attention item
+constexpr int kM1KvStride = 80;                   // floats per staged K/V row (conflict-free LDS.128)
+constexpr int kM1ValFloats = 128;
+
 struct MegaLayer {
     const void *wqkv, *wo, *w1, *w3, *w2;
     const float *attn_norm, *ffn_norm;
@@ -42,11 +53,17 @@ struct MegaParams {
     int has_end;
     int val_floats;  // capacity of the per-task result array (floats)
     int xs_floats;   // capacity of the activation staging area (floats)
+    int ring_depth;  // single-row kernel (fsb_lm_mega1.cuh): 32 KB slots of the TMA weight ring
+    int kvs_floats;  // single-row kernel: K/V staging area == sampler scratch (floats)
+    int sampler_cta; // single-row kernel: CTA that only samples (-1: CTA 0 samples and streams)
     unsigned long long *dbg;  // optional (FSB_MEGA_TIMERS=1): per phase kind {work ns, barrier ns, count} of CTA 0 and the last CTA
 };
 
 // Launchers, one translation unit per weight dtype (fsb_lm_mega_{bf16,f32}.cu).  NB in {1,2,4,8}.
 cudaError_t mega_launch_bf16(int NB, const MegaParams &mp, int grid, size_t smem, cudaStream_t st);
 cudaError_t mega_launch_f32(int NB, const MegaParams &mp, int grid, size_t smem, cudaStream_t st);
+// single-row kernel with the TMA weight ring (fsb_lm_mega1.cuh)
+cudaError_t mega1_launch_bf16(const MegaParams &mp, int grid, size_t smem, cudaStream_t st);
+cudaError_t mega1_launch_f32(const MegaParams &mp, int grid, size_t smem, cudaStream_t st);
 
 }  // namespace fsb

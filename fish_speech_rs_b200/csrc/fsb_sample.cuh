@@ -80,12 +80,24 @@ __device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned long long v,
 
 __device__ unsigned long long *g_sample_dbg = nullptr;  // optional cycle counters (debug builds of the megakernel)
 
-template <int E>
+// Block-synchronisation policy of the sampler: the whole CTA (stand-alone sampler kernels) or the
+// compute warps of a warp-specialised kernel (named barrier; the TMA producer warp does not take part).
+struct SyncAll {
+    static __device__ __forceinline__ void sync() { __syncthreads(); }
+    static __device__ __forceinline__ int nthreads() { return (int)blockDim.x; }
+};
+template <int NT, int BAR>
+struct SyncNamed {
+    static __device__ __forceinline__ void sync() { asm volatile("bar.sync %0, %1;" ::"n"(BAR), "n"(NT) : "memory"); }
+    static __device__ __forceinline__ int nthreads() { return NT; }
+};
+
+template <int E, class SY>
 __device__ __forceinline__ int block_sample_t(float *vals, unsigned long long *keys, float *red, int n, int n_pad,
                                               const SampleParams &sp, float u) {
     const bool tm_ = g_sample_dbg != nullptr && threadIdx.x == 0;
     const long long q0 = tm_ ? clock64() : 0;
-    const int tid = threadIdx.x, nthreads = blockDim.x;
+    const int tid = threadIdx.x, nthreads = SY::nthreads();
     const int lane = tid & 31, warp = tid >> 5, nwarps = nthreads >> 5;
     const int n_eff = E * nthreads;  // elements per thread E: index e * nthreads + tid
     float v[E];
@@ -106,7 +118,7 @@ __device__ __forceinline__ int block_sample_t(float *vals, unsigned long long *k
     }
     int *red_i = reinterpret_cast<int *>(red + 32);
     if (lane == 0) { red[warp] = best; red_i[warp] = best_i; }
-    __syncthreads();
+    SY::sync();
     {
         float b2 = lane < nwarps ? red[lane] : -INFINITY;
         int i2 = lane < nwarps ? red_i[lane] : 0x7fffffff;
@@ -120,7 +132,7 @@ __device__ __forceinline__ int block_sample_t(float *vals, unsigned long long *k
         best_i = i2;
     }
     if (sp.greedy) {
-        __syncthreads();
+        SY::sync();
         return best_i;
     }
     // ---- softmax(logits * inv_temp) ----
@@ -132,9 +144,9 @@ __device__ __forceinline__ int block_sample_t(float *vals, unsigned long long *k
         s += v[e];
     }
     s = warp_sum(s);
-    __syncthreads();  // red[] reads above are done
+    SY::sync();  // red[] reads above are done
     if (lane == 0) red[warp] = s;
-    __syncthreads();
+    SY::sync();
     float denom = lane < nwarps ? red[lane] : 0.f;
     denom = warp_sum(denom);
     // keys: (~prob bits) << 32 | index; ascending sort == prob desc, index asc
@@ -173,7 +185,7 @@ __device__ __forceinline__ int block_sample_t(float *vals, unsigned long long *k
                 unsigned long long *kb = keys + (size_t)buf * n_eff;
 #pragma unroll
                 for (int e = 0; e < E; ++e) kb[e * nthreads + tid] = key[e];
-                __syncthreads();
+                SY::sync();
 #pragma unroll
                 for (int e = 0; e < E; ++e) {
                     const int i = e * nthreads + tid;
@@ -200,7 +212,7 @@ __device__ __forceinline__ int block_sample_t(float *vals, unsigned long long *k
         unsigned long long *kb = keys + (size_t)buf * n_eff;
 #pragma unroll
         for (int e = 0; e < E; ++e) kb[e * nthreads + tid] = key[e];
-        __syncthreads();
+        SY::sync();
         keys = kb;
     }
     const long long q2 = tm_ ? clock64() : 0;
@@ -264,9 +276,9 @@ __device__ __forceinline__ int block_sample_t(float *vals, unsigned long long *k
             red_i[0] = (int)(keys[pick] & 0xffffffffu);
         }
     }
-    __syncthreads();
+    SY::sync();
     int r = red_i[0];
-    __syncthreads();
+    SY::sync();
     if (tm_) {
         const long long q3 = clock64();
         g_sample_dbg[0] += q1 - q0; g_sample_dbg[1] += q2 - q1; g_sample_dbg[2] += q3 - q2; g_sample_dbg[3] += 1;
@@ -276,15 +288,274 @@ __device__ __forceinline__ int block_sample_t(float *vals, unsigned long long *k
 
 // elements per thread is a compile-time constant of the sort network (a generic loop over "up to 8"
 // slots made the sampler issue-bound: 17 us of a 21 us draw)
+template <class SY = SyncAll>
 __device__ inline int block_sample(float *vals, unsigned long long *keys, float *red, int n, int n_pad,
                                    const SampleParams &sp, float u) {
-    const int E = max(n_pad, (int)blockDim.x) / (int)blockDim.x;
+    const int E = max(n_pad, SY::nthreads()) / SY::nthreads();
     switch (E) {
-        case 1: return block_sample_t<1>(vals, keys, red, n, n_pad, sp, u);
-        case 2: return block_sample_t<2>(vals, keys, red, n, n_pad, sp, u);
-        case 4: return block_sample_t<4>(vals, keys, red, n, n_pad, sp, u);
-        default: return block_sample_t<8>(vals, keys, red, n, n_pad, sp, u);
+        case 1: return block_sample_t<1, SY>(vals, keys, red, n, n_pad, sp, u);
+        case 2: return block_sample_t<2, SY>(vals, keys, red, n, n_pad, sp, u);
+        case 4: return block_sample_t<4, SY>(vals, keys, red, n, n_pad, sp, u);
+        default: return block_sample_t<8, SY>(vals, keys, red, n, n_pad, sp, u);
     }
+}
+
+// ---------------------------------------------------------------- selection sampler (top_k <= 256)
+// Same candidates, same order, same running sums as block_sample_t, without sorting all n entries:
+//   1. softmax, composite keys  (~prob bits) << 12 | index  (unique, ascending == prob desc / index asc)
+//   2. radix select of the k-th smallest key: 9 rounds of 5-bit digits, per-warp 32-bin histograms filled
+//      with match_any, one block barrier per round (every warp redoes the 32-lane scan itself)
+//   3. compaction of the k keys <= threshold, rank of each by counting (k^2 / 2 broadcast compares),
+//      scatter into sorted order
+//   4. top-p cut and multinomial walk on warp 0 (identical arithmetic to block_sample_t)
+// Shared-memory scratch: kSelScratchBytes(nthreads).
+constexpr int kSelMaxK = 256;
+constexpr int kSelIdxBits = 12;  // n <= 4096
+__host__ __device__ constexpr int sel_list_entries(int nthreads) { return 256 + 2 * (nthreads / 256); }
+__host__ __device__ constexpr int sel_scratch_bytes(int nthreads) {
+    return sel_list_entries(nthreads) * 8 + 256 * 8 + 3 * (nthreads / 32) * 32 * 4 + 64;
+}
+
+template <int E, class SY>
+__device__ __noinline__ int block_sample_sel_t(const float *vals, unsigned char *scratch, float *red, int n,
+                                               const SampleParams &sp, float u) {
+    const int tid = threadIdx.x, nthreads = SY::nthreads();
+    const int lane = tid & 31, warp = tid >> 5, nwarps = nthreads >> 5;
+    const int G = nthreads / 256, seglen = 256 / G;  // threads per candidate in the rank step
+    unsigned long long *list = reinterpret_cast<unsigned long long *>(scratch);   // G segments of seglen + 2
+    unsigned long long *sorted = list + sel_list_entries(nthreads);               // 256
+    unsigned *hist = reinterpret_cast<unsigned *>(sorted + 256);                  // 3 x nwarps x 32
+    unsigned *counter = hist + 3 * nwarps * 32;
+    int *red_i = reinterpret_cast<int *>(red + 32);
+    const bool tm_ = g_sample_dbg != nullptr && threadIdx.x == 0;
+    const long long q0 = tm_ ? clock64() : 0;
+    float v[E];
+    // ---- max (and first argmax) ----
+    float best = -INFINITY;
+    int best_i = 0x7fffffff;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        const int i = e * nthreads + tid;
+        v[e] = (i < n) ? vals[i] : -INFINITY;
+        if (v[e] > best) { best = v[e]; best_i = i; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        float ov = __shfl_xor_sync(0xffffffffu, best, o);
+        int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+        if (ov > best || (ov == best && oi < best_i)) { best = ov; best_i = oi; }
+    }
+    if (lane == 0) { red[warp] = best; red_i[warp] = best_i; }
+    // scratch initialisation rides on the same barrier
+    for (int i = tid; i < sel_list_entries(nthreads); i += nthreads) list[i] = ~0ull;
+    hist[warp * 32 + lane] = 0;
+    hist[(nwarps + warp) * 32 + lane] = 0;
+    if (tid == 0) *counter = 0;
+    SY::sync();
+    {
+        float b2 = lane < nwarps ? red[lane] : -INFINITY;
+        int i2 = lane < nwarps ? red_i[lane] : 0x7fffffff;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            float ov = __shfl_xor_sync(0xffffffffu, b2, o);
+            int oi = __shfl_xor_sync(0xffffffffu, i2, o);
+            if (ov > b2 || (ov == b2 && oi < i2)) { b2 = ov; i2 = oi; }
+        }
+        best = b2;
+        best_i = i2;
+    }
+    if (sp.greedy) {
+        SY::sync();
+        return best_i;
+    }
+    // ---- softmax(logits * inv_temp) ----
+    const float mx = __fmul_rn(best, sp.inv_temp);
+    float s = 0.f;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        v[e] = (e * nthreads + tid < n) ? expf(__fsub_rn(__fmul_rn(v[e], sp.inv_temp), mx)) : 0.f;
+        s += v[e];
+    }
+    s = warp_sum(s);
+    SY::sync();  // red[] reads above are done
+    if (lane == 0) red[warp] = s;
+    SY::sync();
+    float denom = lane < nwarps ? red[lane] : 0.f;
+    denom = warp_sum(denom);
+    unsigned long long key[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        const int i = e * nthreads + tid;
+        key[e] = ~0ull;
+        if (i < n) {
+            const float p = v[e] / denom;
+            key[e] = ((unsigned long long)(~__float_as_uint(p)) << kSelIdxBits) | (unsigned)i;
+        }
+    }
+    const long long q1 = tm_ ? clock64() : 0;
+    // ---- radix select: k-th smallest key ----
+    const int k = (sp.top_k >= (uint32_t)n) ? n : (int)sp.top_k;
+    unsigned long long prefix = 0;
+    int krem = k;
+#pragma unroll 1
+    for (int r = 0; r < 9; ++r) {
+        const int shift = 40 - 5 * r;
+        unsigned *hb = hist + (r % 3) * nwarps * 32, *hn = hist + ((r + 1) % 3) * nwarps * 32;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const bool part = (key[e] >> (shift + 5)) == prefix;
+            const unsigned d = part ? (unsigned)(key[e] >> shift) & 31u : 32u;
+            const unsigned m = __match_any_sync(0xffffffffu, d);
+            if (part && lane == __ffs(m) - 1) hb[warp * 32 + d] += __popc(m);
+            __syncwarp();
+        }
+        if (r >= 1) hn[warp * 32 + lane] = 0;  // buffers 0 and 1 were cleared up front
+        SY::sync();
+        unsigned tot = 0;
+        for (int w = 0; w < nwarps; ++w) tot += hb[w * 32 + lane];
+        unsigned cum = tot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned t = __shfl_up_sync(0xffffffffu, cum, o);
+            if (lane >= o) cum += t;
+        }
+        const unsigned ball = __ballot_sync(0xffffffffu, cum >= (unsigned)krem);
+        const int d = __ffs(ball) - 1;  // ball != 0: the matching elements number >= krem by construction
+        const unsigned below = __shfl_sync(0xffffffffu, cum - tot, d);
+        krem -= (int)below;
+        prefix = (prefix << 5) | (unsigned)d;
+    }
+    const unsigned long long kth = prefix;
+    const long long q2 = tm_ ? clock64() : 0;
+    // ---- compaction of the k candidates (order irrelevant) ----
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        const bool cand = key[e] <= kth;
+        const unsigned m = __ballot_sync(0xffffffffu, cand);
+        unsigned base = 0;
+        if (lane == 0 && m) base = atomicAdd(counter, __popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (cand) {
+            const unsigned pos = base + __popc(m & ((1u << lane) - 1u));
+            list[(pos / seglen) * (seglen + 2) + (pos % seglen)] = key[e];
+        }
+    }
+    SY::sync();
+    // ---- rank by counting: thread (candidate c, segment g); unused slots hold ~0 ----
+    {
+        const int c = tid % 256, g = tid / 256;
+        const unsigned long long mine = list[(c / seglen) * (seglen + 2) + (c % seglen)];
+        const int nj = min(seglen, max(0, k - g * seglen));
+        const uint4 *seg = reinterpret_cast<const uint4 *>(list + g * (seglen + 2));
+        unsigned cnt = 0;
+        for (int j = 0; j < (nj + 1) / 2; ++j) {
+            const uint4 q = seg[j];
+            const unsigned long long a = ((unsigned long long)q.y << 32) | q.x, b = ((unsigned long long)q.w << 32) | q.z;
+            cnt += (a < mine) ? 1u : 0u;
+            cnt += (b < mine) ? 1u : 0u;
+        }
+        // partner threads of one candidate sit 256 threads apart: combine through shared memory
+        unsigned *rank = reinterpret_cast<unsigned *>(sorted);  // reused below only after the next barrier
+        if (G > 1) {
+            unsigned *part = hist;  // histograms are dead; G * 256 counters fit (3 * nwarps * 32 >= G * 256)
+            part[g * 256 + c] = cnt;
+            SY::sync();
+            if (g == 0) {
+                for (int gg = 1; gg < G; ++gg) cnt += part[gg * 256 + c];
+            }
+        }
+        (void)rank;
+        SY::sync();
+        if (g == 0 && c < k) sorted[cnt] = mine;
+    }
+    SY::sync();
+    const long long q3 = tm_ ? clock64() : 0;
+    // ---- top-k -> top-p -> multinomial on warp 0 (arithmetic identical to block_sample_t) ----
+    if (warp == 0) {
+        const int seg = (k + 31) / 32;  // <= 8
+        const int i0 = min(k, lane * seg), i1 = min(k, i0 + seg);
+        float w[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            w[j] = (i0 + j < i1) ? __uint_as_float(~(uint32_t)(sorted[i0 + j] >> kSelIdxBits)) : 0.f;
+        float local = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (i0 + j < i1) local += w[j];
+        float incl = local;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const float t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+        if (lane == 0) excl = 0.f;
+        const float sum_p = __shfl_sync(0xffffffffu, incl, 31);
+        int kept = k;
+        float total = sum_p;
+        const bool do_topp = !(sp.top_p <= 0.f || sp.top_p >= sum_p) || (sp.top_k >= (uint32_t)n);
+        if (do_topp) {
+            int kl = 0;
+            float tl = 0.f, c = excl;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                if (i0 + j < i1) {
+                    const bool keep = c < sp.top_p;
+                    c += w[j];
+                    if (keep) { kl = i0 + j + 1; tl = c; }
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const int ok = __shfl_xor_sync(0xffffffffu, kl, o);
+                const float ot = __shfl_xor_sync(0xffffffffu, tl, o);
+                if (ok > kl) { kl = ok; tl = ot; }
+            }
+            kept = kl;
+            total = tl;
+        }
+        const float chosen = u * total;
+        int cand = 0x7fffffff;
+        {
+            float c = excl;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                if (i0 + j < min(i1, kept) && cand == 0x7fffffff) {
+                    c += w[j];
+                    if (c > chosen && w[j] > 0.f) cand = i0 + j;
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) cand = min(cand, __shfl_xor_sync(0xffffffffu, cand, o));
+        if (lane == 0) {
+            int pick = cand;
+            if (pick == 0x7fffffff) {
+                pick = max(kept - 1, 0);
+                while (pick > 0 && __uint_as_float(~(uint32_t)(sorted[pick] >> kSelIdxBits)) <= 0.f) --pick;
+            }
+            red_i[0] = (int)(sorted[pick] & ((1u << kSelIdxBits) - 1u));
+        }
+    }
+    SY::sync();
+    const int rsel = red_i[0];
+    SY::sync();
+    if (tm_) {
+        const long long q4 = clock64();
+        g_sample_dbg[0] += q1 - q0; g_sample_dbg[1] += q2 - q1; g_sample_dbg[2] += q3 - q2; g_sample_dbg[3] += 1;
+        g_sample_dbg[4] += q4 - q3;
+    }
+    return rsel;
+}
+
+// n <= 8 * nthreads, n <= 4096, top_k <= kSelMaxK (callers fall back to block_sample otherwise)
+template <class SY>
+__device__ __forceinline__ int block_sample_sel(const float *vals, unsigned char *scratch, float *red, int n,
+                                                const SampleParams &sp, float u) {
+    const int E = (n + SY::nthreads() - 1) / SY::nthreads();
+    if (E <= 2) return block_sample_sel_t<2, SY>(vals, scratch, red, n, sp, u);
+    if (E <= 4) return block_sample_sel_t<4, SY>(vals, scratch, red, n, sp, u);
+    return block_sample_sel_t<8, SY>(vals, scratch, red, n, sp, u);
 }
 
 // Device-resident state of the frame loop (single_batch.rs:19-28 fields that the

@@ -27,6 +27,9 @@ FISH14_TOKENS = dict(im_end_id=4, pad_id=5, semantic_start_id=5, semantic_end_id
 # A small config with the same structure, for tests the CPU oracle finishes in seconds.
 TINY = dict(FISH15, dim=256, n_layer=3, n_fast_layer=2, n_head=4, n_local_heads=2, head_dim=64,
             intermediate_size=512, vocab_size=2304, max_seq_len=512, codebook_size=1024)
+# Full-width blocks (dim 1024, FFN 4096, 16/2 heads) with few layers and a small vocabulary: the shapes the
+# single-row decode megakernel (TMA weight ring) is specialised for, still cheap enough for the CPU oracle.
+WIDE = dict(FISH15, n_layer=2, n_fast_layer=2, vocab_size=2304, max_seq_len=512)
 TINY_TOKENS = dict(im_end_id=1263, pad_id=1200, semantic_start_id=1264, semantic_end_id=1264 + 1023)
 
 

@@ -253,3 +253,29 @@ def test_errors_are_reported(models):
     with pytest.raises(FsbError) as e:
         DualARTransformer(bad, cfg, tok)
     assert e.value.status == -3 and "norm.weight" in str(e.value)
+
+
+@pytest.mark.parametrize("dtype", ["f32", "bf16"])
+def test_single_row_ring_megakernel_full_width(dtype):
+    """Full-width blocks (dim 1024 / FFN 4096 / 16 q + 2 kv heads): one row takes the single-row megakernel
+    (TMA weight ring, register-resident activations, folded RMSNorm).  Token ids equal the oracle's, greedy
+    and sampled, over enough frames to cross an attention-chunk boundary (64 positions) and recycle the ring."""
+    cfg, tok = dict(synth.WIDE), dict(synth.TINY_TOKENS)
+    w = synth.make_lm_weights(cfg, seed=77, round_bf16=(dtype == "bf16"))
+    gpu = DualARTransformer(w, cfg, tok, max_batch=1, max_seq_len=256, decode_mode=2, dtype=dtype)
+    ora = oracle_model(cfg, tok, w)
+    prompt = synth.make_prompt(cfg, tok, 57, seed=21)
+    for sa, so in ((SamplingArgs(temp=0.0), osamp.SamplingArgs(temp=0.0)),
+                   (SamplingArgs(0.7, 0.8, 256, 1.4, seed=11), osamp.SamplingArgs(0.7, 0.8, 256, 1.4, seed=11))):
+        got = generate_blocking(gpu, prompt, 400, sa, fixed_len=12)
+        ora.clear_slow_layer_caches()
+        with torch.no_grad():
+            exp = ogen.generate_blocking(ora, t64(prompt), 400, so, fixed_len=12)
+        np.testing.assert_array_equal(got.astype(np.int64), exp.numpy())
+    # natural stop (no fixed length): the EOS / budget path of the frame loop, and a second call on the same handle
+    got = generate_blocking(gpu, prompt, 57 + 6, SamplingArgs(temp=0.0))
+    ora.clear_slow_layer_caches()
+    with torch.no_grad():
+        exp = ogen.generate_blocking(ora, t64(prompt), 57 + 6, osamp.SamplingArgs(temp=0.0))
+    np.testing.assert_array_equal(got.astype(np.int64), exp.numpy())
+    gpu.close()
