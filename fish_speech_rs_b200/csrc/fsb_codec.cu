@@ -157,23 +157,28 @@ static int load_convnext(fsb_codec *c, const fsb_tensor *w, size_t n, const std:
 }
 
 // ---------------------------------------------------------------- launches
-static int launch_conv(fsb_codec *c, ConvArgs a) {
-    const int BN = 128;
+static int launch_conv(fsb_codec *c, ConvArgs a, int nz = 1) {
     const int off_lo = std::min(0, (a.K - 1) * a.dil) - a.pad, off_hi = std::max(0, (a.K - 1) * a.dil) - a.pad;
-    const int span = (BN - 1) * a.stride + off_hi - off_lo + 1;
-    const int gx = (a.Lout + BN - 1) / BN;
     if (a.Lout <= 0) return FSB_OK;
-#define CONV_CASE(BM, TM)                                                                          \
+#define CONV_CASE(BM, TM, TN)                                                                      \
     {                                                                                              \
+        const int BN = 32 * TN;                                                                    \
+        const int span = (BN - 1) * a.stride + off_hi - off_lo + 1;                                \
+        const int gx = (a.Lout + BN - 1) / BN;                                                     \
         const size_t smem = ((size_t)kConvCK * a.K * BM + (size_t)kConvCK * span) * sizeof(float); \
         FSB_REQUIRE(smem <= 200 * 1024, FSB_ERR_UNSUPPORTED, "conv tile needs %zu B of smem", smem); \
         if (smem > 48 * 1024)                                                                      \
-            FSB_CUDA_OK(cudaFuncSetAttribute(conv1d_kernel<BM, TM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        conv1d_kernel<BM, TM><<<dim3(gx, (a.Cout + BM - 1) / BM), 256, smem, c->stream>>>(a);     \
+            FSB_CUDA_OK(cudaFuncSetAttribute(conv1d_kernel<BM, TM, TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        conv1d_kernel<BM, TM, TN><<<dim3(gx, (a.Cout + BM - 1) / BM, nz), 256, smem, c->stream>>>(a); \
     }
-    if (a.Cout >= 64) CONV_CASE(64, 8)
-    else if (a.Cout >= 32) CONV_CASE(32, 4)
-    else CONV_CASE(16, 2)
+    // 8 x 8 register tiles (64 x 256 outputs per CTA) once the launch still fills the SMs; 8 x 4 below that
+    // 64 x 128 output tiles; launches that would leave most SMs idle (short sequences at the top of the
+    // stack: conv_pre, the first transposed convs) fall back to 32 x 64 tiles = 4x the CTAs
+    const long long ctas64 = (long long)((a.Lout + 127) / 128) * ((a.Cout + 63) / 64) * nz;
+    if (a.Cout >= 64 && ctas64 >= 120) CONV_CASE(64, 8, 4)
+    else if (a.Cout >= 32 && a.Cout < 64 && (long long)((a.Lout + 127) / 128) * ((a.Cout + 31) / 32) * nz >= 120) CONV_CASE(32, 4, 4)
+    else if (a.Cout >= 32) CONV_CASE(32, 4, 2)
+    else CONV_CASE(16, 2, 4)
 #undef CONV_CASE
     CLAUNCH_CHECK(c);
     return FSB_OK;
@@ -199,17 +204,16 @@ static int conv_fwd(fsb_codec *c, const ConvW &w, const float *x, int Lin, float
 static int convT_fwd(fsb_codec *c, const ConvW &w, const float *x, int Lin, float *y, int stride, bool pre_silu) {
     FSB_REQUIRE(w.K == stride || w.K == 2 * stride, FSB_ERR_UNSUPPORTED, "ConvTranspose1d k=%d s=%d unsupported", w.K,
                 stride);
-    for (int r = 0; r < stride; ++r) {
-        ConvArgs a;
-        memset(&a, 0, sizeof(a));
-        a.x = x; a.wt = w.wt; a.bias = w.bias; a.res = nullptr; a.y = y;
-        a.Cin = w.Cin; a.Cout = w.Cout; a.Lin = Lin; a.Lout = Lin; a.Ly = Lin * stride;
-        a.K = w.K / stride; a.Kw = w.K; a.k0 = r; a.kstep = stride;
-        a.dil = -1; a.pad = 0; a.stride = 1; a.ostride = stride; a.ooff = r;
-        a.pre_silu = pre_silu;
-        FSB_TRY(launch_conv(c, a));
-    }
-    return FSB_OK;
+    // one launch, one grid.z slice per output phase r (= t mod stride): taps {r, r + stride}
+    ConvArgs a;
+    memset(&a, 0, sizeof(a));
+    a.x = x; a.wt = w.wt; a.bias = w.bias; a.res = nullptr; a.y = y;
+    a.Cin = w.Cin; a.Cout = w.Cout; a.Lin = Lin; a.Lout = Lin; a.Ly = Lin * stride;
+    a.K = w.K / stride; a.Kw = w.K; a.k0 = 0; a.kstep = stride;
+    a.dil = -1; a.pad = 0; a.stride = 1; a.ostride = stride; a.ooff = 0;
+    a.z_k0 = 1; a.z_ooff = 1;
+    a.pre_silu = pre_silu;
+    return launch_conv(c, a, stride);
 }
 
 // ConvNeXtBlock::forward in place on x (C, L)

@@ -70,17 +70,18 @@ struct ConvArgs {
     int Kw, k0, kstep;         // tap k reads weight slot k0 + k*kstep of Kw
     int dil, pad, stride;      // x index = t*stride + k*dil - pad   (dil may be negative)
     int ostride, ooff;         // output column = t*ostride + ooff
+    int z_k0, z_ooff;          // per blockIdx.z increments of k0 / ooff (transposed conv: one z slice per output phase)
     int pre_silu;              // silu on the input (hifi_gan.rs:76-79,211-213)
     int acc_mode;              // 0: y = v;  1: y = y + v;  2: y = (y + v) * scale   (stack + mean, hifi_gan.rs:113-118)
     float scale;
     int post_tanh;             // hifi_gan.rs:215
 };
 
-constexpr int kConvCK = 8;  // input channels staged per step
+constexpr int kConvCK = 16;  // input channels staged per step (fewer load-sync-compute rounds: the global loads of a round are exposed)
 
-template <int BM, int TM>
+template <int BM, int TM, int TN>
 __global__ void __launch_bounds__(256) conv1d_kernel(ConvArgs a) {
-    constexpr int BN = 128, TN = 4, NTX = 32;  // 32 lanes along t (stride-32 interleave -> conflict-free, coalesced)
+    constexpr int NTX = 32, BN = NTX * TN;  // 32 lanes along t (stride-32 interleave -> conflict-free, coalesced)
     constexpr int NTY = BM / TM;               // 8 warps along co
     static_assert(NTY * NTX == 256, "256 threads");
     extern __shared__ float smem[];
@@ -99,25 +100,41 @@ __global__ void __launch_bounds__(256) conv1d_kernel(ConvArgs a) {
 #pragma unroll
         for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
 
+    const int k0 = a.k0 + (int)blockIdx.z * a.z_k0, ooff = a.ooff + (int)blockIdx.z * a.z_ooff;
+    const bool full_m = co0 + BM <= a.Cout && (a.Cout & 3) == 0;
     for (int c0 = 0; c0 < a.Cin; c0 += kConvCK) {
         const int nc = min(kConvCK, a.Cin - c0);
-        // stage weights: (nc, K, BM)
-        for (int i = tid; i < nc * a.K * BM; i += 256) {
-            const int co = i % BM, k = (i / BM) % a.K, ci = i / (BM * a.K);
-            float w = 0.f;
-            if (co0 + co < a.Cout) w = a.wt[((size_t)(c0 + ci) * a.Kw + a.k0 + k * a.kstep) * a.Cout + co0 + co];
-            ws[i] = w;
-        }
-        // stage x with the causal zero padding
-        for (int i = tid; i < nc * span; i += 256) {
-            const int ci = i / span, p = i % span;
-            const int xi = x_lo + p;
-            float v = 0.f;
-            if (xi >= 0 && xi < a.Lin) {
-                v = a.x[(size_t)(c0 + ci) * a.Lin + xi];
-                if (a.pre_silu) v = silu_f(v);
+        // stage weights: rows (ci, k) of BM contiguous output channels; one division per 16-byte piece
+        if (full_m) {
+            constexpr int PR = BM / 4;  // float4 pieces per row
+            for (int i = tid; i < nc * a.K * PR; i += 256) {
+                const int row = i / PR, q = i - row * PR;
+                const int ci = row / a.K, k = row - ci * a.K;
+                const float4 w4 = *reinterpret_cast<const float4 *>(
+                    a.wt + ((size_t)(c0 + ci) * a.Kw + k0 + k * a.kstep) * a.Cout + co0 + q * 4);
+                *reinterpret_cast<float4 *>(ws + (size_t)row * BM + q * 4) = w4;
             }
-            xs[i] = v;
+        } else {
+            for (int i = tid; i < nc * a.K * BM; i += 256) {
+                const int co = i % BM, k = (i / BM) % a.K, ci = i / (BM * a.K);
+                float w = 0.f;
+                if (co0 + co < a.Cout) w = a.wt[((size_t)(c0 + ci) * a.Kw + k0 + k * a.kstep) * a.Cout + co0 + co];
+                ws[i] = w;
+            }
+        }
+        // stage x with the causal zero padding: one input channel per warp pass, no divisions
+        for (int ci = tid >> 5; ci < nc; ci += 8) {
+            const float *xg = a.x + (size_t)(c0 + ci) * a.Lin;
+            float *xd = xs + (size_t)ci * span;
+            for (int pp = tid & 31; pp < span; pp += 32) {
+                const int xi = x_lo + pp;
+                float v = 0.f;
+                if (xi >= 0 && xi < a.Lin) {
+                    v = xg[xi];
+                    if (a.pre_silu) v = silu_f(v);
+                }
+                xd[pp] = v;
+            }
         }
         __syncthreads();
         for (int ci = 0; ci < nc; ++ci) {
@@ -125,8 +142,16 @@ __global__ void __launch_bounds__(256) conv1d_kernel(ConvArgs a) {
             const float *xrow = xs + (size_t)ci * span - off_lo - a.pad;  // xrow[t_local*stride + k*dil]
             for (int k = 0; k < a.K; ++k) {
                 float w[TM], xv[TN];
+                if (TM % 4 == 0) {  // the warp's TM output channels are contiguous and 16-byte aligned: broadcast LDS.128
 #pragma unroll
-                for (int i = 0; i < TM; ++i) w[i] = wrow[k * BM + i];
+                    for (int i = 0; i < TM; i += 4) {
+                        const float4 w4 = *reinterpret_cast<const float4 *>(wrow + k * BM + i);
+                        w[i] = w4.x; w[i + 1] = w4.y; w[i + 2] = w4.z; w[i + 3] = w4.w;
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < TM; ++i) w[i] = wrow[k * BM + i];
+                }
 #pragma unroll
                 for (int j = 0; j < TN; ++j) xv[j] = xrow[(tx + j * NTX) * a.stride + k * a.dil];
 #pragma unroll
@@ -146,7 +171,7 @@ __global__ void __launch_bounds__(256) conv1d_kernel(ConvArgs a) {
         for (int j = 0; j < TN; ++j) {
             const int t = t0 + tx + j * NTX;
             if (t >= a.Lout) continue;
-            const size_t o = (size_t)co * a.Ly + (size_t)t * a.ostride + a.ooff;
+            const size_t o = (size_t)co * a.Ly + (size_t)t * a.ostride + ooff;
             float v = acc[i][j] + bv;
             if (a.res) v = a.res[o] + v;
             if (a.acc_mode == 1) v = a.y[o] + v;

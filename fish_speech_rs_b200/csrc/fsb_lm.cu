@@ -501,7 +501,8 @@ static size_t mega1_smem_bytes(const fsb_lm *lm, int depth, int *xs_floats, int 
     const int samp_floats = (sel_scratch_bytes(kM1Threads) + 15) / 16 * 4 + ((n_max + 3) & ~3) + 64;
     *xs_floats = (std::max(lm->I, 2 * lm->H * lm->hd) + 3) & ~3;
     *kvs_floats = (std::max(2 * kM1AttChunk * kM1KvStride, samp_floats) + 3) & ~3;
-    const size_t fl = (size_t)*xs_floats + lm->D + kM1ValFloats + 64 + 64 + 8 * 64 + 8 * 68 + *kvs_floats + 4 + 12 + 4 + 20 + 20 +
+    const size_t fl = (size_t)*xs_floats + lm->D + kM1ValFloats + 64 + 64 + 8 * 64 + *kvs_floats + 4 + 12 +
+                      (sizeof(MegaLayer) / 4) * (lm->NL + lm->NFL) + 4 + 20 + 20 +
                       (sizeof(RepPenState) / 4) * 8 + 4 * kM1MaxDepth + 2;
     return (size_t)depth * kM1ChunkBytes + fl * sizeof(float) + 16;
 }

@@ -80,6 +80,7 @@ struct Mega1 {
     unsigned char *ring;
     float *xs, *xres, *val, *red, *kvs, *cs_s, *csf_s, *hmerge;
     int *pos_s, *rtab;
+    const MegaLayer *ltab;
     int *s_active, *s_eos, *s_frame, *s_maxf;
     uint32_t *s_cur, *s_prev;
     RepPenState *s_rep;
@@ -92,9 +93,8 @@ struct Mega1 {
     float xr[32];         // this lane's columns of the staged activation slice (x * g where a norm applies)
     float inv_denom;      // 1 / sqrt(mean(x^2) + eps) of the phase (1 without a norm)
     float2 gpre;          // norm weights of the coming phase for elements 2 * tid, 2 * tid + 1
-    M1Plan plan;
+    struct { int r0, nrows, ksplit, ntasks; } plan;  // consumers' view of the phase (the producer builds full M1Plans)
     int att_item, att_n;
-    long long t_phase0, ring_wait;  // debug timers (FSB_MEGA_TIMERS)
 
     __device__ Mega1(const MegaParams &pp, unsigned char *smem) : p(pp) {
         ring = smem;
@@ -105,10 +105,11 @@ struct Mega1 {
         red = f; f += 64;
         cs_s = f; f += 64;
         csf_s = f; f += 8 * 64;
-        hmerge = f; f += 8 * 68;
+        hmerge = xs;  // attention phases only: xs is idle then
         kvs = f; f += pp.kvs_floats;
         pos_s = reinterpret_cast<int *>(f); f += 4;
         rtab = reinterpret_cast<int *>(f); f += 12;
+        ltab = reinterpret_cast<const MegaLayer *>(f); f += (sizeof(MegaLayer) / 4) * (pp.NL + pp.NFL);
         s_active = reinterpret_cast<int *>(f); f += 1;
         s_eos = reinterpret_cast<int *>(f); f += 1;
         s_frame = reinterpret_cast<int *>(f); f += 1;
@@ -131,8 +132,6 @@ struct Mega1 {
         att_n = 0;
         inv_denom = 1.f;
         gpre = make_float2(1.f, 1.f);
-        t_phase0 = 0;
-        ring_wait = 0;
     }
 
     static __device__ __forceinline__ void csync() { M1Sync::sync(); }
@@ -156,7 +155,8 @@ struct Mega1 {
     enum { K_QKV = 0, K_ATT = 1, K_WO = 2, K_W13 = 3, K_W2 = 4, K_HEAD = 5, K_SAMPLE = 6, K_END = 7 };
     struct Step { int frame, pass, l, kind; };  // pass 0 = slow stack, pass c+1 = fast step of codebook c
 
-    __device__ __forceinline__ const MegaLayer &layer_of(const Step &s) const { return (s.pass == 0 ? p.slow : p.fast)[s.l]; }
+    // layer tables are copied to shared memory once (prep and the producer chase them every phase)
+    __device__ __forceinline__ const MegaLayer &layer_of(const Step &s) const { return ltab[s.pass == 0 ? s.l : p.NL + s.l]; }
 
     __device__ __forceinline__ Step first_step() const {
         Step s;
@@ -254,15 +254,20 @@ struct Mega1 {
 
     __device__ __forceinline__ M1Plan plan_of(const Step &s) const {
         const bool slow = s.pass == 0;
-        switch (s.kind) {
-            case K_QKV: return make_plan(R_QKV, layer_of(s).wqkv, nullptr, p.D, 0, 1);
-            case K_WO: return make_plan(R_WO, layer_of(s).wo, nullptr, p.H * p.hd, 0, 1);
-            case K_W13: return make_plan(R_W13, layer_of(s).w1, layer_of(s).w3, p.D, 0, 1);
-            case K_W2: return make_plan(R_W2, layer_of(s).w2, nullptr, p.I, 0, 1);
-            default:  // K_HEAD
-                if (slow) return make_plan(R_HEAD_SLOW, p.out_w, nullptr, p.D, p.slow_row0, p.slow_rest_base);
-                return make_plan(R_HEAD_FAST, p.fast_out, nullptr, p.D, 0, 1);
+        int rk = R_HEAD_FAST, K = p.D, row_a = 0, row_b = 1;
+        const void *W0 = p.fast_out, *W1 = nullptr;
+        if (s.kind == K_HEAD) {
+            if (slow) { rk = R_HEAD_SLOW; W0 = p.out_w; row_a = p.slow_row0; row_b = p.slow_rest_base; }
+        } else {
+            const MegaLayer &L = layer_of(s);
+            switch (s.kind) {
+                case K_QKV: rk = R_QKV; W0 = L.wqkv; break;
+                case K_WO: rk = R_WO; W0 = L.wo; K = p.H * p.hd; break;
+                case K_W13: rk = R_W13; W0 = L.w1; W1 = L.w3; break;
+                default: rk = R_W2; W0 = L.w2; K = p.I; break;
+            }
         }
+        return make_plan(rk, W0, W1, K, row_a, row_b);  // one body: the plan code stays warm in the I-cache
     }
 
     // ------------------------------------------------------------ producer warp (lane 0)
@@ -358,16 +363,13 @@ struct Mega1 {
         const int depth = p.ring_depth;
         const int nchunks = (plan.ntasks + CT - 1) / CT;
         const int tw = warp % CT;
-        const bool tm = p.dbg != nullptr && tid == 0;
         // slot / parity of chunk gchunk + c, advanced without divisions (cslot, cpar track gchunk itself)
         unsigned slot = cslot + (unsigned)(warp / CT), par = cpar;
         if (slot >= (unsigned)depth) { slot -= depth; par ^= 1; }
 #pragma unroll 1
         for (int c = warp / CT; c < nchunks; c += NG, slot += NG) {
             if (slot >= (unsigned)depth) { slot -= depth; par ^= 1; }
-            const long long w0 = tm ? clock64() : 0;
             m1_mbar_wait(full + slot, par);
-            if (tm) ring_wait += clock64() - w0;
             const int t = c * CT + tw;
             float a = 0.f;
             if (t < plan.ntasks) a = task_dot1(ring + (size_t)slot * kM1ChunkBytes + (size_t)tw * TB);
@@ -677,7 +679,14 @@ struct Mega1 {
     // between barrier arrive and wait: the coming phase's plan and its norm weights
     __device__ __forceinline__ void prep_step(const Step &s) {
         if (s.kind == K_END || s.kind == K_ATT || s.kind == K_SAMPLE) return;
-        plan = plan_of(s);
+        {
+            const int rk = s.kind == K_HEAD ? (s.pass == 0 ? R_HEAD_SLOW : R_HEAD_FAST)
+                         : s.kind == K_QKV ? R_QKV : s.kind == K_WO ? R_WO : s.kind == K_W13 ? R_W13 : R_W2;
+            plan.r0 = rtab[2 * rk];
+            plan.nrows = rtab[2 * rk + 1];
+            plan.ksplit = s.kind == K_W2 ? p.I / kM1Slice : 1;
+            plan.ntasks = plan.nrows * plan.ksplit * (s.kind == K_W13 ? 2 : 1);
+        }
         const float *g = norm_of(s);
         if (g && 2 * tid < p.D) gpre = __ldg(reinterpret_cast<const float2 *>(g) + tid);
     }
@@ -755,23 +764,11 @@ struct Mega1 {
             K = p.I;
             stage_plain(p.h, p.I);
         }
-        const bool sub_timed = p.dbg != nullptr && tid == 0 && blockIdx.x == 0;
-        long long ta = 0, tb = 0;
         csync();
-        if (sub_timed) ta = clock64();
-        finish_norm(D, with_norm);
         load_xr(K > kM1Slice ? (warp % CT) % (K / kM1Slice) : 0);
-        if (sub_timed) tb = clock64();
+        finish_norm(D, with_norm);
         run_tasks1();
         csync();
-        if (sub_timed) {
-            const long long tc = clock64();
-            p.dbg[64 + kind * 4 + 3] += ta - t_phase0;   // prologue (phase start -> activation staged)
-            p.dbg[64 + kind * 4 + 0] += tb - ta;         // norm finish + register load of x
-            p.dbg[64 + kind * 4 + 1] += ring_wait;       // of which: waiting for the ring (warp 0)
-            p.dbg[64 + kind * 4 + 2] += tc - tb;         // tasks
-            ring_wait = 0;
-        }
         // ---- epilogue
         if (kind == K_QKV) {
             // pairs of rows -> rope_i (dual_ar.rs:246-247) -> q buffer / K cache; V rows -> V cache (Tensor::cat, :316-324)
@@ -968,7 +965,6 @@ struct Mega1 {
         while (cur.kind != K_END) {
             unsigned long long t0 = 0, t1 = 0, t2 = 0;
             if (timed) t0 = clock64();
-            t_phase0 = (long long)t0;
             if (cur.kind == K_SAMPLE) {
                 if (samples) {
                     if (cur.pass == 0) sample_slow();
@@ -1013,6 +1009,15 @@ __global__ void __launch_bounds__(kM1AllThreads, 1) mega1_decode_kernel(const __
     Mega1<WT> m(p, mega1_smem);
     if (p.nframes <= 0 || __ldcg(p.st.n_active) == 0) return;
     m.init_row_ranges();
+    {
+        const int nl = p.NL + p.NFL, words = (int)(sizeof(MegaLayer) / 4);
+        uint32_t *dst = reinterpret_cast<uint32_t *>(const_cast<MegaLayer *>(m.ltab));
+        for (int i = threadIdx.x; i < nl * words; i += blockDim.x) {
+            const int l = i / words, w = i - l * words;
+            const MegaLayer *src = l < p.NL ? p.slow + l : p.fast + (l - p.NL);
+            dst[i] = reinterpret_cast<const uint32_t *>(src)[w];
+        }
+    }
     if (threadIdx.x == 0) {
         for (int i = 0; i < p.ring_depth; ++i) {
             m1_mbar_init(m.full + i, 1);
