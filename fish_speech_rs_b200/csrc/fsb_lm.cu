@@ -65,6 +65,7 @@ struct fsb_lm {
     uint64_t launches = 0;
     // tcgen05 prefill (bf16 weights): split-activation buffers (hi | mid | lo) and their TMA maps per N tile
     bool tc_ok = false;
+    float *mega_rep = nullptr;
     size_t smem_optin = 0;  // cudaDevAttrMaxSharedMemoryPerBlockOptin, cached by mega_setup
     __nv_bfloat16 *sp_xn = nullptr, *sp_att = nullptr, *sp_h = nullptr;
     float *tc_ws = nullptr;  // split-K workspace of the decode-sized GEMMs
@@ -585,6 +586,7 @@ static int mega_setup(fsb_lm *lm) {
     const int n_chunks_max = (lm->max_len + kMegaChunk - 1) / kMegaChunk;
     FSB_TRY(dev_alloc(lm, &lm->mega_partial, (size_t)B * lm->H * 2 * n_chunks_max * (lm->hd + 4)));
     FSB_TRY(dev_alloc(lm, &lm->mega_logits, (size_t)B * ldl));
+    FSB_TRY(dev_alloc(lm, &lm->mega_rep, (size_t)(kM1Rep - 1) * (2 * lm->D + lm->I)));
     FSB_TRY(dev_alloc(lm, &lm->mega_bar, 4));  // [0] grid barrier, [1] frames confirmed (single-row kernel)
     if (getenv("FSB_MEGA_TIMERS")) {
         FSB_TRY(dev_alloc(lm, &lm->mega_dbg, 128));
@@ -606,7 +608,7 @@ static int mega_setup(fsb_lm *lm) {
     m.x = lm->s.hidden; m.fx = lm->s.fast_x; m.q = lm->s.q; m.partial = lm->mega_partial; m.h = lm->s.g1;
     m.logits = lm->mega_logits; m.ldl = ldl;
     m.n_chunks_max = n_chunks_max;
-    m.bar = lm->mega_bar; m.dbg = lm->mega_dbg;
+    m.bar = lm->mega_bar; m.dbg = lm->mega_dbg; m.rep = lm->mega_rep;
     m.sem_start = lm->tok.semantic_start_id; m.sem_end = lm->tok.semantic_end_id; m.has_end = lm->tok.has_semantic_end;
     FSB_CUDA_OK(cudaEventCreate(&lm->prof_m0));
     FSB_CUDA_OK(cudaEventCreate(&lm->prof_m1));

@@ -666,6 +666,21 @@ struct Mega1 {
         }
     }
 
+    // ------------------------------------------------------------ replicated activation vectors
+    // Right after a grid barrier all CTAs read the same 4-16 KB vector: 148 requests per 128-byte line
+    // queue up at the few L2 slices that hold it.  Producers therefore store every element kM1Rep times
+    // (replica r at its own address, i.e. its own slices) and CTA b reads replica b % kM1Rep.  (Measured:
+    // -5 % decode time for x / fx / h; replicating q, the attention partials and the fast K/V did not pay
+    // for the extra stores of the few CTAs that produce them.)
+    __device__ __forceinline__ float *stream_rep(bool slow, int rep) const {
+        if (rep == 0) return slow ? p.x : p.fx;
+        return p.rep + (slow ? 0 : (kM1Rep - 1) * p.D) + (rep - 1) * p.D;
+    }
+    __device__ __forceinline__ float *h_rep(int rep) const {
+        return rep == 0 ? p.h : p.rep + 2 * (kM1Rep - 1) * p.D + (rep - 1) * p.I;
+    }
+    __device__ __forceinline__ int my_rep() const { return (int)(blockIdx.x % kM1Rep); }
+
     // ------------------------------------------------------------ one weight phase
     __device__ __forceinline__ const float *norm_of(const Step &s) const {
         const bool slow = s.pass == 0;
@@ -695,7 +710,9 @@ struct Mega1 {
         const bool slow = s.pass == 0;
         const int cb = s.pass - 1;
         const int kind = s.kind;
-        float *xg = slow ? p.x : p.fx;
+        // the slow stream of frame 0 comes from the prefill (canonical copy only) when the launch starts at the tail
+        const bool prefilled = s.frame == 0 && p.first_is_tail != 0;
+        const float *xg = stream_rep(slow, (slow && prefilled) ? 0 : my_rep());
         const size_t kv_stride = (size_t)p.max_batch * p.KV * (slow ? p.max_len : p.fast_len) * p.hd;
         float *kcl = (slow ? p.kc : p.fkc) + s.l * kv_stride, *vcl = (slow ? p.vc : p.fvc) + s.l * kv_stride;
         const int cache_len = slow ? p.max_len : p.fast_len;
@@ -726,7 +743,6 @@ struct Mega1 {
                         const uint32_t code = __ldcg(t + 1 + c);
                         acc = __fadd_rn(acc, __fmul_rn(to_f32(cbe[((size_t)c * p.CS + code) * D + d]), mf));
                     }
-                    if (blockIdx.x == 0) xg[d] = acc;
                     xres[d] = acc;  // scaled into xs below (gpre is laid out for elements 2 * tid, 2 * tid + 1)
                     ss = fmaf(acc, acc, ss);
                 }
@@ -738,8 +754,7 @@ struct Mega1 {
                 const uint32_t code = cb == 0 ? 0u : __ldcg(p.st.cur + cb);
                 float ss = 0.f;
                 for (int d = tid; d < D; d += kM1Threads) {
-                    const float v = cb == 0 ? __ldcg(p.x + d) : to_f32(fe[(size_t)code * D + d]);
-                    if (blockIdx.x == 0) xg[d] = v;
+                    const float v = cb == 0 ? __ldcg(stream_rep(true, prefilled ? 0 : my_rep()) + d) : to_f32(fe[(size_t)code * D + d]);
                     xres[d] = v;
                     ss = fmaf(v, v, ss);
                 }
@@ -762,7 +777,7 @@ struct Mega1 {
             else fast_attn(kcl, vcl, cb);
         } else {  // K_W2
             K = p.I;
-            stage_plain(p.h, p.I);
+            stage_plain(h_rep(my_rep()), p.I);
         }
         csync();
         load_xr(K > kM1Slice ? (warp % CT) % (K / kM1Slice) : 0);
@@ -800,17 +815,20 @@ struct Mega1 {
                 }
             }
         } else {
-            for (int rl = tid; rl < plan.nrows; rl += kM1Threads) {
-                const float s1 = row_val(0, rl);
-                const int r = plan.r0 + rl;
-                if (kind == K_W13) {
-                    p.h[r] = __fmul_rn(silu_f(s1), row_val(1, rl));  // silu(w1 x) * (w3 x), dual_ar.rs:160-165
-                } else if (kind == K_HEAD) {
-                    p.logits[r] = s1;
-                } else if (kind == K_WO) {
-                    xg[r] = __fadd_rn(xres[r], s1);  // residual add, dual_ar.rs:436-440 (xres: this stream at QKV time)
-                } else {  // K_W2: xres holds the stream as staged by w13
-                    xg[r] = __fadd_rn(xres[r], s1);
+            if (kind == K_HEAD) {
+                for (int rl = tid; rl < plan.nrows; rl += kM1Threads) p.logits[plan.r0 + rl] = row_val(0, rl);
+            } else {
+                // thread = (row, replica): every replica of the result vector gets the value
+                for (int i = tid; i < plan.nrows * kM1Rep; i += kM1Threads) {
+                    const int rl = i / kM1Rep, rep = i % kM1Rep;
+                    const int r = plan.r0 + rl;
+                    const float s1 = row_val(0, rl);
+                    if (kind == K_W13) {
+                        h_rep(rep)[r] = __fmul_rn(silu_f(s1), row_val(1, rl));  // silu(w1 x) * (w3 x), dual_ar.rs:160-165
+                    } else {
+                        // residual add, dual_ar.rs:436-440 (xres: the stream as staged by the qkv / w13 prologue)
+                        stream_rep(slow, rep)[r] = __fadd_rn(xres[r], s1);
+                    }
                 }
             }
         }

@@ -21,6 +21,7 @@ constexpr int kM1MaxDepth = 6;
 constexpr int kM1AttChunk = 64;                   // cached positions per attention item
 constexpr int kM1KvStride = 80;                   // floats per staged K/V row (conflict-free LDS.128)
 constexpr int kM1ValFloats = 128;
+constexpr int kM1Rep = 8;  // replicas of the activation vectors every CTA reads after a barrier
 
 struct MegaLayer {
     const void *wqkv, *wo, *w1, *w3, *w2;
@@ -55,6 +56,7 @@ struct MegaParams {
     int xs_floats;   // capacity of the activation staging area (floats)
     int ring_depth;  // single-row kernel (fsb_lm_mega1.cuh): 32 KB slots of the TMA weight ring
     int kvs_floats;  // single-row kernel: K/V staging area == sampler scratch (floats)
+    float *rep;      // single-row kernel: replicas 1..kM1Rep-1 of x | fx | h  ((kM1Rep-1) * (2 D + I) floats)
     int sampler_cta; // single-row kernel: CTA that only samples (-1: CTA 0 samples and streams)
     unsigned long long *dbg;  // optional (FSB_MEGA_TIMERS=1): per phase kind {work ns, barrier ns, count} of CTA 0 and the last CTA
 };
