@@ -252,8 +252,10 @@ def run_ours(a):
     clocks = sampler.stop() if rank == 0 else None
     wb = lm.stats()["weight_bytes_per_frame"]
     if dom_n > 0:
-        dom_kernel = ("mega_decode_kernel (persistent frame loop: weight-streaming GEMV phases + GQA attention + "
-                      "samplers; one launch per utterance batch, timed by CUDA events on its stream in the timed region)")
+        dom_kernel = (("mega1_decode_kernel (single-row persistent frame loop: TMA weight ring + register-resident "
+                       "activations; GEMV phases + GQA attention + samplers" if B == 1 else
+                       "mega_decode_kernel (persistent frame loop: weight-streaming GEMV phases + GQA attention + samplers")
+                      + "; one launch per utterance batch, timed by CUDA events on its stream in the timed region)")
     else:
         # per-op decode path: one extra, untimed, profiled step with per-launch CUDA events around the GEMV
         lm.set_profile(True)
@@ -276,7 +278,7 @@ def run_ours(a):
         e2e = frames_all / (wall_ms_max / 1e3)
         traffic, traffic_note = None, None
         try:
-            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_mega_traffic.json")))
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_mega1_traffic.json" if B == 1 else "r01_mega_traffic.json")))
             if dom_n > 0 and a.dtype == "bf16":
                 # DRAM bytes per frame from the committed ncu capture x frames in this launch
                 traffic = (tr["dram_bytes_read"] + tr["dram_bytes_write"]) / tr["frames_in_launch"] * N

@@ -348,8 +348,7 @@ __device__ __noinline__ int block_sample_sel_t(const float *vals, unsigned char 
     if (lane == 0) { red[warp] = best; red_i[warp] = best_i; }
     // scratch initialisation rides on the same barrier
     for (int i = tid; i < sel_list_entries(nthreads); i += nthreads) list[i] = ~0ull;
-    hist[warp * 32 + lane] = 0;
-    hist[(nwarps + warp) * 32 + lane] = 0;
+    if (warp == 0) { hist[lane] = 0; hist[32 + lane] = 0; }
     if (tid == 0) *counter = 0;
     SY::sync();
     {
@@ -394,25 +393,34 @@ __device__ __noinline__ int block_sample_sel_t(const float *vals, unsigned char 
     }
     const long long q1 = tm_ ? clock64() : 0;
     // ---- radix select: k-th smallest key ----
+    // Round r looks at a 5-bit digit: lane b of every warp counts the warp's matching elements whose digit
+    // is b from six ballots per element (no match_any, no per-element shared-memory traffic), adds the
+    // count to the block histogram (32 bins, one shared atomic per lane), and after one barrier every warp
+    // scans the 32 totals itself.
     const int k = (sp.top_k >= (uint32_t)n) ? n : (int)sp.top_k;
     unsigned long long prefix = 0;
     int krem = k;
 #pragma unroll 1
     for (int r = 0; r < 9; ++r) {
         const int shift = 40 - 5 * r;
-        unsigned *hb = hist + (r % 3) * nwarps * 32, *hn = hist + ((r + 1) % 3) * nwarps * 32;
+        unsigned *hb = hist + (r % 3) * 32, *hn = hist + ((r + 1) % 3) * 32;
+        unsigned cnt = 0;
 #pragma unroll
         for (int e = 0; e < E; ++e) {
             const bool part = (key[e] >> (shift + 5)) == prefix;
-            const unsigned d = part ? (unsigned)(key[e] >> shift) & 31u : 32u;
-            const unsigned m = __match_any_sync(0xffffffffu, d);
-            if (part && lane == __ffs(m) - 1) hb[warp * 32 + d] += __popc(m);
-            __syncwarp();
+            const unsigned d = (unsigned)(key[e] >> shift) & 31u;
+            unsigned m = __ballot_sync(0xffffffffu, part);
+#pragma unroll
+            for (int bit = 0; bit < 5; ++bit) {
+                const unsigned bb = __ballot_sync(0xffffffffu, part && ((d >> bit) & 1u));
+                m &= ((lane >> bit) & 1) ? bb : ~bb;
+            }
+            cnt += __popc(m);
         }
-        if (r >= 1) hn[warp * 32 + lane] = 0;  // buffers 0 and 1 were cleared up front
+        if (cnt) atomicAdd(hb + lane, cnt);
+        if (warp == 0 && r >= 1) hn[lane] = 0;  // buffers 0 and 1 were cleared up front
         SY::sync();
-        unsigned tot = 0;
-        for (int w = 0; w < nwarps; ++w) tot += hb[w * 32 + lane];
+        const unsigned tot = hb[lane];
         unsigned cum = tot;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
