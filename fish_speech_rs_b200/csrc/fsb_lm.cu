@@ -66,6 +66,8 @@ struct fsb_lm {
     // tcgen05 prefill (bf16 weights): split-activation buffers (hi | mid | lo) and their TMA maps per N tile
     bool tc_ok = false;
     float *mega_rep = nullptr;
+    unsigned long long *mega_ll = nullptr;
+    size_t mega_ll_words = 0;
     size_t smem_optin = 0;  // cudaDevAttrMaxSharedMemoryPerBlockOptin, cached by mega_setup
     __nv_bfloat16 *sp_xn = nullptr, *sp_att = nullptr, *sp_h = nullptr;
     float *tc_ws = nullptr;  // split-K workspace of the decode-sized GEMMs
@@ -541,6 +543,19 @@ static int mega_launch(fsb_lm *lm, int row0, int group_index, int nb, int nframe
             mp.xs_floats = xf;
             mp.kvs_floats = kf;
             mp.sampler_cta = getenv("FSB_MEGA_SAMPLER_CTA") ? lm->mega_grid - 1 : -1;
+            // flag-in-data synchronisation instead of grid barriers: opt-in experiment (FSB_MEGA_LL=1).  Measured on
+            // B200 it only ties the barrier version: the tag doubles the bytes every CTA pulls through the few L2
+            // slices that hold a vector, which is exactly where the post-barrier reload is bound
+            const bool ll = getenv("FSB_MEGA_LL") && first_is_tail && mp.sampler_cta < 0 && lm->NL >= 1 && lm->NL < 31 &&
+                            lm->NFL >= 1 && lm->NFL < 31 && lm->C + 2 <= 16 && lm->mega_grid <= kM1FlagStride;
+            mp.ll = ll ? lm->mega_ll : nullptr;
+            if (ll) {
+                const LLLayout lay(lm->D, lm->I, lm->H * lm->hd, lm->KV, lm->hd, lm->NFL, lm->fast_len, lm->H, 2 * mp.n_chunks_max, mp.ldl);
+                unsigned long long *b = lm->mega_ll;
+                mp.ll_xt = b + lay.xt; mp.ll_ht = b + lay.ht; mp.ll_qt = b + lay.qt; mp.ll_nkv = b + lay.nkv; mp.ll_fkv = b + lay.fkv;
+                mp.ll_pt = b + lay.pt; mp.ll_lt = b + lay.lt; mp.ll_ct = b + lay.ct; mp.ll_fl = b + lay.fl;
+            }
+            if (ll) FSB_CUDA_OK(cudaMemsetAsync(lm->mega_ll, 0, lm->mega_ll_words * sizeof(unsigned long long), lm->stream));
             FSB_CUDA_OK(lm->wdt == FSB_F32 ? mega1_launch_f32(mp, lm->mega_grid, smem1, lm->stream)
                                            : mega1_launch_bf16(mp, lm->mega_grid, smem1, lm->stream));
             lm->launches++;
@@ -587,6 +602,11 @@ static int mega_setup(fsb_lm *lm) {
     FSB_TRY(dev_alloc(lm, &lm->mega_partial, (size_t)B * lm->H * 2 * n_chunks_max * (lm->hd + 4)));
     FSB_TRY(dev_alloc(lm, &lm->mega_logits, (size_t)B * ldl));
     FSB_TRY(dev_alloc(lm, &lm->mega_rep, (size_t)(kM1Rep - 1) * (2 * lm->D + lm->I)));
+    {
+        const LLLayout lay(lm->D, lm->I, lm->H * lm->hd, lm->KV, lm->hd, lm->NFL, lm->fast_len, lm->H, 2 * n_chunks_max, ldl);
+        lm->mega_ll_words = lay.total;
+        FSB_TRY(dev_alloc(lm, &lm->mega_ll, lay.total));
+    }
     FSB_TRY(dev_alloc(lm, &lm->mega_bar, 4));  // [0] grid barrier, [1] frames confirmed (single-row kernel)
     if (getenv("FSB_MEGA_TIMERS")) {
         FSB_TRY(dev_alloc(lm, &lm->mega_dbg, 128));

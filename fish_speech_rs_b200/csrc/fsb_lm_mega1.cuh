@@ -58,6 +58,34 @@ __device__ __forceinline__ void m1_bulk_g2s(void *smem, const void *gmem, uint32
                  : "memory");
 }
 
+// ---------------------------------------------------------------- flag-in-data synchronisation ("LL")
+// Every value that crosses CTAs travels as one 8-byte word {fp32 value, 32-bit tag}; the tag names the
+// phase that produced it (frame, pass, layer, kind), so a consumer that sees the tag has the value -- no
+// release fence, no atomic counter, no separate reload after a barrier.  Per-CTA progress flags (plain
+// relaxed stores of the tag, monotonic) are only a hint that keeps the polling traffic small; correctness
+// rests on the tags.  8-byte scalar accesses are single-copy atomic.
+__device__ __forceinline__ void st_ll(unsigned long long *p, float v, unsigned tag) {
+    const unsigned long long w = ((unsigned long long)tag << 32) | __float_as_uint(v);
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_ll_raw(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+constexpr int kLLSpinLimit = 1 << 24;  // ~seconds: a tag that never arrives traps instead of hanging the GPU
+__device__ __forceinline__ float ld_ll(const unsigned long long *p, unsigned tag) {
+    unsigned long long v = ld_ll_raw(p);
+    int spins = 0;
+    while ((unsigned)(v >> 32) != tag) {
+        if (++spins > kLLSpinLimit) __trap();
+        v = ld_ll_raw(p);
+    }
+    return __uint_as_float((unsigned)v);
+}
+__device__ __forceinline__ float ll_take(unsigned long long w, const unsigned long long *p, unsigned tag) {
+    return ((unsigned)(w >> 32) == tag) ? __uint_as_float((unsigned)w) : ld_ll(p, tag);
+}
 // The CTA's share of one weight phase: a stream of tasks (1024-element K-slices, row-major inside
 // the CTA's contiguous row block), made of <= 3 contiguous global segments.
 struct M1Plan {
@@ -67,7 +95,7 @@ struct M1Plan {
     int r0, nrows, ksplit, nmat, ntasks;
 };
 
-template <typename WT>
+template <typename WT, bool LL>
 struct Mega1 {
     static constexpr int NE = WTraits<WT>::NE;                 // elements per 16 bytes
     static constexpr int TB = kM1Slice * (int)sizeof(WT);      // task bytes
@@ -95,8 +123,10 @@ struct Mega1 {
     float2 gpre;          // norm weights of the coming phase for elements 2 * tid, 2 * tid + 1
     struct { int r0, nrows, ksplit, ntasks; } plan;  // consumers' view of the phase (the producer builds full M1Plans)
     int att_item, att_n;
+    int pos0;      // LL: slow position at launch
 
-    __device__ Mega1(const MegaParams &pp, unsigned char *smem) : p(pp) {
+    __device__ Mega1(const MegaParams &pp, unsigned char *smem)
+        : p(pp) {
         ring = smem;
         float *f = reinterpret_cast<float *>(smem + (size_t)pp.ring_depth * kM1ChunkBytes);
         xs = f; f += pp.xs_floats;
@@ -132,6 +162,7 @@ struct Mega1 {
         att_n = 0;
         inv_denom = 1.f;
         gpre = make_float2(1.f, 1.f);
+        pos0 = 0;
     }
 
     static __device__ __forceinline__ void csync() { M1Sync::sync(); }
@@ -150,6 +181,38 @@ struct Mega1 {
         }
         csync();
     }
+
+    // ---- LL: tags, progress flags
+    // tag of the phase (frame, pass, layer, kind); HEAD / SAMPLE count as layer 31 so that tags grow along the schedule
+    static __device__ __forceinline__ unsigned tag_of(int frame, int pass, int l, int kind) {
+        return 1u + ((((unsigned)frame * 16u + (unsigned)pass) * 32u + (unsigned)l) * 8u + (unsigned)kind);
+    }
+    // call after the phase's tagged stores: "CTA blockIdx.x has produced phase `tag`" (hint only)
+    __device__ __forceinline__ void ll_publish(unsigned tag) {
+        csync();
+        if (tid < kM1Rep) st_ll(p.ll_fl + (size_t)tid * kM1FlagStride + blockIdx.x, 0.f, tag);
+    }
+    // wait until CTAs [0, nprod) have published a phase >= tag (tags are monotonic per CTA)
+    __device__ __forceinline__ void ll_wait(unsigned tag, int nprod) {
+        if (warp == 0) {
+            // all flags of a polling round are in flight together: one L2 round trip per round
+            const unsigned long long *f = p.ll_fl + (size_t)my_rep() * kM1FlagStride;
+            int spins = 0;
+            while (true) {
+                unsigned lo = 0xffffffffu;
+#pragma unroll
+                for (int i = 0; i < kM1FlagStride / 32; ++i) {
+                    const int c = lane + 32 * i;
+                    if (c < nprod) lo = min(lo, (unsigned)(ld_ll_raw(f + c) >> 32));
+                }
+                if (__all_sync(0xffffffffu, lo >= tag)) break;
+                if (++spins > kLLSpinLimit) __trap();
+            }
+        }
+        csync();
+    }
+    __device__ __forceinline__ unsigned long long *xt_rep(int par, int rep) const { return p.ll_xt + ((size_t)par * kM1Rep + rep) * p.D; }
+    __device__ __forceinline__ unsigned long long *ht_rep(int rep) const { return p.ll_ht + (size_t)rep * p.I; }
 
     // ------------------------------------------------------------ schedule (shared by producer and consumers)
     enum { K_QKV = 0, K_ATT = 1, K_WO = 2, K_W13 = 3, K_W2 = 4, K_HEAD = 5, K_SAMPLE = 6, K_END = 7 };
@@ -426,6 +489,36 @@ struct Mega1 {
             reinterpret_cast<float4 *>(xs)[(i & ~255) | x4_index(i & 255)] = __ldcg(reinterpret_cast<const float4 *>(src) + i);
     }
 
+    // LL variants: the vector arrives as tagged words (replica my_rep()); same smem results as above
+    __device__ __forceinline__ void stage_norm_ll(const unsigned long long *src, unsigned tag) {
+        float ss = 0.f;
+        if (2 * tid < p.D) {
+            const unsigned long long a = ld_ll_raw(src + 2 * tid), b = ld_ll_raw(src + 2 * tid + 1);
+            float2 v;
+            v.x = ((unsigned)(a >> 32) == tag) ? __uint_as_float((unsigned)a) : ld_ll(src + 2 * tid, tag);
+            v.y = ((unsigned)(b >> 32) == tag) ? __uint_as_float((unsigned)b) : ld_ll(src + 2 * tid + 1, tag);
+            reinterpret_cast<float2 *>(xres)[tid] = v;
+            ss = fmaf(v.x, v.x, v.y * v.y);
+            v.x = __fmul_rn(v.x, gpre.x);
+            v.y = __fmul_rn(v.y, gpre.y);
+            *reinterpret_cast<float2 *>(xs + x_index(2 * tid)) = v;
+        }
+        ss = warp_sum(ss);
+        if (lane == 0) red[warp] = ss;
+    }
+    __device__ __forceinline__ void stage_plain_ll(const unsigned long long *src, int K, unsigned tag) {
+        for (int i = tid; i < K / 4; i += kM1Threads) {
+            unsigned long long w[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) w[j] = ld_ll_raw(src + 4 * i + j);
+            float v[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                v[j] = ((unsigned)(w[j] >> 32) == tag) ? __uint_as_float((unsigned)w[j]) : ld_ll(src + 4 * i + j, tag);
+            reinterpret_cast<float4 *>(xs)[(i & ~255) | x4_index(i & 255)] = make_float4(v[0], v[1], v[2], v[3]);
+        }
+    }
+
     // ------------------------------------------------------------ split-KV GQA attention (slow blocks)
     // item = kvh * n_chunks_max + chunk; positions [chunk*64, min(len, chunk*64 + 64))
     __device__ __forceinline__ void att_stage(const float *kcache, const float *vcache, int kvh, int j0, int from, int to) {
@@ -457,7 +550,7 @@ struct Mega1 {
         cp_async_commit();
     }
 
-    __device__ __forceinline__ void phase_attn_slow(int layer) {
+    __device__ __forceinline__ void phase_attn_slow(int layer, int att_frame) {
         const size_t slow_kv = (size_t)p.max_batch * p.KV * p.max_len * p.hd;
         const float *kcache = p.kc + layer * slow_kv, *vcache = p.vc + layer * slow_kv;
         const int n_rep = p.H / p.KV;
@@ -473,16 +566,44 @@ struct Mega1 {
             const int have = item == att_item ? att_n : 0;
             const int h = kvh * n_rep + hq;
             float4 qv[4];
-            if (hq < n_rep) {
-                const float *qp = p.q + (size_t)h * p.hd + sub * 4;
+            if (LL) {
+                // q and the new K/V row come tagged from the QKV phase of this layer; cached rows (older
+                // positions, fenced once per frame) through cp.async
+                const unsigned qtag = tag_of(att_frame, 0, layer, K_QKV);
+                if (hq < n_rep) {
+                    const unsigned long long *qp = p.ll_qt + (size_t)h * p.hd + sub * 4;
+                    unsigned long long qw[16];
 #pragma unroll
-                for (int jj = 0; jj < 4; ++jj) qv[jj] = __ldcg(reinterpret_cast<const float4 *>(qp + jj * 16));
+                    for (int jj = 0; jj < 16; ++jj) qw[jj] = ld_ll_raw(qp + (jj >> 2) * 16 + (jj & 3));
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) {
+                        qv[jj].x = ll_take(qw[jj * 4 + 0], qp + jj * 16 + 0, qtag); qv[jj].y = ll_take(qw[jj * 4 + 1], qp + jj * 16 + 1, qtag);
+                        qv[jj].z = ll_take(qw[jj * 4 + 2], qp + jj * 16 + 2, qtag); qv[jj].w = ll_take(qw[jj * 4 + 3], qp + jj * 16 + 3, qtag);
+                    }
+                }
+                csync();  // previous item's smem reads are done
+                const int jold = min(j1, len - 1);  // rows below len - 1 are in the cache
+                if (j0 + have < jold) att_stage(kcache, vcache, kvh, j0, have, jold - j0);
+                cp_async_commit();
+                if (j1 == len && tid < 2 * p.hd) {  // this chunk holds the new position
+                    const int which = tid / p.hd, d = tid - which * p.hd;
+                    const float v = ld_ll(p.ll_nkv + (size_t)which * p.KV * p.hd + kvh * p.hd + d, qtag);
+                    kvs[which * kM1AttChunk * kM1KvStride + (len - 1 - j0) * kM1KvStride + d] = v;
+                }
+                cp_async_wait_all();
+                csync();
+            } else {
+                if (hq < n_rep) {
+                    const float *qp = p.q + (size_t)h * p.hd + sub * 4;
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) qv[jj] = __ldcg(reinterpret_cast<const float4 *>(qp + jj * 16));
+                }
+                csync();  // previous item's smem reads are done
+                if (j0 + have < j1) att_stage(kcache, vcache, kvh, j0, have, j1 - j0);
+                cp_async_commit();
+                cp_async_wait_all();
+                csync();
             }
-            csync();  // previous item's smem reads are done
-            if (j0 + have < j1) att_stage(kcache, vcache, kvh, j0, have, j1 - j0);
-            cp_async_commit();
-            cp_async_wait_all();
-            csync();
             float m = -INFINITY, l = 0.f;
             float o[16];
 #pragma unroll
@@ -554,47 +675,79 @@ struct Mega1 {
                 const float M = fmaxf(m, mo);
                 const float wa = (m == -INFINITY) ? 0.f : expf(m - M), wb = (mo == -INFINITY) ? 0.f : expf(mo - M);
                 l = l * wa + lo * wb;
-                float *out = p.partial + ((size_t)h * (2 * p.n_chunks_max) + chunk) * (p.hd + 4);
+                const size_t slot_off = ((size_t)h * (2 * p.n_chunks_max) + chunk) * (p.hd + 4);
+                float *out = p.partial + slot_off;
+                unsigned long long *outl = p.ll_pt + slot_off;
+                const unsigned ptag = tag_of(att_frame, 0, layer, K_ATT);
 #pragma unroll
                 for (int jj = 0; jj < 4; ++jj) {
                     const float4 oo = *reinterpret_cast<const float4 *>(src + jj * 16 + sub * 4);
-                    *reinterpret_cast<float4 *>(out + jj * 16 + sub * 4) =
-                        make_float4(o[jj * 4 + 0] * wa + oo.x * wb, o[jj * 4 + 1] * wa + oo.y * wb,
-                                    o[jj * 4 + 2] * wa + oo.z * wb, o[jj * 4 + 3] * wa + oo.w * wb);
+                    const float4 r4 = make_float4(o[jj * 4 + 0] * wa + oo.x * wb, o[jj * 4 + 1] * wa + oo.y * wb,
+                                                  o[jj * 4 + 2] * wa + oo.z * wb, o[jj * 4 + 3] * wa + oo.w * wb);
+                    if (LL) {
+                        st_ll(outl + jj * 16 + sub * 4 + 0, r4.x, ptag); st_ll(outl + jj * 16 + sub * 4 + 1, r4.y, ptag);
+                        st_ll(outl + jj * 16 + sub * 4 + 2, r4.z, ptag); st_ll(outl + jj * 16 + sub * 4 + 3, r4.w, ptag);
+                    } else {
+                        *reinterpret_cast<float4 *>(out + jj * 16 + sub * 4) = r4;
+                    }
                 }
-                if (sub == 0) { out[p.hd] = M; out[p.hd + 1] = l; }
+                if (sub == 0) {
+                    if (LL) { st_ll(outl + p.hd, M, ptag); st_ll(outl + p.hd + 1, l, ptag); }
+                    else { out[p.hd] = M; out[p.hd + 1] = l; }
+                }
             }
         }
+        if (LL && (int)blockIdx.x < nitems && !is_sampler()) ll_publish(tag_of(att_frame, 0, layer, K_ATT));
         att_item = -1;
     }
 
     // prologue of wo (slow): combine the chunk partials into xs.  Thread = (head, two adjacent dims); the
     // (m, l) pair of a slot is one 8-byte load shared by the warp; 8 slots are in flight at once.
-    __device__ __forceinline__ void combine_attn() {
+    __device__ __forceinline__ void combine_attn(unsigned ll_tag) {
         const int ns = att_chunks();
         const int h = tid >> 5, d2 = (tid & 31) * 2;  // H * hd == 2 * kM1Threads (host-checked: H = 16, hd = 64)
         const float *pp = p.partial + (size_t)h * (2 * p.n_chunks_max) * (p.hd + 4);
+        constexpr int BS = LL ? 4 : 8;  // slots per batch of loads (LL words take two registers each)
         float M = -INFINITY, Lsum = 0.f, o0 = 0.f, o1 = 0.f;
+        const unsigned long long *ppl = p.ll_pt + (size_t)h * (2 * p.n_chunks_max) * (p.hd + 4);
 #pragma unroll 1
-        for (int s0 = 0; s0 < ns; s0 += 8) {
-            float2 ml[8], ov[8];
+        for (int s0 = 0; s0 < ns; s0 += BS) {
+            float2 ml[BS], ov[BS];
+            unsigned long long raw[LL ? 4 * BS : 1];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
+            for (int j = 0; j < BS; ++j) {
                 const int sj = min(s0 + j, ns - 1);  // clamp: the duplicate gets weight 0 below
-                const float *sp = pp + sj * (p.hd + 4);
-                ml[j] = __ldcg(reinterpret_cast<const float2 *>(sp + p.hd));
-                ov[j] = __ldcg(reinterpret_cast<const float2 *>(sp + d2));
-                if (s0 + j >= ns) ml[j].x = -INFINITY;
+                if (LL) {
+                    // (raw words first: all 32 loads of the batch are in flight before the first tag check)
+                    const unsigned long long *sp = ppl + sj * (p.hd + 4);
+                    raw[j * 4 + 0] = ld_ll_raw(sp + p.hd); raw[j * 4 + 1] = ld_ll_raw(sp + p.hd + 1);
+                    raw[j * 4 + 2] = ld_ll_raw(sp + d2); raw[j * 4 + 3] = ld_ll_raw(sp + d2 + 1);
+                } else {
+                    const float *sp = pp + sj * (p.hd + 4);
+                    ml[j] = __ldcg(reinterpret_cast<const float2 *>(sp + p.hd));
+                    ov[j] = __ldcg(reinterpret_cast<const float2 *>(sp + d2));
+                }
+                if (!LL && s0 + j >= ns) ml[j].x = -INFINITY;
+            }
+            if (LL) {
+#pragma unroll
+                for (int j = 0; j < BS; ++j) {
+                    const int sj = min(s0 + j, ns - 1);
+                    const unsigned long long *sp = ppl + sj * (p.hd + 4);
+                    ml[j].x = ll_take(raw[j * 4 + 0], sp + p.hd, ll_tag); ml[j].y = ll_take(raw[j * 4 + 1], sp + p.hd + 1, ll_tag);
+                    ov[j].x = ll_take(raw[j * 4 + 2], sp + d2, ll_tag); ov[j].y = ll_take(raw[j * 4 + 3], sp + d2 + 1, ll_tag);
+                    if (s0 + j >= ns) ml[j].x = -INFINITY;
+                }
             }
             float Mn = M;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) Mn = fmaxf(Mn, ml[j].x);
+            for (int j = 0; j < BS; ++j) Mn = fmaxf(Mn, ml[j].x);
             const float c0 = (M == -INFINITY) ? 0.f : expf(M - Mn);
             Lsum *= c0;
             o0 *= c0;
             o1 *= c0;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
+            for (int j = 0; j < BS; ++j) {
                 const float w = (ml[j].x == -INFINITY) ? 0.f : expf(ml[j].x - Mn);
                 Lsum = fmaf(ml[j].y, w, Lsum);
                 o0 = fmaf(ov[j].x, w, o0);
@@ -606,21 +759,54 @@ struct Mega1 {
     }
 
     // prologue of wo (fast): the whole attention over <= C cached positions, recomputed by every CTA
-    __device__ __forceinline__ void fast_attn(const float *kcache, const float *vcache, int cb) {
+    __device__ __forceinline__ void fast_attn(const float *kcache, const float *vcache, int cb, int ll_frame = 0, int ll_layer = 0) {
         const int Hhd = p.H * p.hd, n_rep = p.H / p.KV;
         const float scale = 1.0f / sqrtf((float)p.hd);
         const int npos = cb + 1;
         float *qs = xs + Hhd;                          // behind the output row (xs holds >= 2 * Hhd floats)
         float *kss = kvs;                              // KV * fast_len * hd
         float *vss = kss + p.KV * p.fast_len * p.hd;   // same
-        for (int i = tid; i < Hhd / 4; i += kM1Threads)
-            reinterpret_cast<float4 *>(qs)[i] = __ldcg(reinterpret_cast<const float4 *>(p.q) + i);
-        const int seg = p.hd / 4;
-        for (int i = tid; i < p.KV * npos * seg; i += kM1Threads) {
-            const int r = i / (npos * seg), rem = i - r * npos * seg;
-            const size_t off = (size_t)r * p.fast_len * p.hd + rem * 4;
-            *reinterpret_cast<float4 *>(kss + off) = __ldcg(reinterpret_cast<const float4 *>(kcache + off));
-            *reinterpret_cast<float4 *>(vss + off) = __ldcg(reinterpret_cast<const float4 *>(vcache + off));
+        if (LL) {
+            // q: this phase's QKV; K / V row j: the QKV phase of pass j + 1 of this frame (tagged fast cache)
+            const unsigned qtag = tag_of(ll_frame, cb + 1, ll_layer, K_QKV);
+            // all of a thread's words are requested before the first tag check (H * hd == 2 * kM1Threads,
+            // KV * fast_len * hd <= 2 * kM1Threads: host-checked)
+            const unsigned long long *ql = p.ll_qt;
+            const size_t lsz = (size_t)p.KV * p.fast_len * p.hd;
+            const unsigned long long *kl = p.ll_fkv + (size_t)ll_layer * 2 * lsz, *vl = kl + lsz;
+            const int nkv = p.KV * npos * p.hd;
+            unsigned long long w[6];
+            size_t off[2];
+            unsigned rtag[2];
+            w[0] = ld_ll_raw(ql + tid);
+            w[1] = ld_ll_raw(ql + tid + kM1Threads);
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int i = tid + u * kM1Threads;
+                const int r = i / (npos * p.hd), rem = i - r * npos * p.hd;
+                off[u] = (size_t)r * p.fast_len * p.hd + rem;
+                rtag[u] = tag_of(ll_frame, rem / p.hd + 1, ll_layer, K_QKV);
+                if (i < nkv) { w[2 + 2 * u] = ld_ll_raw(kl + off[u]); w[3 + 2 * u] = ld_ll_raw(vl + off[u]); }
+            }
+            qs[tid] = ll_take(w[0], ql + tid, qtag);
+            qs[tid + kM1Threads] = ll_take(w[1], ql + tid + kM1Threads, qtag);
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                if (tid + u * kM1Threads < nkv) {
+                    kss[off[u]] = ll_take(w[2 + 2 * u], kl + off[u], rtag[u]);
+                    vss[off[u]] = ll_take(w[3 + 2 * u], vl + off[u], rtag[u]);
+                }
+            }
+        } else {
+            for (int i = tid; i < Hhd / 4; i += kM1Threads)
+                reinterpret_cast<float4 *>(qs)[i] = __ldcg(reinterpret_cast<const float4 *>(p.q) + i);
+            const int seg = p.hd / 4;
+            for (int i = tid; i < p.KV * npos * seg; i += kM1Threads) {
+                const int r = i / (npos * seg), rem = i - r * npos * seg;
+                const size_t off = (size_t)r * p.fast_len * p.hd + rem * 4;
+                *reinterpret_cast<float4 *>(kss + off) = __ldcg(reinterpret_cast<const float4 *>(kcache + off));
+                *reinterpret_cast<float4 *>(vss + off) = __ldcg(reinterpret_cast<const float4 *>(vcache + off));
+            }
         }
         csync();
         // one warp per head: lane = (position j = lane / 4, 16 of the 64 dims) for the scores, then every
@@ -724,23 +910,30 @@ struct Mega1 {
             with_norm = true;
             if (slow) {
                 // once per frame: the slow position and its RoPE row
+                int *codes_s = reinterpret_cast<int *>(red + 32);
+                if (LL) {
+                    // previous frame's codes: tagged words from the sampler (the launch starts at the tail, so
+                    // frame >= 1 here); the position advances by one per slow step
+                    if (tid <= p.C) codes_s[tid] = (int)__float_as_uint(ld_ll(p.ll_ct + tid, tag_of(s.frame - 1, tid, 31, K_SAMPLE)));
+                    csync();
+                }
                 if (tid < p.hd) {
                     const int half = p.hd / 2;
-                    const int pos = __ldcg(p.st.pos);
+                    const int pos = LL ? pos0 + s.frame - 1 : __ldcg(p.st.pos);
                     cs_s[tid] = tid < half ? p.cosT[(size_t)pos * half + tid] : p.sinT[(size_t)pos * half + tid - half];
                     if (tid == 0) pos_s[0] = pos;
                 }
                 // DualARTransformer::embed, dual_ar.rs:532-567, on the previous frame's codes
                 const WT *emb = reinterpret_cast<const WT *>(p.emb), *cbe = reinterpret_cast<const WT *>(p.cb_emb);
                 const uint32_t *t = p.st.prev;
-                const uint32_t tok0 = __ldcg(t);
+                const uint32_t tok0 = LL ? (uint32_t)codes_s[0] : __ldcg(t);
                 const bool msk = p.has_end ? (tok0 <= p.sem_end && tok0 >= p.sem_start) : (tok0 == p.sem_start);
                 const float mf = msk ? 1.f : 0.f;
                 float ss = 0.f;
                 for (int d = tid; d < D; d += kM1Threads) {
                     float acc = to_f32(emb[(size_t)tok0 * D + d]);
                     for (int c = 0; c < p.C; ++c) {
-                        const uint32_t code = __ldcg(t + 1 + c);
+                        const uint32_t code = LL ? (uint32_t)codes_s[1 + c] : __ldcg(t + 1 + c);
                         acc = __fadd_rn(acc, __fmul_rn(to_f32(cbe[((size_t)c * p.CS + code) * D + d]), mf));
                     }
                     xres[d] = acc;  // scaled into xs below (gpre is laid out for elements 2 * tid, 2 * tid + 1)
@@ -751,10 +944,24 @@ struct Mega1 {
             } else {
                 // fast stack input: pre-norm slow hidden (Q1) for codebook 0, else fast_embeddings[previous code]
                 const WT *fe = reinterpret_cast<const WT *>(p.fast_emb);
-                const uint32_t code = cb == 0 ? 0u : __ldcg(p.st.cur + cb);
+                uint32_t code = 0u;
+                if (LL) {
+                    // the code sampled by the previous pass (and, after the slow sample, whether the next frame runs)
+                    int *codes_s = reinterpret_cast<int *>(red + 32);
+                    if (tid == 0) {
+                        if (cb > 0) codes_s[0] = (int)__float_as_uint(ld_ll(p.ll_ct + cb, tag_of(s.frame, cb, 31, K_SAMPLE)));
+                        else *go_frames = (int)__float_as_uint(ld_ll(p.ll_ct + p.C + 1, tag_of(s.frame, 0, 31, K_SAMPLE)));
+                    }
+                    csync();
+                    code = (uint32_t)codes_s[0];
+                } else if (cb > 0) {
+                    code = __ldcg(p.st.cur + cb);
+                }
+                const float *xslow = kvs + 6144;  // LL: raw slow hidden stashed by the slow HEAD prologue
                 float ss = 0.f;
                 for (int d = tid; d < D; d += kM1Threads) {
-                    const float v = cb == 0 ? __ldcg(stream_rep(true, prefilled ? 0 : my_rep()) + d) : to_f32(fe[(size_t)code * D + d]);
+                    const float v = cb == 0 ? (LL ? xslow[d] : __ldcg(stream_rep(true, prefilled ? 0 : my_rep()) + d))
+                                            : to_f32(fe[(size_t)code * D + d]);
                     xres[d] = v;
                     ss = fmaf(v, v, ss);
                 }
@@ -770,14 +977,39 @@ struct Mega1 {
             }
         } else if (kind == K_QKV || kind == K_W13 || kind == K_HEAD) {
             with_norm = true;
-            stage_norm(xg, D, true);
+            if (LL && !(kind == K_HEAD && slow && prefilled)) {
+                // producer of the stream: w2 of the previous layer (qkv), wo of this layer (w13), w2 of the last layer (head)
+                const int pl = kind == K_QKV ? s.l - 1 : kind == K_W13 ? s.l : (slow ? p.NL : p.NFL) - 1;
+                const int pk = kind == K_W13 ? K_WO : K_W2;
+                const unsigned tg = tag_of(s.frame, s.pass, pl, pk);
+                ll_wait(tg, (int)gridDim.x);
+                stage_norm_ll(xt_rep(pk == K_WO ? 0 : 1, my_rep()), tg);
+            } else {
+                stage_norm(xg, D, true);
+            }
+            if (LL && kind == K_HEAD && slow) {
+                csync();  // xres holds the raw slow hidden: keep it for codebook 0 of the fast stack (Q1)
+                if (2 * tid < D) reinterpret_cast<float2 *>(kvs + 6144)[tid] = reinterpret_cast<const float2 *>(xres)[tid];
+            }
         } else if (kind == K_WO) {
             K = p.H * p.hd;
-            if (slow) combine_attn();
-            else fast_attn(kcl, vcl, cb);
+            if (slow) {
+                const unsigned tg = tag_of(s.frame, 0, s.l, K_ATT);
+                if (LL) ll_wait(tg, min(p.KV * att_chunks(), (int)gridDim.x));
+                combine_attn(tg);
+            } else {
+                if (LL) ll_wait(tag_of(s.frame, s.pass, s.l, K_QKV), (int)gridDim.x);
+                fast_attn(kcl, vcl, cb, s.frame, s.l);
+            }
         } else {  // K_W2
             K = p.I;
-            stage_plain(h_rep(my_rep()), p.I);
+            if (LL) {
+                const unsigned tg = tag_of(s.frame, s.pass, s.l, K_W13);
+                ll_wait(tg, (int)gridDim.x);
+                stage_plain_ll(ht_rep(my_rep()), p.I, tg);
+            } else {
+                stage_plain(h_rep(my_rep()), p.I);
+            }
         }
         csync();
         load_xr(K > kM1Slice ? (warp % CT) % (K / kM1Slice) : 0);
@@ -785,6 +1017,7 @@ struct Mega1 {
         run_tasks1();
         csync();
         // ---- epilogue
+        const unsigned mytag = tag_of(s.frame, s.pass, kind == K_HEAD ? 31 : s.l, kind);
         if (kind == K_QKV) {
             // pairs of rows -> rope_i (dual_ar.rs:246-247) -> q buffer / K cache; V rows -> V cache (Tensor::cat, :316-324)
             const int half = p.hd / 2, Hhd = p.H * p.hd, KVhd = p.KV * p.hd;
@@ -799,24 +1032,43 @@ struct Mega1 {
                     const float o0 = __fsub_rn(__fmul_rn(v0, c), __fmul_rn(v1, sn));
                     const float o1 = __fadd_rn(__fmul_rn(v0, sn), __fmul_rn(v1, c));
                     if (r < Hhd) {
-                        p.q[r] = o0;
-                        p.q[r + 1] = o1;
+                        if (LL) { st_ll(p.ll_qt + r, o0, mytag); st_ll(p.ll_qt + r + 1, o1, mytag); }
+                        else { p.q[r] = o0; p.q[r + 1] = o1; }
                     } else {
                         const int rk = r - Hhd, kvh = rk / p.hd, d = rk % p.hd;
-                        float *dst = kcl + ((size_t)kvh * cache_len + pos) * p.hd + d;
-                        dst[0] = o0;
-                        dst[1] = o1;
+                        if (!LL || slow) {
+                            float *dst = kcl + ((size_t)kvh * cache_len + pos) * p.hd + d;
+                            dst[0] = o0;
+                            dst[1] = o1;
+                        }
+                        if (LL) {
+                            unsigned long long *dl = slow ? p.ll_nkv + rk
+                                : p.ll_fkv + (size_t)s.l * 2 * KVhd * p.fast_len + ((size_t)kvh * p.fast_len + pos) * p.hd + d;
+                            st_ll(dl, o0, mytag);
+                            st_ll(dl + 1, o1, mytag);
+                        }
                     }
                 } else {
                     const int rv = r - Hhd - KVhd, kvh = rv / p.hd, d = rv % p.hd;
-                    float *dst = vcl + ((size_t)kvh * cache_len + pos) * p.hd + d;
-                    dst[0] = v0;
-                    dst[1] = v1;
+                    if (!LL || slow) {
+                        float *dst = vcl + ((size_t)kvh * cache_len + pos) * p.hd + d;
+                        dst[0] = v0;
+                        dst[1] = v1;
+                    }
+                    if (LL) {
+                        unsigned long long *dl = slow ? p.ll_nkv + KVhd + rv
+                            : p.ll_fkv + ((size_t)s.l * 2 + 1) * KVhd * p.fast_len + ((size_t)kvh * p.fast_len + pos) * p.hd + d;
+                        st_ll(dl, v0, mytag);
+                        st_ll(dl + 1, v1, mytag);
+                    }
                 }
             }
         } else {
             if (kind == K_HEAD) {
-                for (int rl = tid; rl < plan.nrows; rl += kM1Threads) p.logits[plan.r0 + rl] = row_val(0, rl);
+                for (int rl = tid; rl < plan.nrows; rl += kM1Threads) {
+                    if (LL) st_ll(p.ll_lt + plan.r0 + rl, row_val(0, rl), mytag);
+                    else p.logits[plan.r0 + rl] = row_val(0, rl);
+                }
             } else {
                 // thread = (row, replica): every replica of the result vector gets the value
                 for (int i = tid; i < plan.nrows * kM1Rep; i += kM1Threads) {
@@ -824,14 +1076,19 @@ struct Mega1 {
                     const int r = plan.r0 + rl;
                     const float s1 = row_val(0, rl);
                     if (kind == K_W13) {
-                        h_rep(rep)[r] = __fmul_rn(silu_f(s1), row_val(1, rl));  // silu(w1 x) * (w3 x), dual_ar.rs:160-165
+                        const float hv = __fmul_rn(silu_f(s1), row_val(1, rl));  // silu(w1 x) * (w3 x), dual_ar.rs:160-165
+                        if (LL) st_ll(ht_rep(rep) + r, hv, mytag);
+                        else h_rep(rep)[r] = hv;
                     } else {
                         // residual add, dual_ar.rs:436-440 (xres: the stream as staged by the qkv / w13 prologue)
-                        stream_rep(slow, rep)[r] = __fadd_rn(xres[r], s1);
+                        const float xv = __fadd_rn(xres[r], s1);
+                        if (LL) st_ll(xt_rep(kind == K_WO ? 0 : 1, rep) + r, xv, mytag);
+                        else stream_rep(slow, rep)[r] = xv;
                     }
                 }
             }
         }
+        if (LL) ll_publish(mytag);
     }
 
     // ------------------------------------------------------------ samplers (CTA 0 only; scratch on the K/V staging area)
@@ -861,7 +1118,7 @@ struct Mega1 {
         *sred = *vals + ((n + 3) & ~3);
     }
 
-    __device__ __forceinline__ void sample_slow() {
+    __device__ __forceinline__ void sample_slow(int kframe) {
         const GenState &st = p.st;
         const int n = p.n_slow_logits;
         unsigned char *scratch;
@@ -871,14 +1128,17 @@ struct Mega1 {
             const int frame = s_frame[0];
             const float u = philox_uniform(st.sp.seed, (uint64_t)frame * (st.C + 1), (uint32_t)p.row0);
             uint32_t tok;
+            const unsigned htag = tag_of(kframe, 0, 31, K_HEAD);
+            if (LL) ll_wait(htag, (int)gridDim.x);
             if (st.legacy_slow) {
-                const float eos_l = __ldcg(p.logits), pad_l = __ldcg(p.logits + 1);
+                const float eos_l = LL ? ld_ll(p.ll_lt, htag) : __ldcg(p.logits);
+                const float pad_l = LL ? ld_ll(p.ll_lt + 1, htag) : __ldcg(p.logits + 1);
                 const float mx = fmaxf(pad_l, eos_l);
                 const float e_pad = expf(pad_l - mx), e_eos = expf(eos_l - mx);
                 tok = (st.fixed_len || u < e_pad / (e_pad + e_eos)) ? st.pad_id : st.im_end_id;
             } else {
                 for (int i = tid; i < n; i += kM1Threads) {
-                    float v = __ldcg(p.logits + i);
+                    float v = LL ? ld_ll(p.ll_lt + i, htag) : __ldcg(p.logits + i);
                     if (i == 0 && st.fixed_len) v = -INFINITY;
                     vals[i] = v;
                 }
@@ -899,13 +1159,21 @@ struct Mega1 {
                     }
                 // the next frame runs iff this row goes on (single_batch.rs:193-204): tell every CTA's
                 // producer now, 8 fast steps ahead of the frame boundary
-                if (!eos && frame + 1 < s_maxf[0]) p.bar[1] = (unsigned)(frame + 2);
+                const bool cont = !eos && frame + 1 < s_maxf[0];
+                if (LL) {
+                    // the slow token, and whether frame kframe + 1 runs, as tagged words for every CTA
+                    const unsigned stag = tag_of(kframe, 0, 31, K_SAMPLE);
+                    st_ll(p.ll_ct, __uint_as_float(tok), stag);
+                    st_ll(p.ll_ct + st.C + 1, __uint_as_float((unsigned)(cont ? kframe + 2 : kframe + 1)), stag);
+                } else if (cont) {
+                    p.bar[1] = (unsigned)(frame + 2);
+                }
             }
             csync();
         }
     }
 
-    __device__ __forceinline__ void sample_fast(int cb) {
+    __device__ __forceinline__ void sample_fast(int cb, int kframe) {
         const GenState &st = p.st;
         const int n = p.CS, C = st.C;
         unsigned char *scratch;
@@ -920,8 +1188,10 @@ struct Mega1 {
                 if (tid == 0) rep_pen_update(rp, s_prev[1 + cb]);
                 csync();
             }
+            const unsigned htag = tag_of(kframe, cb + 1, 31, K_HEAD);
+            if (LL) ll_wait(htag, (int)gridDim.x);
             for (int i = tid; i < n; i += kM1Threads) {
-                float v = __ldcg(p.logits + i);
+                float v = LL ? ld_ll(p.ll_lt + i, htag) : __ldcg(p.logits + i);
                 if (frame > 0 && ((rp->seen[i >> 5] >> (i & 31)) & 1u)) v = __fdiv_rn(v, st.sp.penalty);
                 vals[i] = v;
             }
@@ -933,6 +1203,8 @@ struct Mega1 {
                 st.cur[1 + cb] = (uint32_t)a;
             }
         }
+        if (LL && tid == 0)  // published for every pass (0 after <|im_end|>): the next prologue waits for it
+            st_ll(p.ll_ct + 1 + cb, __uint_as_float(s_cur[1 + cb]), tag_of(kframe, cb + 1, 31, K_SAMPLE));
         if (cb == C - 1) {
             csync();
             // frame bookkeeping (single_batch.rs:193-204), write-through
@@ -947,8 +1219,8 @@ struct Mega1 {
                 s_frame[0] = nf;
                 st.frame[0] = nf;
                 if (frame > 0) {
-                    pos_s[0] += 1;
-                    st.pos[0] = pos_s[0];
+                    if (LL) st.pos[0] = pos0 + kframe;  // the launch starts at the tail: frame k >= 1 ran the slow step at pos0 + k - 1
+                    else { pos_s[0] += 1; st.pos[0] = pos_s[0]; }
                 }
                 if (eos || nf >= s_maxf[0]) {
                     s_active[0] = 0;
@@ -972,6 +1244,7 @@ struct Mega1 {
             csf_s[i] = d < half ? p.cosT[(size_t)row * half + d] : p.sinT[(size_t)row * half + d - half];
         }
         if (tid == 0) pos_s[0] = p.st.pos[0];
+        pos0 = p.st.pos[0];
         const bool sampler = is_sampler();                                  // streams nothing
         const bool samples = p.sampler_cta >= 0 ? sampler : blockIdx.x == 0;  // runs the K_SAMPLE phases
         if (samples) load_sampler_state();
@@ -984,24 +1257,28 @@ struct Mega1 {
             unsigned long long t0 = 0, t1 = 0, t2 = 0;
             if (timed) t0 = clock64();
             if (cur.kind == K_SAMPLE) {
+                // LL: once per pass every CTA makes its plain stores (slow K/V cache rows) visible before its next
+                // tagged store, and orders its later cache reads after the tagged data it has seen (hidden behind
+                // the sampler for the 147 CTAs that wait for the code anyway)
+                if (LL) __threadfence();
                 if (samples) {
-                    if (cur.pass == 0) sample_slow();
-                    else sample_fast(cur.pass - 1);
+                    if (cur.pass == 0) sample_slow(cur.frame);
+                    else sample_fast(cur.pass - 1, cur.frame);
                 }
             } else if (!sampler) {
-                if (cur.kind == K_ATT) phase_attn_slow(cur.l);
+                if (cur.kind == K_ATT) phase_attn_slow(cur.l, cur.frame);
                 else gemv_phase(cur);
             }
             const Step nxt = advance(cur);
             if (timed) t1 = clock64();
-            grid_arrive1();
+            if (!LL) grid_arrive1();
             if (!sampler) {
                 if (nxt.kind == K_SAMPLE) prep_step(advance(nxt));
                 else if (cur.kind != K_SAMPLE) prep_step(nxt);
                 if (nxt.kind == K_ATT) att_prefetch(nxt.l);
             }
             if (timed) t2 = clock64();
-            grid_wait1();
+            if (!LL) grid_wait1();
             if (timed) {
                 const unsigned long long t3 = clock64();
                 dbg[cur.kind * 4 + 0] += t1 - t0;
@@ -1009,8 +1286,9 @@ struct Mega1 {
                 dbg[cur.kind * 4 + 2] += t3 - t2;
                 dbg[cur.kind * 4 + 3] += 1;
             }
-            if (cur.kind == K_SAMPLE && cur.pass == 0) {
+            if (!LL && cur.kind == K_SAMPLE && cur.pass == 0) {
                 // CTA 0 published whether frame cur.frame + 1 runs before it arrived at this barrier
+                // (LL: the flag travels with the slow token and is picked up by the first fast prologue)
                 if (tid == 0) *go_frames = (int)ld_relaxed_u32(p.bar + 1);
                 csync();
             }
@@ -1021,10 +1299,10 @@ struct Mega1 {
     }
 };
 
-template <typename WT>
+template <typename WT, bool LL>
 __global__ void __launch_bounds__(kM1AllThreads, 1) mega1_decode_kernel(const __grid_constant__ MegaParams p) {
     extern __shared__ __align__(128) unsigned char mega1_smem[];
-    Mega1<WT> m(p, mega1_smem);
+    Mega1<WT, LL> m(p, mega1_smem);
     if (p.nframes <= 0 || __ldcg(p.st.n_active) == 0) return;
     m.init_row_ranges();
     {
@@ -1039,7 +1317,7 @@ __global__ void __launch_bounds__(kM1AllThreads, 1) mega1_decode_kernel(const __
     if (threadIdx.x == 0) {
         for (int i = 0; i < p.ring_depth; ++i) {
             m1_mbar_init(m.full + i, 1);
-            m1_mbar_init(m.empty + i, Mega1<WT>::CT);
+            m1_mbar_init(m.empty + i, Mega1<WT, LL>::CT);
         }
         *m.go_frames = 1;
         *m.done_flag = 0;
@@ -1055,7 +1333,7 @@ __global__ void __launch_bounds__(kM1AllThreads, 1) mega1_decode_kernel(const __
 
 template <typename WT>
 static cudaError_t mega1_launch_impl(const MegaParams &mp, int grid, size_t smem, cudaStream_t st) {
-    const void *kern = (const void *)mega1_decode_kernel<WT>;
+    const void *kern = mp.ll ? (const void *)mega1_decode_kernel<WT, true> : (const void *)mega1_decode_kernel<WT, false>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     void *args[] = {(void *)&mp};

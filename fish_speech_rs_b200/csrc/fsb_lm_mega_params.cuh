@@ -23,6 +23,25 @@ constexpr int kM1KvStride = 80;                   // floats per staged K/V row (
 constexpr int kM1ValFloats = 128;
 constexpr int kM1Rep = 8;  // replicas of the activation vectors every CTA reads after a barrier
 
+// word offsets of the LL arena (MegaParams::ll); kM1FlagStride flag slots per replica
+constexpr int kM1FlagStride = 160;
+struct LLLayout {
+    size_t xt, ht, qt, nkv, fkv, pt, lt, ct, fl, total;
+    __host__ __device__ LLLayout(int D, int I, int Hhd, int KV, int hd, int NFL, int fast_len, int H, int slots, int ldl) {
+        size_t o = 0;
+        xt = o; o += (size_t)2 * kM1Rep * D;
+        ht = o; o += (size_t)kM1Rep * I;
+        qt = o; o += Hhd;
+        nkv = o; o += (size_t)2 * KV * hd;
+        fkv = o; o += (size_t)NFL * 2 * KV * fast_len * hd;
+        pt = o; o += (size_t)H * slots * (hd + 4);
+        lt = o; o += ldl;
+        ct = o; o += 16;
+        fl = o; o += (size_t)kM1Rep * kM1FlagStride;
+        total = o;
+    }
+};
+
 struct MegaLayer {
     const void *wqkv, *wo, *w1, *w3, *w2;
     const float *attn_norm, *ffn_norm;
@@ -57,6 +76,8 @@ struct MegaParams {
     int ring_depth;  // single-row kernel (fsb_lm_mega1.cuh): 32 KB slots of the TMA weight ring
     int kvs_floats;  // single-row kernel: K/V staging area == sampler scratch (floats)
     float *rep;      // single-row kernel: replicas 1..kM1Rep-1 of x | fx | h  ((kM1Rep-1) * (2 D + I) floats)
+    unsigned long long *ll;  // single-row kernel: arena of tagged words (flag-in-data synchronisation), null = grid barriers
+    unsigned long long *ll_xt, *ll_ht, *ll_qt, *ll_nkv, *ll_fkv, *ll_pt, *ll_lt, *ll_ct, *ll_fl;  // its regions (LLLayout)
     int sampler_cta; // single-row kernel: CTA that only samples (-1: CTA 0 samples and streams)
     unsigned long long *dbg;  // optional (FSB_MEGA_TIMERS=1): per phase kind {work ns, barrier ns, count} of CTA 0 and the last CTA
 };

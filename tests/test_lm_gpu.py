@@ -255,11 +255,13 @@ def test_errors_are_reported(models):
     assert e.value.status == -3 and "norm.weight" in str(e.value)
 
 
-@pytest.mark.parametrize("dtype", ["f32", "bf16"])
-def test_single_row_ring_megakernel_full_width(dtype):
+@pytest.mark.parametrize("dtype,sync", [("f32", "barrier"), ("bf16", "barrier"), ("bf16", "ll")])
+def test_single_row_ring_megakernel_full_width(dtype, sync, monkeypatch):
     """Full-width blocks (dim 1024 / FFN 4096 / 16 q + 2 kv heads): one row takes the single-row megakernel
     (TMA weight ring, register-resident activations, folded RMSNorm).  Token ids equal the oracle's, greedy
     and sampled, over enough frames to cross an attention-chunk boundary (64 positions) and recycle the ring."""
+    if sync == "ll":  # flag-in-data synchronisation instead of grid barriers (opt-in variant of the same kernel)
+        monkeypatch.setenv("FSB_MEGA_LL", "1")
     cfg, tok = dict(synth.WIDE), dict(synth.TINY_TOKENS)
     w = synth.make_lm_weights(cfg, seed=77, round_bf16=(dtype == "bf16"))
     gpu = DualARTransformer(w, cfg, tok, max_batch=1, max_seq_len=256, decode_mode=2, dtype=dtype)
