@@ -335,7 +335,7 @@ static int prefill_chunk(fsb_lm *lm, const uint32_t *toks_dev, int S_total, int 
         rope_append_rows_kernel<<<S, 256, 0, lm->stream>>>(s.qkv, s.q, slow_k(lm, l), slow_v(lm, l), lm->cosT,
                                                            lm->sinT, b, pos0, rope_delta, H, KV, hd, lm->max_len);
         LAUNCH_CHECK(lm);
-        attn_prefill_kernel<<<dim3((S + 3) / 4, H), 128, 0, lm->stream>>>(s.q, slow_k(lm, l), slow_v(lm, l), b, pos0,
+        attn_prefill_kernel<<<dim3((S + kPrefQ - 1) / kPrefQ, KV), 512, 0, lm->stream>>>(s.q, slow_k(lm, l), slow_v(lm, l), b, pos0,
                                                                           S, H, KV, hd, lm->max_len, scale, s.att);
         LAUNCH_CHECK(lm);
         if (tc) {

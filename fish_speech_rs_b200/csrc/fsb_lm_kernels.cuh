@@ -412,56 +412,93 @@ __global__ void rope_append_rows_kernel(const float *__restrict__ qkv, float *__
 }
 
 // Causal attention with KV offset for prefill (get_mask_abs, :702-712: query s sees
-// cached positions [0, pos0 + s]).  grid (ceil(S/4), H), block 128: one warp per query.
-__global__ void attn_prefill_kernel(const float *__restrict__ q, const float *__restrict__ kc,
-                                    const float *__restrict__ vc, int b, int pos0, int S, int H, int KV, int hd,
-                                    int max_len, float scale, float *__restrict__ y) {
+// cached positions [0, pos0 + s]).  grid (ceil(S/8), KV), block 512: one CTA = 8 consecutive queries x the
+// n_rep <= 8 query heads that share one KV head (GQA: replaces repeat_kv); warp w = (query w / n_rep... see below).
+// K / V tiles of 32 positions are staged in shared memory once (coalesced) and reused by all 16 warps.
+constexpr int kPrefQ = 8;          // queries per CTA
+constexpr int kPrefStride = 65;    // floats per staged K row (conflict-free column reads)
+constexpr int kPrefIPW = 4;        // (query, head) items per warp kept in registers while the K / V tiles stream by
+__global__ void __launch_bounds__(512) attn_prefill_kernel(const float *__restrict__ q, const float *__restrict__ kc,
+                                                           const float *__restrict__ vc, int b, int pos0, int S, int H, int KV,
+                                                           int hd, int max_len, float scale, float *__restrict__ y) {
+    // hd == 64 (host-checked).  Work items = kPrefQ queries x n_rep heads; 16 warps x kPrefIPW items per round.
+    __shared__ float ks[32 * kPrefStride];
+    __shared__ float vs[32 * 64];
+    __shared__ float qsm[16 * kPrefIPW][64];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int s = blockIdx.x * 4 + warp, h = blockIdx.y;
-    if (s >= S) return;
-    __shared__ float qsm[4][64];
-    const int kvh = h / (H / KV);
-    qsm[warp][lane] = q[((size_t)s * H + h) * hd + lane];
-    qsm[warp][lane + 32] = q[((size_t)s * H + h) * hd + lane + 32];
-    __syncwarp();
-    const float *qh = qsm[warp];
+    const int n_rep = H / KV, kvh = blockIdx.y;
+    const int s0 = blockIdx.x * kPrefQ;
+    const int nq = min(kPrefQ, S - s0);
+    const int nitems = nq * n_rep;
     const float *kb = kc + ((size_t)b * KV + kvh) * max_len * hd;
     const float *vb = vc + ((size_t)b * KV + kvh) * max_len * hd;
-    const int len = pos0 + s + 1;
-    float m = -INFINITY, l = 0.f, o0 = 0.f, o1 = 0.f;
-    for (int t = 0; t < len; t += 32) {
-        const int j = t + lane;
-        float sc = -INFINITY;
-        if (j < len) {
-            const float4 *kr = reinterpret_cast<const float4 *>(kb + (size_t)j * hd);
-            float acc = 0.f;
+    const int len_max = pos0 + s0 + nq;  // the last query of the CTA sees this many positions
+    for (int it0 = 0; it0 < nitems; it0 += 16 * kPrefIPW) {
+        int sq[kPrefIPW], hh[kPrefIPW];
+        float m[kPrefIPW], l[kPrefIPW], o0[kPrefIPW], o1[kPrefIPW];
+        __syncthreads();  // qsm of the previous round consumed
 #pragma unroll
-            for (int d4 = 0; d4 < 16; ++d4) {
-                float4 kk = kr[d4];
-                acc = fmaf(qh[4 * d4 + 0], kk.x * scale, acc);
-                acc = fmaf(qh[4 * d4 + 1], kk.y * scale, acc);
-                acc = fmaf(qh[4 * d4 + 2], kk.z * scale, acc);
-                acc = fmaf(qh[4 * d4 + 3], kk.w * scale, acc);
+        for (int u = 0; u < kPrefIPW; ++u) {
+            const int item = it0 + u * 16 + warp;
+            const bool active = item < nitems;
+            sq[u] = active ? s0 + item / n_rep : -1;
+            hh[u] = kvh * n_rep + (active ? item % n_rep : 0);
+            m[u] = -INFINITY; l[u] = 0.f; o0[u] = 0.f; o1[u] = 0.f;
+            if (active) {
+                qsm[u * 16 + warp][lane] = q[((size_t)sq[u] * H + hh[u]) * hd + lane];
+                qsm[u * 16 + warp][lane + 32] = q[((size_t)sq[u] * H + hh[u]) * hd + lane + 32];
             }
-            sc = acc;
         }
-        const float m_new = fmaxf(m, warp_max(sc));
-        const float corr = expf(m - m_new);
-        const float p = (j < len) ? expf(sc - m_new) : 0.f;
-        l = l * corr + warp_sum(p);
-        o0 *= corr;
-        o1 *= corr;
-        const int cnt = min(32, len - t);
-        for (int jj = 0; jj < cnt; ++jj) {
-            const float pj = __shfl_sync(0xffffffffu, p, jj);
-            const float *vr = vb + (size_t)(t + jj) * hd;
-            o0 = fmaf(pj, vr[lane], o0);
-            o1 = fmaf(pj, vr[lane + 32], o1);
+        for (int t = 0; t < len_max; t += 32) {
+            __syncthreads();  // previous tile consumed (and qsm written)
+            for (int i = threadIdx.x; i < 32 * 16; i += 512) {
+                const int j = i >> 4, sg = i & 15;
+                float4 kk = make_float4(0.f, 0.f, 0.f, 0.f), vv = kk;
+                if (t + j < len_max) {
+                    kk = *reinterpret_cast<const float4 *>(kb + (size_t)(t + j) * hd + sg * 4);
+                    vv = *reinterpret_cast<const float4 *>(vb + (size_t)(t + j) * hd + sg * 4);
+                }
+                float *kd = ks + j * kPrefStride + sg * 4;
+                kd[0] = kk.x; kd[1] = kk.y; kd[2] = kk.z; kd[3] = kk.w;
+                *reinterpret_cast<float4 *>(vs + j * 64 + sg * 4) = vv;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int u = 0; u < kPrefIPW; ++u) {
+                const int len = pos0 + sq[u] + 1;  // sq < 0: inactive item
+                if (sq[u] < 0 || t >= len) continue;
+                const int j = t + lane;
+                float sc = -INFINITY;
+                if (j < len) {
+                    const float *kr = ks + lane * kPrefStride, *qh = qsm[u * 16 + warp];
+                    float acc = 0.f;
+#pragma unroll
+                    for (int d = 0; d < 64; ++d) acc = fmaf(qh[d], kr[d] * scale, acc);
+                    sc = acc;
+                }
+                const float m_new = fmaxf(m[u], warp_max(sc));
+                const float corr = expf(m[u] - m_new);
+                const float pr = (j < len) ? expf(sc - m_new) : 0.f;
+                l[u] = l[u] * corr + warp_sum(pr);
+                o0[u] *= corr;
+                o1[u] *= corr;
+                const int cnt = min(32, len - t);
+                for (int jj = 0; jj < cnt; ++jj) {
+                    const float pj = __shfl_sync(0xffffffffu, pr, jj);
+                    o0[u] = fmaf(pj, vs[jj * 64 + lane], o0[u]);
+                    o1[u] = fmaf(pj, vs[jj * 64 + lane + 32], o1[u]);
+                }
+                m[u] = m_new;
+            }
         }
-        m = m_new;
+#pragma unroll
+        for (int u = 0; u < kPrefIPW; ++u) {
+            if (sq[u] >= 0) {
+                y[((size_t)sq[u] * H + hh[u]) * hd + lane] = o0[u] / l[u];
+                y[((size_t)sq[u] * H + hh[u]) * hd + lane + 32] = o1[u] / l[u];
+            }
+        }
     }
-    y[((size_t)s * H + h) * hd + lane] = o0 / l;
-    y[((size_t)s * H + h) * hd + lane + 32] = o1 / l;
 }
 
 // ------------------------------------------------------------------ samplers
