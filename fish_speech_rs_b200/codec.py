@@ -9,7 +9,7 @@ from . import _ffi as F
 
 
 class FireflyCodec:
-    """`FireflyCodec::load(cfg, vb, version)`; `.decode`, `.encode_mel`, `.sample_rate`."""
+    """`FireflyCodec::load(cfg, vb, version)`; `.decode`, `.encode` (+ `.log_mel`, `.encode_mel`), `.sample_rate`."""
 
     def __init__(self, weights: Dict[str, "object"], fish_version: str = "1.5", device: int = 0,
                  max_frames: int = 512, with_encoder: bool = False, stream: int = 0):
@@ -71,6 +71,25 @@ class FireflyCodec:
         out = np.zeros((1, 8, cap), np.int64)
         n = C.c_size_t()
         F.check(F.lib().fsb_codec_encode_mel(self._h, mel.ctypes.data, Lm, out.ctypes.data, cap, C.byref(n)))
+        return out[:, :, : n.value].copy()
+
+    def log_mel(self, pcm: np.ndarray) -> np.ndarray:
+        """mono 44.1 kHz pcm f32 (n) -> log-mel f32 (1, 160, Lm)  (`LogMelSpectrogram::forward`, spectrogram.rs:141-158)."""
+        pcm = np.ascontiguousarray(pcm, dtype=np.float32).reshape(-1)
+        cap = pcm.size // 512 + 8
+        out = np.zeros((160, cap), np.float32)
+        n = C.c_size_t()
+        F.check(F.lib().fsb_codec_log_mel(self._h, pcm.ctypes.data, pcm.size, out.ctypes.data, cap, C.byref(n)))
+        # the library writes (160, Lm) densely
+        return out.reshape(-1)[: 160 * n.value].reshape(1, 160, n.value).copy()
+
+    def encode(self, pcm: np.ndarray) -> np.ndarray:
+        """`FireflyCodec::encode` (firefly.rs:36-39): pcm f32 (1, 1, n) -> codes i64 (1, 8, L); the mel stays on the device."""
+        pcm = np.ascontiguousarray(pcm, dtype=np.float32).reshape(-1)
+        cap = pcm.size // 2048 + 8
+        out = np.zeros((1, 8, cap), np.int64)
+        n = C.c_size_t()
+        F.check(F.lib().fsb_codec_encode(self._h, pcm.ctypes.data, pcm.size, out.ctypes.data, cap, C.byref(n)))
         return out[:, :, : n.value].copy()
 
     def stats(self) -> Dict:

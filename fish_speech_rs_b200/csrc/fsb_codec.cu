@@ -57,6 +57,8 @@ struct fsb_codec {
     float *buf[4] = {};  // 4 activation buffers of 32768 * max_frames floats
     float *cn_h = nullptr, *cn_g = nullptr;
     long long *d_idx = nullptr;
+    double *d_tw = nullptr;   // STFT twiddles (cos | sin), encoder only
+    float *d_melfb = nullptr; // mel table (1025, 160), encoder only
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evd0 = nullptr, evd1 = nullptr;
     double device_ms_acc = 0;
     fsb_codec_stats stats;
@@ -153,6 +155,68 @@ static int load_convnext(fsb_codec *c, const fsb_tensor *w, size_t n, const std:
     FSB_TRY(load_vec(c, w, n, p + "pwconv2.weight", {dim, 4 * dim}, &o->pw2_w));
     FSB_TRY(load_vec(c, w, n, p + "pwconv2.bias", {dim}, &o->pw2_b));
     FSB_TRY(load_vec(c, w, n, p + "gamma", {dim}, &o->gamma));  // layer_scale_init_value > 0 in every preset
+    return FSB_OK;
+}
+
+// ---------------------------------------------------------------- log-mel front-end
+static double hz_to_mel_slaney(double f) {
+    const double f_sp = 200.0 / 3.0, min_log_hz = 1000.0, logstep = std::log(6.4) / 27.0;
+    return f >= min_log_hz ? min_log_hz / f_sp + std::log(f / min_log_hz) / logstep : f / f_sp;
+}
+static double mel_to_hz_slaney(double m) {
+    const double f_sp = 200.0 / 3.0, min_log_hz = 1000.0, min_log_mel = min_log_hz / f_sp, logstep = std::log(6.4) / 27.0;
+    return m >= min_log_mel ? min_log_hz * std::exp(logstep * (m - min_log_mel)) : f_sp * m;
+}
+// The table the reference embeds as audio/melfilters160.bytes (spectrogram.rs:85-96): triangular filters on the
+// Slaney mel scale with area normalisation, 1025 x 160, f_max = 22050.  Rebuilt here in double precision; equal to
+// the reference's bytes to 1.8e-7 (tests/golden/mel_golden.json).
+static std::vector<float> mel_filterbank() {
+    const double nyq = 22050.0;
+    std::vector<double> f_pts(kMels + 2);
+    const double m_lo = hz_to_mel_slaney(0.0), m_hi = hz_to_mel_slaney(nyq);
+    for (int i = 0; i < kMels + 2; ++i) f_pts[i] = mel_to_hz_slaney(m_lo + (m_hi - m_lo) * i / (kMels + 1));
+    std::vector<float> fb((size_t)kBins * kMels);
+    for (int k = 0; k < kBins; ++k) {
+        const double fr = nyq * k / (kBins - 1);
+        for (int m = 0; m < kMels; ++m) {
+            const double down = (fr - f_pts[m]) / (f_pts[m + 1] - f_pts[m]);
+            const double up = (f_pts[m + 2] - fr) / (f_pts[m + 2] - f_pts[m + 1]);
+            const double v = std::max(0.0, std::min(down, up)) * (2.0 / (f_pts[m + 2] - f_pts[m]));
+            fb[(size_t)k * kMels + m] = (float)v;
+        }
+    }
+    return fb;
+}
+
+// frames the streaming STFT emits for n samples (stft.rs:52-90 driven by spectrogram.rs:44-66)
+static int n_mel_frames_of(long long n) {
+    const long long lp = n + (kFft - kHop);
+    const long long full = lp / kHop, rem = lp % kHop;
+    long long nf = std::max<long long>(full - (kFft / kHop - 1), 0);
+    if (rem > 0 && lp >= kFft) nf += 1;
+    return (int)nf;
+}
+
+// pcm (host, n samples) -> log-mel (160, Lm) in buf[2]
+static int log_mel_to_device(fsb_codec *c, const float *pcm, long long n, int *Lm_out) {
+    FSB_REQUIRE(c->opt.with_encoder && c->d_tw && c->d_melfb, FSB_ERR_STATE, "codec was created without the encoder");
+    const int pad = (kFft - kHop) / 2;
+    FSB_REQUIRE(n > pad, FSB_ERR_INVALID, "log_mel: %lld samples, need more than the reflect pad (%d)", n, pad);
+    const int Lm = n_mel_frames_of(n);
+    FSB_REQUIRE(Lm >= 4 && Lm <= 4 * c->max_frames, FSB_ERR_INVALID, "log_mel: %d mel frames outside [4, %d]", Lm,
+                4 * c->max_frames);
+    cudaStream_t st = c->stream;
+    const int Lp = (int)n + 2 * pad;
+    float *raw = c->buf[1], *xp = c->buf[3], *mag = c->buf[0];
+    FSB_CUDA_OK(cudaMemcpyAsync(raw, pcm, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, st));
+    reflect_pad_kernel<<<(Lp + 255) / 256, 256, 0, st>>>(raw, (int)n, pad, xp);
+    CLAUNCH_CHECK(c);
+    const size_t smem = 3 * kFft * sizeof(double);
+    stft_mag_kernel<<<Lm, 256, smem, st>>>(xp, Lp, c->d_tw, mag);
+    CLAUNCH_CHECK(c);
+    mel_log_kernel<<<Lm, kMels, 0, st>>>(mag, c->d_melfb, Lm, c->buf[2]);
+    CLAUNCH_CHECK(c);
+    *Lm_out = Lm;
     return FSB_OK;
 }
 
@@ -328,6 +392,17 @@ static int codec_create_impl(fsb_codec *c, const fsb_tensor *w, size_t n) {
     }
     FSB_TRY(load_conv(c, w, n, "head.conv_post.conv", 16, 1, 13, false, &c->conv_post));
     if (c->opt.with_encoder) {
+        // log-mel front-end tables: STFT twiddles (f64) and the Slaney mel table
+        FSB_TRY(calloc_dev(c, &c->d_tw, (size_t)2 * kFft));
+        stft_twiddle_kernel<<<kFft / 256, 256, 0, c->stream>>>(c->d_tw);
+        FSB_CUDA_OK(cudaGetLastError());
+        FSB_CUDA_OK(cudaFuncSetAttribute(stft_mag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(3 * kFft * sizeof(double))));
+        {
+            const std::vector<float> fb = mel_filterbank();
+            FSB_TRY(calloc_dev(c, &c->d_melfb, fb.size()));
+            FSB_CUDA_OK(cudaMemcpyAsync(c->d_melfb, fb.data(), fb.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+            FSB_CUDA_OK(cudaStreamSynchronize(c->stream));  // fb is a local
+        }
         for (int i = 0; i < 2; ++i) {
             const std::string p = "quantizer.downsample." + std::to_string(i) + ".";
             FSB_TRY(load_conv(c, w, n, p + "0.conv", kDim, kDim, 2, false, &c->down_conv[i]));
@@ -465,6 +540,28 @@ int fsb_codec_decode_batch(fsb_codec *c, const uint32_t *const *codes, const int
     return FSB_OK;
 }
 
+static int encode_from_device_mel(fsb_codec *c, int Lm, int64_t *codes, size_t cap, size_t *out_len);
+
+int fsb_codec_log_mel(fsb_codec *c, const float *pcm, int64_t n_samples, float *mel, size_t cap_frames, size_t *out_frames) {
+    FSB_REQUIRE(c && pcm && mel && out_frames, FSB_ERR_INVALID, "log_mel: null argument");
+    FSB_CUDA_OK(cudaSetDevice(c->opt.device));
+    int Lm = 0;
+    FSB_TRY(log_mel_to_device(c, pcm, n_samples, &Lm));
+    FSB_REQUIRE((size_t)Lm <= cap_frames, FSB_ERR_INVALID, "log_mel: capacity %zu < %d frames", cap_frames, Lm);
+    FSB_CUDA_OK(cudaMemcpyAsync(mel, c->buf[2], (size_t)kMels * Lm * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    FSB_CUDA_OK(cudaStreamSynchronize(c->stream));
+    *out_frames = (size_t)Lm;
+    return FSB_OK;
+}
+
+int fsb_codec_encode(fsb_codec *c, const float *pcm, int64_t n_samples, int64_t *codes, size_t cap, size_t *out_len) {
+    FSB_REQUIRE(c && pcm && codes && out_len, FSB_ERR_INVALID, "encode: null argument");
+    FSB_CUDA_OK(cudaSetDevice(c->opt.device));
+    int Lm = 0;
+    FSB_TRY(log_mel_to_device(c, pcm, n_samples, &Lm));  // the mel stays on the device (buf[2])
+    return encode_from_device_mel(c, Lm, codes, cap, out_len);
+}
+
 int fsb_codec_encode_mel(fsb_codec *c, const float *mel, int32_t n_mel_frames, int64_t *codes, size_t cap,
                          size_t *out_len) {
     FSB_REQUIRE(c && mel && codes && out_len, FSB_ERR_INVALID, "encode_mel: null argument");
@@ -473,10 +570,14 @@ int fsb_codec_encode_mel(fsb_codec *c, const float *mel, int32_t n_mel_frames, i
     const int Lm = n_mel_frames;
     FSB_REQUIRE(Lm >= 4 && Lm <= 4 * c->max_frames, FSB_ERR_INVALID, "encode_mel: %d mel frames outside [4, %d]", Lm,
                 4 * c->max_frames);
+    // mel (160, Lm) staged in buf[2]
+    FSB_CUDA_OK(cudaMemcpyAsync(c->buf[2], mel, (size_t)160 * Lm * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    return encode_from_device_mel(c, Lm, codes, cap, out_len);
+}
+
+static int encode_from_device_mel(fsb_codec *c, int Lm, int64_t *codes, size_t cap, size_t *out_len) {
     cudaStream_t st = c->stream;
     float *A = c->buf[0], *B = c->buf[1];
-    // mel (160, Lm) staged in buf[2]
-    FSB_CUDA_OK(cudaMemcpyAsync(c->buf[2], mel, (size_t)160 * Lm * sizeof(float), cudaMemcpyHostToDevice, st));
     // ConvNeXtEncoder::forward (convnext.rs:325-334)
     FSB_TRY(conv_fwd(c, c->stem, c->buf[2], Lm, A, 1, 1, false, nullptr, 0, 0.f, false, nullptr));
     ln_channels_first_kernel<<<(Lm + 3) / 4, 128, 0, st>>>(A, kEncDims[0], Lm, c->stem_ln_w, c->stem_ln_b, 1e-6f, B);

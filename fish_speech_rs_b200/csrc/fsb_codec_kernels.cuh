@@ -337,4 +337,69 @@ __global__ void fsq_encode_kernel(const float *__restrict__ z, int L, int G, con
     idx[(size_t)g * L + t] = (long long)out;
 }
 
+// ------------------------------------------------------------------ log-mel front-end (voice-clone path)
+// LogMelSpectrogram::forward, audio/spectrogram.rs:29-83,141-158 on the streaming STFT of audio/stft.rs:52-90:
+// reflect pad 768 (edge sample repeated), frame f = padded[512 f, 512 f + 2048) x periodic Hann, 2048-point DFT in
+// f64 (the reference: rustfft in f64), magnitude of the first 1025 bins -> f32, + 1e-6, x mel table, clamp, ln.
+constexpr int kFft = 2048, kHop = 512, kBins = 1025, kMels = 160;
+
+// tw[m] = cos(2 pi m / 2048), tw[2048 + m] = sin(2 pi m / 2048), correctly rounded (cospi / sinpi)
+__global__ void stft_twiddle_kernel(double *tw) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m < kFft) {
+        tw[m] = cospi((double)m / 1024.0);
+        tw[kFft + m] = sinpi((double)m / 1024.0);
+    }
+}
+
+__global__ void reflect_pad_kernel(const float *__restrict__ x, int N, int pad, float *__restrict__ xp) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N + 2 * pad) return;
+    int j;
+    if (i < pad) j = pad - 1 - i;                 // spectrogram.rs:18: signal[0..pad] reversed
+    else if (i < pad + N) j = i - pad;
+    else j = N - 1 - (i - pad - N);               // :24: signal[N-pad..] reversed
+    xp[i] = x[j];
+}
+
+// one CTA per frame; direct DFT with a shared twiddle table: bin k = sum_n xw[n] * (cos, -sin)(2 pi k n / 2048).
+// 2.1 M double FMAs per frame -- a few ms for a 13 s clip; exact to ~1e-13 like an f64 FFT.
+__global__ void __launch_bounds__(256) stft_mag_kernel(const float *__restrict__ xp, int Lp, const double *__restrict__ tw,
+                                                       float *__restrict__ mag) {
+    extern __shared__ double stft_sm[];
+    double *xw = stft_sm, *cs = stft_sm + kFft, *sn = cs + kFft;
+    const int f = blockIdx.x;
+    for (int n = threadIdx.x; n < kFft; n += 256) {
+        const int i = f * kHop + n;
+        const double c = tw[n], s = tw[kFft + n];
+        cs[n] = c;
+        sn[n] = s;
+        // periodic Hann (stft.rs:33-35); a final partial chunk is zero padded (:61-64)
+        xw[n] = i < Lp ? (double)xp[i] * (0.5 * (1.0 - c)) : 0.0;
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < kBins; k += 256) {
+        double re = 0.0, im = 0.0;
+        int idx = 0;
+        for (int n = 0; n < kFft; ++n) {
+            re = fma(xw[n], cs[idx], re);
+            im = fma(xw[n], sn[idx], im);
+            idx = (idx + k) & (kFft - 1);
+        }
+        mag[(size_t)f * kBins + k] = (float)sqrt(re * re + im * im) + 1e-6f;  // spectrogram.rs:10,82
+    }
+}
+
+// mel[m, f] = ln(clamp(sum_k mag[f, k] * fb[k, m], 1e-5, 100)); one CTA per frame, thread = mel bin
+__global__ void __launch_bounds__(kMels) mel_log_kernel(const float *__restrict__ mag, const float *__restrict__ fb,
+                                                        int nframes, float *__restrict__ mel) {
+    __shared__ float row[kBins];
+    const int f = blockIdx.x, m = threadIdx.x;
+    for (int k = m; k < kBins; k += kMels) row[k] = mag[(size_t)f * kBins + k];
+    __syncthreads();
+    float acc = 0.f;
+    for (int k = 0; k < kBins; ++k) acc = fmaf(row[k], fb[k * kMels + m], acc);
+    mel[(size_t)m * nframes + f] = logf(fminf(fmaxf(acc, 1e-5f), 100.0f));
+}
+
 }  // namespace fsb

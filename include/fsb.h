@@ -215,6 +215,13 @@ int fsb_codec_decode_batch(fsb_codec *codec, const uint32_t *const *codes, const
 /* FireflyEncoder::encode on a log-mel input, encoder.rs:38-42: mel f32 (1, 160, Lm) -> i64 (1, 8, L). */
 int fsb_codec_encode_mel(fsb_codec *codec, const float *mel, int32_t n_mel_frames, int64_t *codes, size_t cap,
                          size_t *out_len);
+/* LogMelSpectrogram::forward, audio/spectrogram.rs:141-158 (on the streaming STFT of audio/stft.rs:52-90): mono
+ * 44.1 kHz pcm f32 (n_samples) -> log-mel f32 (1, 160, Lm), Lm = fsb-internal frame count of the reference's
+ * chunked STFT (1099 for the 562 265 samples of tests/resources/sky.wav).  Needs with_encoder. */
+int fsb_codec_log_mel(fsb_codec *codec, const float *pcm, int64_t n_samples, float *mel, size_t cap_frames,
+                      size_t *out_frames);
+/* FireflyCodec::encode, firefly.rs:36-39: pcm f32 (1, 1, n_samples) -> i64 (1, 8, L); the mel never leaves the device. */
+int fsb_codec_encode(fsb_codec *codec, const float *pcm, int64_t n_samples, int64_t *codes, size_t cap, size_t *out_len);
 int fsb_codec_get_stats(fsb_codec *codec, fsb_codec_stats *out);
 int32_t fsb_codec_sample_rate(const fsb_codec *codec); /* FireflyCodec.sample_rate, firefly.rs:13 */
 

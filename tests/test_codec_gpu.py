@@ -81,3 +81,33 @@ def test_encode_mel_matches_oracle(codec, codec_weights, Lm):
     # integer indices: exact except where a pre-round value sits within float noise of .5
     mism = (got != exp).mean()
     assert mism <= 0.002, f"{mism:.4f} of the indices differ"
+
+
+@pytest.mark.parametrize("n", [6000, 512 * 40 - 1536, 44100 + 89])
+def test_log_mel_matches_oracle(codec, n):
+    """STFT (f64 DFT, periodic Hann, reflect pad) + mel table + clamp/log on the GPU == oracle.mel (numpy f64 rfft).
+    Lengths: a short clip, an exact multiple of the hop (no partial chunk), one second + a partial chunk."""
+    from oracle import mel as omel
+    rng = np.random.default_rng(n)
+    t = np.arange(n) / 44100.0
+    pcm = (0.3 * np.sin(2 * np.pi * 220.0 * t) + 0.05 * rng.standard_normal(n)).astype(np.float32)
+    pcm[n // 2: n // 2 + 700] = 0.0  # a silent stretch exercises the 1e-6 / clamp floor
+    exp = omel.log_mel(pcm)
+    got = codec.log_mel(pcm)
+    assert got.shape == (1, 160, omel.n_mel_frames(n))
+    # fp32 tolerance on the log-mel: 5e-4 absolute (values span [-11.5, 4.6]); measured 5e-7 on a 13 s clip
+    np.testing.assert_allclose(got[0], exp, atol=5e-4, rtol=0)
+
+
+def test_encode_from_pcm_equals_encode_of_the_oracle_mel(codec, codec_weights):
+    """FireflyCodec::encode (firefly.rs:36-39): pcm -> codes with the mel kept on the device == encoder on the oracle's mel."""
+    from oracle import mel as omel
+    rng = np.random.default_rng(5)
+    n = 30000
+    pcm = (0.2 * rng.standard_normal(n)).astype(np.float32)
+    m = omel.log_mel(pcm)
+    with torch.no_grad():
+        exp = ocodec.encode_mel(torch.from_numpy(m[None]), codec_weights).numpy()
+    got = codec.encode(pcm)
+    assert got.shape == exp.shape
+    assert (got != exp).mean() <= 0.005

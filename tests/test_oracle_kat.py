@@ -157,3 +157,53 @@ def test_tiny_lm_generate_is_deterministic(tiny_lm):
         m.clear_slow_layer_caches()
         o2 = ogen.generate_blocking(m, prompt, 40, a, fixed_len=4)
     assert o1.shape == (8, 4) and torch.equal(o1, o2)
+
+
+# ---------------------------------------------------------------- log-mel front-end
+def test_mel_filterbank_is_pinned_to_the_reference_table():
+    """oracle.mel.mel_filterbank() was compared with the reference's embedded melfilters160.bytes where the reference
+    tree is mounted (tests/golden/make_mel_golden.py); here: the recorded difference, and that the formula has not moved."""
+    import hashlib
+    import json
+    import os
+
+    from oracle import mel
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "mel_golden.json")))
+    assert g["melfilters160_max_abs_diff"] < 5e-7
+    fb = mel.mel_filterbank()
+    assert fb.shape == (1025, 160) and fb.dtype == np.float32
+    assert hashlib.sha256(fb.tobytes()).hexdigest() == g["oracle_fb_sha256"]
+    assert int((fb > 0).sum()) == g["oracle_fb_nonzeros"]
+    np.testing.assert_allclose(fb.sum(0)[:8], g["oracle_fb_col_sums_first8"], rtol=1e-6)
+
+
+def test_mel_frame_count_and_code_frames_of_sky_wav():
+    """562 265 samples (tests/resources/sky.wav) -> 1099 mel frames -> 274 code frames == voices-template/default.npy."""
+    import json
+    import os
+
+    from oracle import mel
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "mel_golden.json")))["sky_wav"]
+    assert mel.n_mel_frames(g["samples"]) == g["mel_frames"] == 1099
+    lm = g["mel_frames"]
+    l1 = (lm - 2) // 2 + 1
+    assert (l1 - 2) // 2 + 1 == g["code_frames"] == 274
+    voice = np.load(os.path.join(os.path.dirname(__file__), "golden", "default_voice.npy"))
+    assert voice.shape == (8, 274)
+    # chunk arithmetic of the streaming STFT: exact multiples of the hop emit no partial frame
+    assert mel.n_mel_frames(512 * 10 - 1536) == 10 - 3
+    assert mel.n_mel_frames(512 * 10 - 1536 + 1) == 10 - 3 + 1
+
+
+def test_mel_of_a_pure_tone_peaks_in_the_right_filter():
+    from oracle import mel
+    sr, f0 = 44100, 1000.0
+    t = np.arange(sr // 2) / sr
+    m = mel.log_mel((0.5 * np.sin(2 * np.pi * f0 * t)).astype(np.float32))
+    assert m.shape == (160, mel.n_mel_frames(len(t)))
+    fb = mel.mel_filterbank()
+    want = int(np.argmax(fb[int(round(f0 / (sr / 2) * 1024))]))
+    assert abs(int(np.argmax(m[:, m.shape[1] // 2])) - want) <= 1
+    assert m.min() >= np.log(1e-5) - 1e-6 and m.max() <= np.log(100.0) + 1e-6
+    # reflect padding repeats the edge sample (spectrogram.rs:14-27)
+    np.testing.assert_array_equal(mel.reflect_pad(np.arange(5, dtype=np.float32), 2), [1, 0, 0, 1, 2, 3, 4, 4, 3])
