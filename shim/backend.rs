@@ -161,6 +161,17 @@ impl FireflyCodec {
         check(unsafe { fsb_codec_decode(self.handle, host.as_ptr(), t as i32, pcm.as_mut_ptr()) })?;
         Tensor::from_vec(pcm, (1, 1, 2048 * t), &Device::Cpu)
     }
+
+    /// `encode(&Tensor f32 (1, 1, N)) -> Tensor i64 (1, 8, L)` (firefly.rs:36-39): log-mel, encoder and FSQ run on the GPU
+    pub fn encode(&self, audio: &Tensor) -> Result<Tensor> {
+        let host: Vec<f32> = audio.to_dtype(DType::F32)?.flatten_all()?.to_vec1()?;
+        let cap = host.len() / 2048 + 8;
+        let mut codes = vec![0i64; 8 * cap];
+        let mut n = 0usize;
+        check(unsafe { fsb_codec_encode(self.handle, host.as_ptr(), host.len() as i64, codes.as_mut_ptr(), cap, &mut n) })?;
+        let rows: Vec<i64> = (0..8).flat_map(|g| codes[g * cap..g * cap + n].to_vec()).collect();
+        Tensor::from_vec(rows, (1, 8, n), &Device::Cpu)
+    }
 }
 
 impl Drop for FireflyCodec {
