@@ -1,6 +1,8 @@
 """GPU parity tests of the dual-AR token loop against the oracle, through the C ABI.
 Tolerances: logits / hidden atol 1e-3 (the reference author's own bar, tests/e2e/
 backbone-allclose.py:82); token ids bit-exact under greedy decode (north_star)."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -281,3 +283,58 @@ def test_single_row_ring_megakernel_full_width(dtype, sync, monkeypatch):
         exp = ogen.generate_blocking(ora, t64(prompt), 57 + 6, osamp.SamplingArgs(temp=0.0))
     np.testing.assert_array_equal(got.astype(np.int64), exp.numpy())
     gpu.close()
+
+
+def test_cfg4_voice_clone_chain(tiny_lm, codec_weights):
+    """cfg4 plumbing: wav -> log-mel -> codes on the GPU (`FireflyCodec::encode`), codes (+1, prompt.rs:88) into a
+    Fish-1.4 style prompt, conditioned greedy decode, vocode.  Same prompt through the oracle: same tokens, same PCM."""
+    from fish_speech_rs_b200 import FireflyCodec
+    from oracle import codec as ocodec
+    cfg, _, w = tiny_lm
+    tok = dict(im_end_id=4, pad_id=5, semantic_start_id=5, semantic_end_id=None)
+    codec = FireflyCodec(codec_weights, max_frames=64, with_encoder=True)
+    rng = np.random.default_rng(11)
+    pcm = (0.2 * rng.standard_normal(2048 * 12)).astype(np.float32)
+    ref_codes = codec.encode(pcm)[0]  # (8, L)
+    L = ref_codes.shape[1]
+    assert L == ((((2048 * 12 + 1536) // 512 - 3) - 2) // 2 + 1 - 2) // 2 + 1
+    prompt = synth.make_prompt(cfg, tok, L + 12, seed=3, voice=(ref_codes + 1).astype(np.int64))
+    gpu = DualARTransformer(w, cfg, tok, fish_version="1.4", max_seq_len=256)
+    ora = oracle_model(cfg, tok, w, "1.4")
+    got = generate_blocking(gpu, prompt, 400, SamplingArgs(temp=0.0), fixed_len=5)
+    with torch.no_grad():
+        exp = ogen.generate_blocking(ora, t64(prompt), 400, osamp.SamplingArgs(temp=0.0), fixed_len=5,
+                                     force_slow=[tok["pad_id"]])
+    np.testing.assert_array_equal(got.astype(np.int64), exp.numpy())
+    out_codes = np.minimum(got, 999)[None]  # random-weight LMs emit codes >= 1000 (Q11): harness-side clamp
+    wav = codec.decode(out_codes)
+    with torch.no_grad():
+        wav_o = ocodec.decode(t64(out_codes), codec_weights).numpy()
+    np.testing.assert_allclose(wav, wav_o, atol=1e-4, rtol=0)
+    gpu.close()
+    codec.close()
+
+
+def test_full_size_properties_fish15():
+    """BASELINE.json's full Fish-1.5 shapes (24 + 4 layers, vocab 102 048; too big for the CPU oracle): properties that
+    do not need it.  (i) the single-row megakernel and the per-op CUDA-graph path -- two independent implementations of
+    the frame loop, with different samplers (radix select vs bitonic sort) -- emit the same codes, greedy and sampled;
+    (ii) a second call with the same seed repeats them, another seed does not; (iii) exactly fixed_len frames, codes < 1024."""
+    cfg, tok = dict(synth.FISH15), dict(synth.FISH15_TOKENS)
+    w = synth.make_lm_weights(cfg, seed=1234, round_bf16=True)
+    voice = np.load(os.path.join(os.path.dirname(__file__), "golden", "default_voice.npy"))
+    prompt = synth.make_prompt(cfg, tok, 384, seed=1000, voice=voice)
+    outs = {}
+    for mode in (2, 1):
+        lm = DualARTransformer(w, cfg, tok, dtype="bf16", max_batch=1, max_seq_len=448, decode_mode=mode)
+        outs[mode, "greedy"] = generate_blocking(lm, prompt, 100000, SamplingArgs(temp=0.0), fixed_len=10)
+        outs[mode, "s5"] = generate_blocking(lm, prompt, 100000, SamplingArgs(0.7, 0.8, 256, 1.4, seed=5), fixed_len=10)
+        if mode == 2:
+            outs["again"] = generate_blocking(lm, prompt, 100000, SamplingArgs(0.7, 0.8, 256, 1.4, seed=5), fixed_len=10)
+            outs["s6"] = generate_blocking(lm, prompt, 100000, SamplingArgs(0.7, 0.8, 256, 1.4, seed=6), fixed_len=10)
+        lm.close()
+    for k in ("greedy", "s5"):
+        assert outs[2, k].shape == (8, 10) and outs[2, k].max() < 1024
+        np.testing.assert_array_equal(outs[2, k], outs[1, k])
+    np.testing.assert_array_equal(outs["again"], outs[2, "s5"])
+    assert not np.array_equal(outs["s6"], outs[2, "s5"])
