@@ -1036,6 +1036,9 @@ static int generate_impl(fsb_lm *lm, const uint32_t *const *prompts, const int32
         if (h[107])
             fprintf(stderr, "[block_sample] max+softmax+keys %.2f  sort|select %.2f  scan|rank %.2f  (walk %.2f) us (n=%llu)\n",
                     h[104] / 1965.0 / h[107], h[105] / 1965.0 / h[107], h[106] / 1965.0 / h[107], h[108] / 1965.0 / h[107], h[107]);
+        if (h[107])
+            fprintf(stderr, "[sampler] per select round: ballots %.3f  atomic+barrier %.3f  scan %.3f us\n",
+                    h[113] / 1965.0 / h[107] / 9, h[114] / 1965.0 / h[107] / 9, h[115] / 1965.0 / h[107] / 9);
         for (int c = 0; c < 2; ++c)
             for (int k = 0; k < 7; ++k) {
                 const unsigned long long *e = h + c * 32 + k * 4;

@@ -402,6 +402,7 @@ __device__ __noinline__ int block_sample_sel_t(const float *vals, unsigned char 
     int krem = k;
 #pragma unroll 1
     for (int r = 0; r < 9; ++r) {
+        const long long r0 = tm_ ? clock64() : 0;
         const int shift = 40 - 5 * r;
         unsigned *hb = hist + (r % 3) * 32, *hn = hist + ((r + 1) % 3) * 32;
         unsigned cnt = 0;
@@ -417,10 +418,12 @@ __device__ __noinline__ int block_sample_sel_t(const float *vals, unsigned char 
             }
             cnt += __popc(m);
         }
+        const long long r1 = tm_ ? clock64() : 0;
         if (cnt) atomicAdd(hb + lane, cnt);
         if (warp == 0 && r >= 1) hn[lane] = 0;  // buffers 0 and 1 were cleared up front
         SY::sync();
         const unsigned tot = hb[lane];
+        const long long r2 = tm_ ? clock64() : 0;
         unsigned cum = tot;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -432,6 +435,10 @@ __device__ __noinline__ int block_sample_sel_t(const float *vals, unsigned char 
         const unsigned below = __shfl_sync(0xffffffffu, cum - tot, d);
         krem -= (int)below;
         prefix = (prefix << 5) | (unsigned)d;
+        if (tm_) {
+            const long long r3 = clock64();
+            g_sample_dbg[9] += r1 - r0; g_sample_dbg[10] += r2 - r1; g_sample_dbg[11] += r3 - r2;
+        }
     }
     const unsigned long long kth = prefix;
     const long long q2 = tm_ ? clock64() : 0;
