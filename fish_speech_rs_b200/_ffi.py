@@ -95,6 +95,9 @@ SYMBOLS = {
     "fsb_codec_decode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "fsb_codec_decode_batch": (C.c_int, [C.c_void_p, P(C.c_void_p), P(C.c_int32), C.c_int32, P(C.c_void_p)]),
     "fsb_codec_encode_mel": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_size_t, P(C.c_size_t)]),
+    "fsb_codec_decode_block": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    "fsb_codec_decode_block_s16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_uint32, C.c_void_p,
+                                            C.c_size_t, P(C.c_size_t)]),
     "fsb_codec_log_mel": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_size_t, P(C.c_size_t)]),
     "fsb_codec_encode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_size_t, P(C.c_size_t)]),
     "fsb_codec_get_stats": (C.c_int, [C.c_void_p, P(fsb_codec_stats)]),

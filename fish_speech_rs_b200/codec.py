@@ -73,6 +73,24 @@ class FireflyCodec:
         F.check(F.lib().fsb_codec_encode_mel(self._h, mel.ctypes.data, Lm, out.ctypes.data, cap, C.byref(n)))
         return out[:, :, : n.value].copy()
 
+    def decode_block(self, codes: np.ndarray, t0: int, t1: int) -> np.ndarray:
+        """frames [t0, t1) of codes u32 (1, 8, T) -> pcm f32 (1, 1, 2048*(t1-t0)), identical to the same samples of
+        `decode(codes)` (causal decoder, 16-frame left halo): the streaming path of speech.rs:180-236."""
+        codes = np.ascontiguousarray(np.asarray(codes, dtype=np.uint32).reshape(8, -1))
+        out = np.zeros((1, 1, 2048 * (t1 - t0)), np.float32)
+        F.check(F.lib().fsb_codec_decode_block(self._h, codes.ctypes.data, codes.shape[1], t0, t1, out.ctypes.data))
+        return out
+
+    def decode_block_s16(self, codes: np.ndarray, t0: int, t1: int, to_rate: int = 0) -> np.ndarray:
+        """same block as s16 for the wire, optionally resampled on the device (functional.rs:3-37, wav.rs:9-13)."""
+        codes = np.ascontiguousarray(np.asarray(codes, dtype=np.uint32).reshape(8, -1))
+        cap = 2048 * (t1 - t0) + 16
+        out = np.zeros(cap, np.int16)
+        n = C.c_size_t()
+        F.check(F.lib().fsb_codec_decode_block_s16(self._h, codes.ctypes.data, codes.shape[1], t0, t1, to_rate,
+                                                   out.ctypes.data, cap, C.byref(n)))
+        return out[: n.value].copy()
+
     def log_mel(self, pcm: np.ndarray) -> np.ndarray:
         """mono 44.1 kHz pcm f32 (n) -> log-mel f32 (1, 160, Lm)  (`LogMelSpectrogram::forward`, spectrogram.rs:141-158)."""
         pcm = np.ascontiguousarray(pcm, dtype=np.float32).reshape(-1)

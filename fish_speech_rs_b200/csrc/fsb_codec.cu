@@ -472,9 +472,87 @@ static int decode_one(fsb_codec *c, const uint32_t *codes, int T, float *pcm) {
     return FSB_OK;
 }
 
+// Left context (code frames) after which a causal decode no longer depends on earlier codes: ConvNeXt k7 at 2x and
+// 4x (3 + 1.5 frames), conv_pre k13 at 4x (3), first transposed conv (0.25), ResBlock1 chains k=11, d=1,3,5 at
+// 32x .. 2048x (180 samples each: 5.6 + 0.7 + 0.35 + 0.18 + 0.09) = 14.7 frames.
+constexpr int kHaloFrames = 16;
+
+// frames [t0, t1) of an utterance whose codes (8, T_total) sit on the host -> device PCM at buf[3] + offset
+static int decode_block_device(fsb_codec *c, const uint32_t *codes, int T_total, int t0, int t1, float **pcm_dev,
+                               long long *n_samples) {
+    FSB_REQUIRE(codes, FSB_ERR_INVALID, "decode: null pointer");
+    FSB_REQUIRE(0 <= t0 && t0 < t1 && t1 <= T_total, FSB_ERR_INVALID, "decode_block: bad frame range [%d, %d) of %d", t0,
+                t1, T_total);
+    const int h = std::min(t0, kHaloFrames), Tb = t1 - t0 + h;
+    FSB_REQUIRE(Tb <= c->max_frames, FSB_ERR_INVALID, "decode_block: %d frames (with halo) exceed max_frames=%d", Tb,
+                c->max_frames);
+    cudaStream_t st = c->stream;
+    // gather the (8, Tb) window out of the row-major (8, T_total) host array
+    FSB_CUDA_OK(cudaMemcpy2DAsync(c->d_codes, (size_t)Tb * sizeof(uint32_t), codes + (t0 - h),
+                                  (size_t)T_total * sizeof(uint32_t), (size_t)Tb * sizeof(uint32_t), kGroups,
+                                  cudaMemcpyHostToDevice, st));
+    FSB_CUDA_OK(cudaEventRecord(c->evd0, st));
+    FSB_TRY(decode_device(c, Tb, c->buf[3]));
+    FSB_CUDA_OK(cudaEventRecord(c->evd1, st));
+    *pcm_dev = c->buf[3] + (size_t)h * 2048;
+    *n_samples = (long long)(t1 - t0) * 2048;
+    return FSB_OK;
+}
+
+static int finish_decode(fsb_codec *c, const char *what) {
+    int err = 0;
+    FSB_CUDA_OK(cudaMemcpyAsync(&err, c->d_err, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    FSB_CUDA_OK(cudaStreamSynchronize(c->stream));
+    FSB_REQUIRE(err == 0, FSB_ERR_INVALID, "%s: a code is >= 1000 (outside the FSQ implicit codebook, Q11)", what);
+    float dms = 0.f;
+    FSB_CUDA_OK(cudaEventElapsedTime(&dms, c->evd0, c->evd1));
+    c->stats.device_ms = dms;
+    return FSB_OK;
+}
+
 }  // namespace fsb
 
 extern "C" {
+
+int fsb_codec_decode_block(fsb_codec *c, const uint32_t *codes, int32_t n_frames_total, int32_t t0, int32_t t1, float *pcm) {
+    FSB_REQUIRE(c && pcm, FSB_ERR_INVALID, "decode_block: null argument");
+    FSB_CUDA_OK(cudaSetDevice(c->opt.device));
+    float *dev = nullptr;
+    long long n = 0;
+    FSB_TRY(decode_block_device(c, codes, n_frames_total, t0, t1, &dev, &n));
+    FSB_CUDA_OK(cudaMemcpyAsync(pcm, dev, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    return finish_decode(c, "decode_block");
+}
+
+int fsb_codec_decode_block_s16(fsb_codec *c, const uint32_t *codes, int32_t n_frames_total, int32_t t0, int32_t t1,
+                               uint32_t to_rate, int16_t *out, size_t cap, size_t *out_len) {
+    FSB_REQUIRE(c && out && out_len, FSB_ERR_INVALID, "decode_block_s16: null argument");
+    FSB_CUDA_OK(cudaSetDevice(c->opt.device));
+    float *dev = nullptr;
+    long long n = 0;
+    FSB_TRY(decode_block_device(c, codes, n_frames_total, t0, t1, &dev, &n));
+    cudaStream_t st = c->stream;
+    const uint32_t from_rate = 44100;
+    long long n_out = n;
+    float *src = dev;
+    if (to_rate != 0 && to_rate != from_rate) {
+        // audio/functional.rs:8-9: ratio and length in f64
+        const double ratio = (double)to_rate / (double)from_rate;
+        n_out = (long long)std::ceil((double)n * ratio);
+        FSB_REQUIRE(n_out >= 1 && (size_t)n_out <= (size_t)32768 * c->max_frames, FSB_ERR_INVALID, "decode_block_s16: %lld output samples",
+                    n_out);
+        resample_linear_kernel<<<(unsigned)((n_out + 255) / 256), 256, 0, st>>>(dev, n, ratio, n_out, c->buf[0]);
+        CLAUNCH_CHECK(c);
+        src = c->buf[0];
+    }
+    FSB_REQUIRE((size_t)n_out <= cap, FSB_ERR_INVALID, "decode_block_s16: capacity %zu < %lld samples", cap, n_out);
+    short *s16 = reinterpret_cast<short *>(c->buf[1]);
+    pcm_f32_to_s16_kernel<<<(unsigned)((n_out + 255) / 256), 256, 0, st>>>(src, n_out, s16);
+    CLAUNCH_CHECK(c);
+    FSB_CUDA_OK(cudaMemcpyAsync(out, s16, (size_t)n_out * sizeof(short), cudaMemcpyDeviceToHost, st));
+    *out_len = (size_t)n_out;
+    return finish_decode(c, "decode_block_s16");
+}
 
 int fsb_codec_create(const fsb_tensor *weights, size_t n_weights, const fsb_codec_options *opts, fsb_codec **out) {
     FSB_REQUIRE(weights && opts && out, FSB_ERR_INVALID, "fsb_codec_create: null argument");

@@ -402,4 +402,30 @@ __global__ void __launch_bounds__(kMels) mel_log_kernel(const float *__restrict_
     mel[(size_t)m * nframes + f] = logf(fminf(fmaxf(acc, 1e-5f), 100.0f));
 }
 
+// ------------------------------------------------------------------ output stage (streaming path)
+// audio/functional.rs:3-37 `resample`: linear interpolation, index arithmetic in f64, weights in f32, two products
+// and one sum (no contraction: bit-exact with the reference's separate mul / add tensors).
+__global__ void resample_linear_kernel(const float *__restrict__ x, long long n, double ratio, long long n_out,
+                                       float *__restrict__ y) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_out) return;
+    const double idx = (double)i / ratio;
+    const double fl = floor(idx);
+    const long long i0 = (long long)fl;
+    long long i1 = (long long)ceil(idx);
+    if (i1 > n - 1) i1 = n - 1;
+    const float t = (float)(idx - fl);
+    const float omt = __fsub_rn(1.0f, t);
+    y[i] = __fadd_rn(__fmul_rn(x[i0], omt), __fmul_rn(x[i1], t));
+}
+
+// audio/wav.rs:9-13 `Sample for f32`: (x.clamp(-1, 1) * 32767.0) as i16 (truncation toward zero; NaN -> 0)
+__global__ void pcm_f32_to_s16_kernel(const float *__restrict__ x, long long n, short *__restrict__ y) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float v = x[i];
+    v = v != v ? 0.f : fminf(fmaxf(v, -1.0f), 1.0f);
+    y[i] = (short)(int)__fmul_rn(v, 32767.0f);
+}
+
 }  // namespace fsb

@@ -212,6 +212,17 @@ int fsb_codec_decode(fsb_codec *codec, const uint32_t *codes, int32_t n_frames, 
  * the server concatenates along time instead, speech.rs:90-91). */
 int fsb_codec_decode_batch(fsb_codec *codec, const uint32_t *const *codes, const int32_t *n_frames, int32_t n,
                            float *const *pcm);
+/* Streaming output stage (server/src/handlers/speech.rs:180-236 vocodes and ships audio block by block).
+ * Frames [t0, t1) of an utterance whose codes (8, n_frames_total) are given in full: every convolution of the decoder
+ * is causal and the receptive field is 14.7 code frames, so the block is decoded with a 16-frame left halo and the
+ * result is bit-identical to the same samples of a whole-utterance fsb_codec_decode. */
+int fsb_codec_decode_block(fsb_codec *codec, const uint32_t *codes, int32_t n_frames_total, int32_t t0, int32_t t1,
+                           float *pcm);
+/* Same block, finished on the device for the wire: optional linear-interpolation resample 44.1 kHz -> to_rate
+ * (audio/functional.rs:3-37; 0 or 44100 = none; the server uses 24 kHz for Opus, opus.rs:12-93) and the f32 -> s16
+ * conversion of audio/wav.rs:9-13; half the bytes of the f32 PCM cross PCIe. */
+int fsb_codec_decode_block_s16(fsb_codec *codec, const uint32_t *codes, int32_t n_frames_total, int32_t t0, int32_t t1,
+                               uint32_t to_rate, int16_t *out, size_t cap, size_t *out_len);
 /* FireflyEncoder::encode on a log-mel input, encoder.rs:38-42: mel f32 (1, 160, Lm) -> i64 (1, 8, L). */
 int fsb_codec_encode_mel(fsb_codec *codec, const float *mel, int32_t n_mel_frames, int64_t *codes, size_t cap,
                          size_t *out_len);

@@ -121,6 +121,8 @@ extern "C" {
     pub fn fsb_codec_create(weights: *const fsb_tensor, n_weights: usize, opts: *const fsb_codec_options, out: *mut *mut fsb_codec) -> c_int;
     pub fn fsb_codec_destroy(codec: *mut fsb_codec) -> c_int;
     pub fn fsb_codec_decode(codec: *mut fsb_codec, codes: *const u32, n_frames: i32, pcm: *mut f32) -> c_int;
+    pub fn fsb_codec_decode_block(codec: *mut fsb_codec, codes: *const u32, n_frames_total: i32, t0: i32, t1: i32, pcm: *mut f32) -> c_int;
+    pub fn fsb_codec_decode_block_s16(codec: *mut fsb_codec, codes: *const u32, n_frames_total: i32, t0: i32, t1: i32, to_rate: u32, out: *mut i16, cap: usize, out_len: *mut usize) -> c_int;
     pub fn fsb_codec_log_mel(codec: *mut fsb_codec, pcm: *const f32, n_samples: i64, mel: *mut f32, cap_frames: usize, out_frames: *mut usize) -> c_int;
     pub fn fsb_codec_encode(codec: *mut fsb_codec, pcm: *const f32, n_samples: i64, codes: *mut i64, cap: usize, out_len: *mut usize) -> c_int;
     pub fn fsb_codec_encode_mel(codec: *mut fsb_codec, mel: *const f32, n_mel_frames: i32, codes: *mut i64, cap: usize, out_len: *mut usize) -> c_int;

@@ -111,3 +111,20 @@ def test_encode_from_pcm_equals_encode_of_the_oracle_mel(codec, codec_weights):
     got = codec.encode(pcm)
     assert got.shape == exp.shape
     assert (got != exp).mean() <= 0.005
+
+
+def test_block_decode_is_bit_identical_to_the_whole_utterance(codec, codec_weights):
+    """Streaming: frames [t0, t1) decoded with a 16-frame causal halo == the same samples of decode(codes), bit for
+    bit (the decoder's receptive field is 14.7 code frames); s16 + 44.1 -> 24 kHz resample on the device == the oracle
+    output stage applied to the float PCM of that block."""
+    from oracle import audio_out as ao
+    rng = np.random.default_rng(3)
+    T = 57
+    codes = rng.integers(0, 1000, size=(1, 8, T)).astype(np.uint32)
+    full = codec.decode(codes)[0, 0]
+    for t0, t1 in ((0, 9), (9, 30), (30, 41), (41, 57), (17, 18)):
+        blk = codec.decode_block(codes, t0, t1)[0, 0]
+        np.testing.assert_array_equal(blk, full[2048 * t0: 2048 * t1])
+        np.testing.assert_array_equal(codec.decode_block_s16(codes, t0, t1), ao.to_i16(blk))
+        np.testing.assert_array_equal(codec.decode_block_s16(codes, t0, t1, to_rate=24000),
+                                      ao.to_i16(ao.resample(blk, 44100, 24000)))

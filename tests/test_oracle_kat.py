@@ -207,3 +207,21 @@ def test_mel_of_a_pure_tone_peaks_in_the_right_filter():
     assert m.min() >= np.log(1e-5) - 1e-6 and m.max() <= np.log(100.0) + 1e-6
     # reflect padding repeats the edge sample (spectrogram.rs:14-27)
     np.testing.assert_array_equal(mel.reflect_pad(np.arange(5, dtype=np.float32), 2), [1, 0, 0, 1, 2, 3, 4, 4, 3])
+
+
+# ---------------------------------------------------------------- output stage (resample, s16, WAV header)
+def test_output_stage_known_answers():
+    from oracle import audio_out as ao
+    x = np.array([0.0, 1.0, 0.0, -1.0], np.float32)
+    # 2x upsampling: indices 0, .5, 1, 1.5, 2, 2.5, 3, 3.5 (ceil clamped to the last sample)
+    np.testing.assert_allclose(ao.resample(x, 1, 2), [0, .5, 1, .5, 0, -.5, -1, -1], atol=0)
+    np.testing.assert_array_equal(ao.resample(x, 44100, 44100), x)
+    assert len(ao.resample(np.zeros(2048 * 3, np.float32), 44100, 24000)) == int(np.ceil(2048 * 3 * 24000 / 44100))
+    # (x.clamp(-1, 1) * 32767) as i16: truncation toward zero, saturation, NaN -> 0
+    np.testing.assert_array_equal(ao.to_i16(np.array([0.5, -0.5, 2.0, -2.0, 1e-5, np.nan, 0.99999], np.float32)),
+                                  [16383, -16383, 32767, -32767, 0, 0, 32766])
+    # write_pcm_as_wav (wav.rs:27-58): 44-byte header, RIFF length = 36 + 2 n, byte rate = 2 sr
+    b = ao.wav_bytes(np.array([1, -2, 3], np.int16), 44100)
+    assert len(b) == 44 + 6 and b[:4] == b"RIFF" and b[8:16] == b"WAVEfmt "
+    assert int.from_bytes(b[4:8], "little") == 36 + 6 and int.from_bytes(b[28:32], "little") == 88200
+    assert int.from_bytes(b[40:44], "little") == 6 and b[44:] == np.array([1, -2, 3], "<i2").tobytes()
