@@ -224,7 +224,7 @@ static int log_mel_to_device(fsb_codec *c, const float *pcm, long long n, int *L
 static int launch_conv(fsb_codec *c, ConvArgs a, int nz = 1) {
     const int off_lo = std::min(0, (a.K - 1) * a.dil) - a.pad, off_hi = std::max(0, (a.K - 1) * a.dil) - a.pad;
     if (a.Lout <= 0) return FSB_OK;
-#define CONV_CASE(BM, TM, TN)                                                                      \
+#define CONV_LAUNCH(BM, TM, TN, KT)                                                                \
     {                                                                                              \
         const int BN = 32 * TN;                                                                    \
         const int span = (BN - 1) * a.stride + off_hi - off_lo + 1;                                \
@@ -232,10 +232,20 @@ static int launch_conv(fsb_codec *c, ConvArgs a, int nz = 1) {
         const size_t smem = ((size_t)kConvCK * a.K * BM + (size_t)kConvCK * span) * sizeof(float); \
         FSB_REQUIRE(smem <= 200 * 1024, FSB_ERR_UNSUPPORTED, "conv tile needs %zu B of smem", smem); \
         if (smem > 48 * 1024)                                                                      \
-            FSB_CUDA_OK(cudaFuncSetAttribute(conv1d_kernel<BM, TM, TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        conv1d_kernel<BM, TM, TN><<<dim3(gx, (a.Cout + BM - 1) / BM, nz), 256, smem, c->stream>>>(a); \
+            FSB_CUDA_OK(cudaFuncSetAttribute(conv1d_kernel<BM, TM, TN, KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        conv1d_kernel<BM, TM, TN, KT><<<dim3(gx, (a.Cout + BM - 1) / BM, nz), 256, smem, c->stream>>>(a); \
     }
-    // 8 x 8 register tiles (64 x 256 outputs per CTA) once the launch still fills the SMs; 8 x 4 below that
+    // taps of the ResBlock convs (3 / 7 / 11), of the transposed-conv phases (2) and of conv_pre / conv_post (13) are
+    // compile-time constants of the kernel; anything else runs the generic tap loop
+#define CONV_CASE(BM, TM, TN)                                                                      \
+    switch (a.K) {                                                                                 \
+        case 2: CONV_LAUNCH(BM, TM, TN, 2) break;                                                  \
+        case 3: CONV_LAUNCH(BM, TM, TN, 3) break;                                                  \
+        case 7: CONV_LAUNCH(BM, TM, TN, 7) break;                                                  \
+        case 11: CONV_LAUNCH(BM, TM, TN, 11) break;                                                \
+        case 13: CONV_LAUNCH(BM, TM, TN, 13) break;                                                \
+        default: CONV_LAUNCH(BM, TM, TN, 0) break;                                                 \
+    }
     // 64 x 128 output tiles; launches that would leave most SMs idle (short sequences at the top of the
     // stack: conv_pre, the first transposed convs) fall back to 32 x 64 tiles = 4x the CTAs
     const long long ctas64 = (long long)((a.Lout + 127) / 128) * ((a.Cout + 63) / 64) * nz;
@@ -243,6 +253,7 @@ static int launch_conv(fsb_codec *c, ConvArgs a, int nz = 1) {
     else if (a.Cout >= 32 && a.Cout < 64 && (long long)((a.Lout + 127) / 128) * ((a.Cout + 31) / 32) * nz >= 120) CONV_CASE(32, 4, 4)
     else if (a.Cout >= 32) CONV_CASE(32, 4, 2)
     else CONV_CASE(16, 2, 4)
+#undef CONV_LAUNCH
 #undef CONV_CASE
     CLAUNCH_CHECK(c);
     return FSB_OK;

@@ -79,7 +79,9 @@ struct ConvArgs {
 
 constexpr int kConvCK = 16;  // input channels staged per step (fewer load-sync-compute rounds: the global loads of a round are exposed)
 
-template <int BM, int TM, int TN>
+// KT: taps as a compile-time constant (0 = run-time a.K): the tap loop is then fully unrolled, its address
+// arithmetic (k * BM, k * dil) disappears and the loads of consecutive taps overlap.
+template <int BM, int TM, int TN, int KT = 0>
 __global__ void __launch_bounds__(256) conv1d_kernel(ConvArgs a) {
     constexpr int NTX = 32, BN = NTX * TN;  // 32 lanes along t (stride-32 interleave -> conflict-free, coalesced)
     constexpr int NTY = BM / TM;               // 8 warps along co
@@ -140,7 +142,9 @@ __global__ void __launch_bounds__(256) conv1d_kernel(ConvArgs a) {
         for (int ci = 0; ci < nc; ++ci) {
             const float *wrow = ws + (size_t)ci * a.K * BM + ty * TM;
             const float *xrow = xs + (size_t)ci * span - off_lo - a.pad;  // xrow[t_local*stride + k*dil]
-            for (int k = 0; k < a.K; ++k) {
+            const int ntap = KT > 0 ? KT : a.K;
+#pragma unroll
+            for (int k = 0; k < ntap; ++k) {
                 float w[TM], xv[TN];
                 if (TM % 4 == 0) {  // the warp's TM output channels are contiguous and 16-byte aligned: broadcast LDS.128
 #pragma unroll
