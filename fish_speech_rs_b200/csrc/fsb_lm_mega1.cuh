@@ -97,6 +97,9 @@ struct M1Plan {
 
 template <typename WT, bool LL>
 struct Mega1 {
+    // shapes the kernel is specialised for (host-checked in mega1_eligible): compile-time constants keep divisions and
+    // index arithmetic out of the per-phase code
+    static constexpr int kD = kM1Slice, kHd = 64, kHhd = kM1Slice, kH = kHhd / kHd;
     static constexpr int NE = WTraits<WT>::NE;                 // elements per 16 bytes
     static constexpr int TB = kM1Slice * (int)sizeof(WT);      // task bytes
     static constexpr int U = TB / 512;                         // 16-byte units per lane per task
@@ -211,7 +214,7 @@ struct Mega1 {
         }
         csync();
     }
-    __device__ __forceinline__ unsigned long long *xt_rep(int par, int rep) const { return p.ll_xt + ((size_t)par * kM1Rep + rep) * p.D; }
+    __device__ __forceinline__ unsigned long long *xt_rep(int par, int rep) const { return p.ll_xt + ((size_t)par * kM1Rep + rep) * kD; }
     __device__ __forceinline__ unsigned long long *ht_rep(int rep) const { return p.ll_ht + (size_t)rep * p.I; }
 
     // ------------------------------------------------------------ schedule (shared by producer and consumers)
@@ -269,7 +272,7 @@ struct Mega1 {
         if (threadIdx.x < R_COUNT) {
             const int k = threadIdx.x;
             const int rows_total = k == R_QKV ? p.QKV : k == R_W13 ? p.I : k == R_HEAD_SLOW ? p.n_slow_logits
-                                 : k == R_HEAD_FAST ? p.CS : p.D;
+                                 : k == R_HEAD_FAST ? p.CS : kD;
             const int align = k == R_QKV ? 2 : 1;
             const unsigned groups = rows_total / align, nc = (unsigned)n_compute();
             const unsigned g0 = (blockIdx.x * groups) / nc, g1 = ((blockIdx.x + 1) * groups) / nc;
@@ -317,7 +320,7 @@ struct Mega1 {
 
     __device__ __forceinline__ M1Plan plan_of(const Step &s) const {
         const bool slow = s.pass == 0;
-        int rk = R_HEAD_FAST, K = p.D, row_a = 0, row_b = 1;
+        int rk = R_HEAD_FAST, K = kD, row_a = 0, row_b = 1;
         const void *W0 = p.fast_out, *W1 = nullptr;
         if (s.kind == K_HEAD) {
             if (slow) { rk = R_HEAD_SLOW; W0 = p.out_w; row_a = p.slow_row0; row_b = p.slow_rest_base; }
@@ -325,7 +328,7 @@ struct Mega1 {
             const MegaLayer &L = layer_of(s);
             switch (s.kind) {
                 case K_QKV: rk = R_QKV; W0 = L.wqkv; break;
-                case K_WO: rk = R_WO; W0 = L.wo; K = p.H * p.hd; break;
+                case K_WO: rk = R_WO; W0 = L.wo; K = kHhd; break;
                 case K_W13: rk = R_W13; W0 = L.w1; W1 = L.w3; break;
                 default: rk = R_W2; W0 = L.w2; K = p.I; break;
             }
@@ -492,7 +495,7 @@ struct Mega1 {
     // LL variants: the vector arrives as tagged words (replica my_rep()); same smem results as above
     __device__ __forceinline__ void stage_norm_ll(const unsigned long long *src, unsigned tag) {
         float ss = 0.f;
-        if (2 * tid < p.D) {
+        if (2 * tid < kD) {
             const unsigned long long a = ld_ll_raw(src + 2 * tid), b = ld_ll_raw(src + 2 * tid + 1);
             float2 v;
             v.x = ((unsigned)(a >> 32) == tag) ? __uint_as_float((unsigned)a) : ld_ll(src + 2 * tid, tag);
@@ -522,8 +525,8 @@ struct Mega1 {
     // ------------------------------------------------------------ split-KV GQA attention (slow blocks)
     // item = kvh * n_chunks_max + chunk; positions [chunk*64, min(len, chunk*64 + 64))
     __device__ __forceinline__ void att_stage(const float *kcache, const float *vcache, int kvh, int j0, int from, int to) {
-        const float *kb = kcache + ((size_t)kvh * p.max_len + j0) * p.hd;
-        const float *vb = vcache + ((size_t)kvh * p.max_len + j0) * p.hd;
+        const float *kb = kcache + ((size_t)kvh * p.max_len + j0) * kHd;
+        const float *vb = vcache + ((size_t)kvh * p.max_len + j0) * kHd;
         float *ks = kvs, *vs = kvs + kM1AttChunk * kM1KvStride;
         // hd == 64 (host-checked): 16 16-byte segments per row
         for (int i = tid; i < (to - from) * 16; i += kM1Threads) {
@@ -539,7 +542,7 @@ struct Mega1 {
         att_item = -1;
         const int len = pos_s[0] + 1, nch = att_chunks();
         const int nitems = p.KV * nch;
-        const size_t slow_kv = (size_t)p.max_batch * p.KV * p.max_len * p.hd;
+        const size_t slow_kv = (size_t)p.max_batch * p.KV * p.max_len * kHd;
         if ((int)blockIdx.x < nitems && !is_sampler()) {
             const int item = blockIdx.x, kvh = item / nch, chunk = item - kvh * nch;
             const int j0 = chunk * kM1AttChunk, j1 = min(len - 1, j0 + kM1AttChunk);  // exclude position len-1
@@ -551,12 +554,12 @@ struct Mega1 {
     }
 
     __device__ __forceinline__ void phase_attn_slow(int layer, int att_frame) {
-        const size_t slow_kv = (size_t)p.max_batch * p.KV * p.max_len * p.hd;
+        const size_t slow_kv = (size_t)p.max_batch * p.KV * p.max_len * kHd;
         const float *kcache = p.kc + layer * slow_kv, *vcache = p.vc + layer * slow_kv;
-        const int n_rep = p.H / p.KV;
+        const int n_rep = kH / p.KV;
         const int hq = warp & 7, hf = warp >> 3;
         const int g = lane >> 2, sub = lane & 3;
-        const float scale = 1.0f / sqrtf((float)p.hd);
+        const float scale = 1.0f / sqrtf((float)kHd);
         const int len = pos_s[0] + 1, nch = att_chunks();
         const int nitems = p.KV * nch;
         const float *ks = kvs, *vs = kvs + kM1AttChunk * kM1KvStride;
@@ -571,7 +574,7 @@ struct Mega1 {
                 // positions, fenced once per frame) through cp.async
                 const unsigned qtag = tag_of(att_frame, 0, layer, K_QKV);
                 if (hq < n_rep) {
-                    const unsigned long long *qp = p.ll_qt + (size_t)h * p.hd + sub * 4;
+                    const unsigned long long *qp = p.ll_qt + (size_t)h * kHd + sub * 4;
                     unsigned long long qw[16];
 #pragma unroll
                     for (int jj = 0; jj < 16; ++jj) qw[jj] = ld_ll_raw(qp + (jj >> 2) * 16 + (jj & 3));
@@ -585,16 +588,16 @@ struct Mega1 {
                 const int jold = min(j1, len - 1);  // rows below len - 1 are in the cache
                 if (j0 + have < jold) att_stage(kcache, vcache, kvh, j0, have, jold - j0);
                 cp_async_commit();
-                if (j1 == len && tid < 2 * p.hd) {  // this chunk holds the new position
-                    const int which = tid / p.hd, d = tid - which * p.hd;
-                    const float v = ld_ll(p.ll_nkv + (size_t)which * p.KV * p.hd + kvh * p.hd + d, qtag);
+                if (j1 == len && tid < 2 * kHd) {  // this chunk holds the new position
+                    const int which = tid / kHd, d = tid - which * kHd;
+                    const float v = ld_ll(p.ll_nkv + (size_t)which * p.KV * kHd + kvh * kHd + d, qtag);
                     kvs[which * kM1AttChunk * kM1KvStride + (len - 1 - j0) * kM1KvStride + d] = v;
                 }
                 cp_async_wait_all();
                 csync();
             } else {
                 if (hq < n_rep) {
-                    const float *qp = p.q + (size_t)h * p.hd + sub * 4;
+                    const float *qp = p.q + (size_t)h * kHd + sub * 4;
 #pragma unroll
                     for (int jj = 0; jj < 4; ++jj) qv[jj] = __ldcg(reinterpret_cast<const float4 *>(qp + jj * 16));
                 }
@@ -675,7 +678,7 @@ struct Mega1 {
                 const float M = fmaxf(m, mo);
                 const float wa = (m == -INFINITY) ? 0.f : expf(m - M), wb = (mo == -INFINITY) ? 0.f : expf(mo - M);
                 l = l * wa + lo * wb;
-                const size_t slot_off = ((size_t)h * (2 * p.n_chunks_max) + chunk) * (p.hd + 4);
+                const size_t slot_off = ((size_t)h * (2 * p.n_chunks_max) + chunk) * (kHd + 4);
                 float *out = p.partial + slot_off;
                 unsigned long long *outl = p.ll_pt + slot_off;
                 const unsigned ptag = tag_of(att_frame, 0, layer, K_ATT);
@@ -692,8 +695,8 @@ struct Mega1 {
                     }
                 }
                 if (sub == 0) {
-                    if (LL) { st_ll(outl + p.hd, M, ptag); st_ll(outl + p.hd + 1, l, ptag); }
-                    else { out[p.hd] = M; out[p.hd + 1] = l; }
+                    if (LL) { st_ll(outl + kHd, M, ptag); st_ll(outl + kHd + 1, l, ptag); }
+                    else { out[kHd] = M; out[kHd + 1] = l; }
                 }
             }
         }
@@ -706,10 +709,10 @@ struct Mega1 {
     __device__ __forceinline__ void combine_attn(unsigned ll_tag) {
         const int ns = att_chunks();
         const int h = tid >> 5, d2 = (tid & 31) * 2;  // H * hd == 2 * kM1Threads (host-checked: H = 16, hd = 64)
-        const float *pp = p.partial + (size_t)h * (2 * p.n_chunks_max) * (p.hd + 4);
+        const float *pp = p.partial + (size_t)h * (2 * p.n_chunks_max) * (kHd + 4);
         constexpr int BS = LL ? 4 : 8;  // slots per batch of loads (LL words take two registers each)
         float M = -INFINITY, Lsum = 0.f, o0 = 0.f, o1 = 0.f;
-        const unsigned long long *ppl = p.ll_pt + (size_t)h * (2 * p.n_chunks_max) * (p.hd + 4);
+        const unsigned long long *ppl = p.ll_pt + (size_t)h * (2 * p.n_chunks_max) * (kHd + 4);
 #pragma unroll 1
         for (int s0 = 0; s0 < ns; s0 += BS) {
             float2 ml[BS], ov[BS];
@@ -719,12 +722,12 @@ struct Mega1 {
                 const int sj = min(s0 + j, ns - 1);  // clamp: the duplicate gets weight 0 below
                 if (LL) {
                     // (raw words first: all 32 loads of the batch are in flight before the first tag check)
-                    const unsigned long long *sp = ppl + sj * (p.hd + 4);
-                    raw[j * 4 + 0] = ld_ll_raw(sp + p.hd); raw[j * 4 + 1] = ld_ll_raw(sp + p.hd + 1);
+                    const unsigned long long *sp = ppl + sj * (kHd + 4);
+                    raw[j * 4 + 0] = ld_ll_raw(sp + kHd); raw[j * 4 + 1] = ld_ll_raw(sp + kHd + 1);
                     raw[j * 4 + 2] = ld_ll_raw(sp + d2); raw[j * 4 + 3] = ld_ll_raw(sp + d2 + 1);
                 } else {
-                    const float *sp = pp + sj * (p.hd + 4);
-                    ml[j] = __ldcg(reinterpret_cast<const float2 *>(sp + p.hd));
+                    const float *sp = pp + sj * (kHd + 4);
+                    ml[j] = __ldcg(reinterpret_cast<const float2 *>(sp + kHd));
                     ov[j] = __ldcg(reinterpret_cast<const float2 *>(sp + d2));
                 }
                 if (!LL && s0 + j >= ns) ml[j].x = -INFINITY;
@@ -733,8 +736,8 @@ struct Mega1 {
 #pragma unroll
                 for (int j = 0; j < BS; ++j) {
                     const int sj = min(s0 + j, ns - 1);
-                    const unsigned long long *sp = ppl + sj * (p.hd + 4);
-                    ml[j].x = ll_take(raw[j * 4 + 0], sp + p.hd, ll_tag); ml[j].y = ll_take(raw[j * 4 + 1], sp + p.hd + 1, ll_tag);
+                    const unsigned long long *sp = ppl + sj * (kHd + 4);
+                    ml[j].x = ll_take(raw[j * 4 + 0], sp + kHd, ll_tag); ml[j].y = ll_take(raw[j * 4 + 1], sp + kHd + 1, ll_tag);
                     ov[j].x = ll_take(raw[j * 4 + 2], sp + d2, ll_tag); ov[j].y = ll_take(raw[j * 4 + 3], sp + d2 + 1, ll_tag);
                     if (s0 + j >= ns) ml[j].x = -INFINITY;
                 }
@@ -755,26 +758,26 @@ struct Mega1 {
             }
             M = Mn;
         }
-        *reinterpret_cast<float2 *>(xs + x_index(h * p.hd + d2)) = make_float2(o0 / Lsum, o1 / Lsum);
+        *reinterpret_cast<float2 *>(xs + x_index(h * kHd + d2)) = make_float2(o0 / Lsum, o1 / Lsum);
     }
 
     // prologue of wo (fast): the whole attention over <= C cached positions, recomputed by every CTA
     __device__ __forceinline__ void fast_attn(const float *kcache, const float *vcache, int cb, int ll_frame = 0, int ll_layer = 0) {
-        const int Hhd = p.H * p.hd, n_rep = p.H / p.KV;
-        const float scale = 1.0f / sqrtf((float)p.hd);
+        const int Hhd = kHhd, n_rep = kH / p.KV;
+        const float scale = 1.0f / sqrtf((float)kHd);
         const int npos = cb + 1;
         float *qs = xs + Hhd;                          // behind the output row (xs holds >= 2 * Hhd floats)
         float *kss = kvs;                              // KV * fast_len * hd
-        float *vss = kss + p.KV * p.fast_len * p.hd;   // same
+        float *vss = kss + p.KV * p.fast_len * kHd;   // same
         if (LL) {
             // q: this phase's QKV; K / V row j: the QKV phase of pass j + 1 of this frame (tagged fast cache)
             const unsigned qtag = tag_of(ll_frame, cb + 1, ll_layer, K_QKV);
             // all of a thread's words are requested before the first tag check (H * hd == 2 * kM1Threads,
             // KV * fast_len * hd <= 2 * kM1Threads: host-checked)
             const unsigned long long *ql = p.ll_qt;
-            const size_t lsz = (size_t)p.KV * p.fast_len * p.hd;
+            const size_t lsz = (size_t)p.KV * p.fast_len * kHd;
             const unsigned long long *kl = p.ll_fkv + (size_t)ll_layer * 2 * lsz, *vl = kl + lsz;
-            const int nkv = p.KV * npos * p.hd;
+            const int nkv = p.KV * npos * kHd;
             unsigned long long w[6];
             size_t off[2];
             unsigned rtag[2];
@@ -783,9 +786,9 @@ struct Mega1 {
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
                 const int i = tid + u * kM1Threads;
-                const int r = i / (npos * p.hd), rem = i - r * npos * p.hd;
-                off[u] = (size_t)r * p.fast_len * p.hd + rem;
-                rtag[u] = tag_of(ll_frame, rem / p.hd + 1, ll_layer, K_QKV);
+                const int r = i / (npos * kHd), rem = i - r * npos * kHd;
+                off[u] = (size_t)r * p.fast_len * kHd + rem;
+                rtag[u] = tag_of(ll_frame, rem / kHd + 1, ll_layer, K_QKV);
                 if (i < nkv) { w[2 + 2 * u] = ld_ll_raw(kl + off[u]); w[3 + 2 * u] = ld_ll_raw(vl + off[u]); }
             }
             qs[tid] = ll_take(w[0], ql + tid, qtag);
@@ -800,10 +803,10 @@ struct Mega1 {
         } else {
             for (int i = tid; i < Hhd / 4; i += kM1Threads)
                 reinterpret_cast<float4 *>(qs)[i] = __ldcg(reinterpret_cast<const float4 *>(p.q) + i);
-            const int seg = p.hd / 4;
+            const int seg = kHd / 4;
             for (int i = tid; i < p.KV * npos * seg; i += kM1Threads) {
                 const int r = i / (npos * seg), rem = i - r * npos * seg;
-                const size_t off = (size_t)r * p.fast_len * p.hd + rem * 4;
+                const size_t off = (size_t)r * p.fast_len * kHd + rem * 4;
                 *reinterpret_cast<float4 *>(kss + off) = __ldcg(reinterpret_cast<const float4 *>(kcache + off));
                 *reinterpret_cast<float4 *>(vss + off) = __ldcg(reinterpret_cast<const float4 *>(vcache + off));
             }
@@ -813,10 +816,10 @@ struct Mega1 {
         // lane owns two output dims for P.V (the probabilities are broadcast by shuffles)
         const int j = lane >> 2, sub = lane & 3;
         const bool valid = j < npos;
-        for (int h = warp; h < p.H; h += kM1Warps) {
+        for (int h = warp; h < kH; h += kM1Warps) {
             const int kvh = h / n_rep;
-            const float *qp = qs + h * p.hd + sub * 4;
-            const float *kr = kss + ((size_t)kvh * p.fast_len + (valid ? j : 0)) * p.hd + sub * 4;
+            const float *qp = qs + h * kHd + sub * 4;
+            const float *kr = kss + ((size_t)kvh * p.fast_len + (valid ? j : 0)) * kHd + sub * 4;
             float dot = 0.f;
 #pragma unroll
             for (int jj = 0; jj < 4; ++jj) {
@@ -837,18 +840,18 @@ struct Mega1 {
             float l = pj;
 #pragma unroll
             for (int off = 4; off < 32; off <<= 1) l += __shfl_xor_sync(0xffffffffu, l, off);
-            const float *vbase = vss + (size_t)kvh * p.fast_len * p.hd + lane * 2;
+            const float *vbase = vss + (size_t)kvh * p.fast_len * kHd + lane * 2;
             float o0 = 0.f, o1 = 0.f;
 #pragma unroll
             for (int jj = 0; jj < 8; ++jj) {
                 const float pw = __shfl_sync(0xffffffffu, pj, jj * 4);
                 if (jj < npos) {
-                    const float2 vv = *reinterpret_cast<const float2 *>(vbase + jj * p.hd);
+                    const float2 vv = *reinterpret_cast<const float2 *>(vbase + jj * kHd);
                     o0 = fmaf(pw, vv.x, o0);
                     o1 = fmaf(pw, vv.y, o1);
                 }
             }
-            *reinterpret_cast<float2 *>(xs + x_index(h * p.hd + lane * 2)) = make_float2(o0 / l, o1 / l);
+            *reinterpret_cast<float2 *>(xs + x_index(h * kHd + lane * 2)) = make_float2(o0 / l, o1 / l);
         }
     }
 
@@ -860,10 +863,10 @@ struct Mega1 {
     // for the extra stores of the few CTAs that produce them.)
     __device__ __forceinline__ float *stream_rep(bool slow, int rep) const {
         if (rep == 0) return slow ? p.x : p.fx;
-        return p.rep + (slow ? 0 : (kM1Rep - 1) * p.D) + (rep - 1) * p.D;
+        return p.rep + (slow ? 0 : (kM1Rep - 1) * kD) + (rep - 1) * kD;
     }
     __device__ __forceinline__ float *h_rep(int rep) const {
-        return rep == 0 ? p.h : p.rep + 2 * (kM1Rep - 1) * p.D + (rep - 1) * p.I;
+        return rep == 0 ? p.h : p.rep + 2 * (kM1Rep - 1) * kD + (rep - 1) * p.I;
     }
     __device__ __forceinline__ int my_rep() const { return (int)(blockIdx.x % kM1Rep); }
 
@@ -889,7 +892,7 @@ struct Mega1 {
             plan.ntasks = plan.nrows * plan.ksplit * (s.kind == K_W13 ? 2 : 1);
         }
         const float *g = norm_of(s);
-        if (g && 2 * tid < p.D) gpre = __ldg(reinterpret_cast<const float2 *>(g) + tid);
+        if (g && 2 * tid < kD) gpre = __ldg(reinterpret_cast<const float2 *>(g) + tid);
     }
 
     __device__ __forceinline__ void gemv_phase(const Step &s) {
@@ -899,10 +902,10 @@ struct Mega1 {
         // the slow stream of frame 0 comes from the prefill (canonical copy only) when the launch starts at the tail
         const bool prefilled = s.frame == 0 && p.first_is_tail != 0;
         const float *xg = stream_rep(slow, (slow && prefilled) ? 0 : my_rep());
-        const size_t kv_stride = (size_t)p.max_batch * p.KV * (slow ? p.max_len : p.fast_len) * p.hd;
+        const size_t kv_stride = (size_t)p.max_batch * p.KV * (slow ? p.max_len : p.fast_len) * kHd;
         float *kcl = (slow ? p.kc : p.fkc) + s.l * kv_stride, *vcl = (slow ? p.vc : p.fvc) + s.l * kv_stride;
         const int cache_len = slow ? p.max_len : p.fast_len;
-        const int D = p.D;
+        const int D = kD;
         bool with_norm = false;
         int K = D;
         // ---- prologue: the activation vector -> xs (scaled by the norm weights where a norm applies)
@@ -917,8 +920,8 @@ struct Mega1 {
                     if (tid <= p.C) codes_s[tid] = (int)__float_as_uint(ld_ll(p.ll_ct + tid, tag_of(s.frame - 1, tid, 31, K_SAMPLE)));
                     csync();
                 }
-                if (tid < p.hd) {
-                    const int half = p.hd / 2;
+                if (tid < kHd) {
+                    const int half = kHd / 2;
                     const int pos = LL ? pos0 + s.frame - 1 : __ldcg(p.st.pos);
                     cs_s[tid] = tid < half ? p.cosT[(size_t)pos * half + tid] : p.sinT[(size_t)pos * half + tid - half];
                     if (tid == 0) pos_s[0] = pos;
@@ -992,7 +995,7 @@ struct Mega1 {
                 if (2 * tid < D) reinterpret_cast<float2 *>(kvs + 6144)[tid] = reinterpret_cast<const float2 *>(xres)[tid];
             }
         } else if (kind == K_WO) {
-            K = p.H * p.hd;
+            K = kHhd;
             if (slow) {
                 const unsigned tg = tag_of(s.frame, 0, s.l, K_ATT);
                 if (LL) ll_wait(tg, min(p.KV * att_chunks(), (int)gridDim.x));
@@ -1020,14 +1023,14 @@ struct Mega1 {
         const unsigned mytag = tag_of(s.frame, s.pass, kind == K_HEAD ? 31 : s.l, kind);
         if (kind == K_QKV) {
             // pairs of rows -> rope_i (dual_ar.rs:246-247) -> q buffer / K cache; V rows -> V cache (Tensor::cat, :316-324)
-            const int half = p.hd / 2, Hhd = p.H * p.hd, KVhd = p.KV * p.hd;
+            const int half = kHd / 2, Hhd = kHhd, KVhd = p.KV * kHd;
             for (int pr = tid; pr < plan.nrows / 2; pr += kM1Threads) {
                 const int r = plan.r0 + 2 * pr;
                 const float v0 = row_val(0, 2 * pr), v1 = row_val(0, 2 * pr + 1);
                 const int pos = slow ? pos_s[0] : cb;
                 if (r < Hhd + KVhd) {
-                    const int pi = (r % p.hd) / 2;
-                    const float *cs = slow ? cs_s : csf_s + cb * p.hd;
+                    const int pi = (r % kHd) / 2;
+                    const float *cs = slow ? cs_s : csf_s + cb * kHd;
                     const float c = cs[pi], sn = cs[half + pi];
                     const float o0 = __fsub_rn(__fmul_rn(v0, c), __fmul_rn(v1, sn));
                     const float o1 = __fadd_rn(__fmul_rn(v0, sn), __fmul_rn(v1, c));
@@ -1035,29 +1038,29 @@ struct Mega1 {
                         if (LL) { st_ll(p.ll_qt + r, o0, mytag); st_ll(p.ll_qt + r + 1, o1, mytag); }
                         else { p.q[r] = o0; p.q[r + 1] = o1; }
                     } else {
-                        const int rk = r - Hhd, kvh = rk / p.hd, d = rk % p.hd;
+                        const int rk = r - Hhd, kvh = rk / kHd, d = rk % kHd;
                         if (!LL || slow) {
-                            float *dst = kcl + ((size_t)kvh * cache_len + pos) * p.hd + d;
+                            float *dst = kcl + ((size_t)kvh * cache_len + pos) * kHd + d;
                             dst[0] = o0;
                             dst[1] = o1;
                         }
                         if (LL) {
                             unsigned long long *dl = slow ? p.ll_nkv + rk
-                                : p.ll_fkv + (size_t)s.l * 2 * KVhd * p.fast_len + ((size_t)kvh * p.fast_len + pos) * p.hd + d;
+                                : p.ll_fkv + (size_t)s.l * 2 * KVhd * p.fast_len + ((size_t)kvh * p.fast_len + pos) * kHd + d;
                             st_ll(dl, o0, mytag);
                             st_ll(dl + 1, o1, mytag);
                         }
                     }
                 } else {
-                    const int rv = r - Hhd - KVhd, kvh = rv / p.hd, d = rv % p.hd;
+                    const int rv = r - Hhd - KVhd, kvh = rv / kHd, d = rv % kHd;
                     if (!LL || slow) {
-                        float *dst = vcl + ((size_t)kvh * cache_len + pos) * p.hd + d;
+                        float *dst = vcl + ((size_t)kvh * cache_len + pos) * kHd + d;
                         dst[0] = v0;
                         dst[1] = v1;
                     }
                     if (LL) {
                         unsigned long long *dl = slow ? p.ll_nkv + KVhd + rv
-                            : p.ll_fkv + ((size_t)s.l * 2 + 1) * KVhd * p.fast_len + ((size_t)kvh * p.fast_len + pos) * p.hd + d;
+                            : p.ll_fkv + ((size_t)s.l * 2 + 1) * KVhd * p.fast_len + ((size_t)kvh * p.fast_len + pos) * kHd + d;
                         st_ll(dl, v0, mytag);
                         st_ll(dl + 1, v1, mytag);
                     }
@@ -1239,8 +1242,8 @@ struct Mega1 {
     // ------------------------------------------------------------ frame loop (compute warps)
     __device__ __forceinline__ void run() {
         Step cur = first_step();
-        for (int i = tid; i < p.C * p.hd; i += kM1Threads) {
-            const int row = i / p.hd, d = i - row * p.hd, half = p.hd / 2;
+        for (int i = tid; i < p.C * kHd; i += kM1Threads) {
+            const int row = i / kHd, d = i - row * kHd, half = kHd / 2;
             csf_s[i] = d < half ? p.cosT[(size_t)row * half + d] : p.sinT[(size_t)row * half + d - half];
         }
         if (tid == 0) pos_s[0] = p.st.pos[0];
