@@ -496,8 +496,7 @@ static bool mega1_eligible(const fsb_lm *lm) {
     const int Hhd = lm->H * lm->hd;
     const SampleParams &sp = lm->h_st.sp;  // the single-row kernel carries the selection sampler only
     if (!sp.greedy && (sp.top_k > (uint32_t)kSelMaxK || std::max(lm->n_slow_logits, lm->CS) > (1 << kSelIdxBits))) return false;
-    return lm->mega_ok && lm->D == kM1Slice && lm->I % kM1Slice == 0 && Hhd == kM1Slice && lm->I / kM1Slice <= 8 &&
-           8 % (lm->I / kM1Slice) == 0 && lm->hd == 64 && lm->QKV % 2 == 0;
+    return lm->mega_ok && lm->D == kM1Slice && lm->I == 4 * kM1Slice && Hhd == kM1Slice && lm->hd == 64 && lm->KV == 2 && lm->QKV % 2 == 0;
 }
 static size_t mega1_smem_bytes(const fsb_lm *lm, int depth, int *xs_floats, int *kvs_floats) {
     const int n_max = std::max(lm->n_slow_logits, lm->CS);
@@ -629,6 +628,8 @@ static int mega_setup(fsb_lm *lm) {
     m.logits = lm->mega_logits; m.ldl = ldl;
     m.n_chunks_max = n_chunks_max;
     m.bar = lm->mega_bar; m.dbg = lm->mega_dbg; m.rep = lm->mega_rep;
+    m.slow_kv_stride = (size_t)lm->max_batch * lm->KV * lm->max_len * lm->hd;
+    m.fast_kv_stride = (size_t)lm->max_batch * lm->KV * lm->fast_len * lm->hd;
     m.sem_start = lm->tok.semantic_start_id; m.sem_end = lm->tok.semantic_end_id; m.has_end = lm->tok.has_semantic_end;
     FSB_CUDA_OK(cudaEventCreate(&lm->prof_m0));
     FSB_CUDA_OK(cudaEventCreate(&lm->prof_m1));

@@ -99,7 +99,7 @@ template <typename WT, bool LL>
 struct Mega1 {
     // shapes the kernel is specialised for (host-checked in mega1_eligible): compile-time constants keep divisions and
     // index arithmetic out of the per-phase code
-    static constexpr int kD = kM1Slice, kHd = 64, kHhd = kM1Slice, kH = kHhd / kHd;
+    static constexpr int kD = kM1Slice, kHd = 64, kHhd = kM1Slice, kH = kHhd / kHd, kKV = 2, kI = 4 * kM1Slice;
     static constexpr int NE = WTraits<WT>::NE;                 // elements per 16 bytes
     static constexpr int TB = kM1Slice * (int)sizeof(WT);      // task bytes
     static constexpr int U = TB / 512;                         // 16-byte units per lane per task
@@ -215,7 +215,7 @@ struct Mega1 {
         csync();
     }
     __device__ __forceinline__ unsigned long long *xt_rep(int par, int rep) const { return p.ll_xt + ((size_t)par * kM1Rep + rep) * kD; }
-    __device__ __forceinline__ unsigned long long *ht_rep(int rep) const { return p.ll_ht + (size_t)rep * p.I; }
+    __device__ __forceinline__ unsigned long long *ht_rep(int rep) const { return p.ll_ht + (size_t)rep * kI; }
 
     // ------------------------------------------------------------ schedule (shared by producer and consumers)
     enum { K_QKV = 0, K_ATT = 1, K_WO = 2, K_W13 = 3, K_W2 = 4, K_HEAD = 5, K_SAMPLE = 6, K_END = 7 };
@@ -271,7 +271,7 @@ struct Mega1 {
     __device__ __forceinline__ void init_row_ranges() {
         if (threadIdx.x < R_COUNT) {
             const int k = threadIdx.x;
-            const int rows_total = k == R_QKV ? p.QKV : k == R_W13 ? p.I : k == R_HEAD_SLOW ? p.n_slow_logits
+            const int rows_total = k == R_QKV ? p.QKV : k == R_W13 ? kI : k == R_HEAD_SLOW ? p.n_slow_logits
                                  : k == R_HEAD_FAST ? p.CS : kD;
             const int align = k == R_QKV ? 2 : 1;
             const unsigned groups = rows_total / align, nc = (unsigned)n_compute();
@@ -330,7 +330,7 @@ struct Mega1 {
                 case K_QKV: rk = R_QKV; W0 = L.wqkv; break;
                 case K_WO: rk = R_WO; W0 = L.wo; K = kHhd; break;
                 case K_W13: rk = R_W13; W0 = L.w1; W1 = L.w3; break;
-                default: rk = R_W2; W0 = L.w2; K = p.I; break;
+                default: rk = R_W2; W0 = L.w2; K = kI; break;
             }
         }
         return make_plan(rk, W0, W1, K, row_a, row_b);  // one body: the plan code stays warm in the I-cache
@@ -541,8 +541,8 @@ struct Mega1 {
     __device__ __forceinline__ void att_prefetch(int layer) {
         att_item = -1;
         const int len = pos_s[0] + 1, nch = att_chunks();
-        const int nitems = p.KV * nch;
-        const size_t slow_kv = (size_t)p.max_batch * p.KV * p.max_len * kHd;
+        const int nitems = kKV * nch;
+        const size_t slow_kv = p.slow_kv_stride;
         if ((int)blockIdx.x < nitems && !is_sampler()) {
             const int item = blockIdx.x, kvh = item / nch, chunk = item - kvh * nch;
             const int j0 = chunk * kM1AttChunk, j1 = min(len - 1, j0 + kM1AttChunk);  // exclude position len-1
@@ -554,14 +554,14 @@ struct Mega1 {
     }
 
     __device__ __forceinline__ void phase_attn_slow(int layer, int att_frame) {
-        const size_t slow_kv = (size_t)p.max_batch * p.KV * p.max_len * kHd;
+        const size_t slow_kv = p.slow_kv_stride;
         const float *kcache = p.kc + layer * slow_kv, *vcache = p.vc + layer * slow_kv;
-        const int n_rep = kH / p.KV;
+        const int n_rep = kH / kKV;
         const int hq = warp & 7, hf = warp >> 3;
         const int g = lane >> 2, sub = lane & 3;
         const float scale = 1.0f / sqrtf((float)kHd);
         const int len = pos_s[0] + 1, nch = att_chunks();
-        const int nitems = p.KV * nch;
+        const int nitems = kKV * nch;
         const float *ks = kvs, *vs = kvs + kM1AttChunk * kM1KvStride;
         for (int item = is_sampler() ? nitems : (int)blockIdx.x; item < nitems; item += n_compute()) {
             const int kvh = item / nch, chunk = item - kvh * nch;
@@ -590,7 +590,7 @@ struct Mega1 {
                 cp_async_commit();
                 if (j1 == len && tid < 2 * kHd) {  // this chunk holds the new position
                     const int which = tid / kHd, d = tid - which * kHd;
-                    const float v = ld_ll(p.ll_nkv + (size_t)which * p.KV * kHd + kvh * kHd + d, qtag);
+                    const float v = ld_ll(p.ll_nkv + (size_t)which * kKV * kHd + kvh * kHd + d, qtag);
                     kvs[which * kM1AttChunk * kM1KvStride + (len - 1 - j0) * kM1KvStride + d] = v;
                 }
                 cp_async_wait_all();
@@ -763,21 +763,21 @@ struct Mega1 {
 
     // prologue of wo (fast): the whole attention over <= C cached positions, recomputed by every CTA
     __device__ __forceinline__ void fast_attn(const float *kcache, const float *vcache, int cb, int ll_frame = 0, int ll_layer = 0) {
-        const int Hhd = kHhd, n_rep = kH / p.KV;
+        const int Hhd = kHhd, n_rep = kH / kKV;
         const float scale = 1.0f / sqrtf((float)kHd);
         const int npos = cb + 1;
         float *qs = xs + Hhd;                          // behind the output row (xs holds >= 2 * Hhd floats)
         float *kss = kvs;                              // KV * fast_len * hd
-        float *vss = kss + p.KV * p.fast_len * kHd;   // same
+        float *vss = kss + kKV * p.fast_len * kHd;   // same
         if (LL) {
             // q: this phase's QKV; K / V row j: the QKV phase of pass j + 1 of this frame (tagged fast cache)
             const unsigned qtag = tag_of(ll_frame, cb + 1, ll_layer, K_QKV);
             // all of a thread's words are requested before the first tag check (H * hd == 2 * kM1Threads,
             // KV * fast_len * hd <= 2 * kM1Threads: host-checked)
             const unsigned long long *ql = p.ll_qt;
-            const size_t lsz = (size_t)p.KV * p.fast_len * kHd;
+            const size_t lsz = (size_t)kKV * p.fast_len * kHd;
             const unsigned long long *kl = p.ll_fkv + (size_t)ll_layer * 2 * lsz, *vl = kl + lsz;
-            const int nkv = p.KV * npos * kHd;
+            const int nkv = kKV * npos * kHd;
             unsigned long long w[6];
             size_t off[2];
             unsigned rtag[2];
@@ -804,7 +804,7 @@ struct Mega1 {
             for (int i = tid; i < Hhd / 4; i += kM1Threads)
                 reinterpret_cast<float4 *>(qs)[i] = __ldcg(reinterpret_cast<const float4 *>(p.q) + i);
             const int seg = kHd / 4;
-            for (int i = tid; i < p.KV * npos * seg; i += kM1Threads) {
+            for (int i = tid; i < kKV * npos * seg; i += kM1Threads) {
                 const int r = i / (npos * seg), rem = i - r * npos * seg;
                 const size_t off = (size_t)r * p.fast_len * kHd + rem * 4;
                 *reinterpret_cast<float4 *>(kss + off) = __ldcg(reinterpret_cast<const float4 *>(kcache + off));
@@ -866,7 +866,7 @@ struct Mega1 {
         return p.rep + (slow ? 0 : (kM1Rep - 1) * kD) + (rep - 1) * kD;
     }
     __device__ __forceinline__ float *h_rep(int rep) const {
-        return rep == 0 ? p.h : p.rep + 2 * (kM1Rep - 1) * kD + (rep - 1) * p.I;
+        return rep == 0 ? p.h : p.rep + 2 * (kM1Rep - 1) * kD + (rep - 1) * kI;
     }
     __device__ __forceinline__ int my_rep() const { return (int)(blockIdx.x % kM1Rep); }
 
@@ -888,7 +888,7 @@ struct Mega1 {
                          : s.kind == K_QKV ? R_QKV : s.kind == K_WO ? R_WO : s.kind == K_W13 ? R_W13 : R_W2;
             plan.r0 = rtab[2 * rk];
             plan.nrows = rtab[2 * rk + 1];
-            plan.ksplit = s.kind == K_W2 ? p.I / kM1Slice : 1;
+            plan.ksplit = s.kind == K_W2 ? kI / kM1Slice : 1;
             plan.ntasks = plan.nrows * plan.ksplit * (s.kind == K_W13 ? 2 : 1);
         }
         const float *g = norm_of(s);
@@ -902,7 +902,7 @@ struct Mega1 {
         // the slow stream of frame 0 comes from the prefill (canonical copy only) when the launch starts at the tail
         const bool prefilled = s.frame == 0 && p.first_is_tail != 0;
         const float *xg = stream_rep(slow, (slow && prefilled) ? 0 : my_rep());
-        const size_t kv_stride = (size_t)p.max_batch * p.KV * (slow ? p.max_len : p.fast_len) * kHd;
+        const size_t kv_stride = slow ? p.slow_kv_stride : p.fast_kv_stride;
         float *kcl = (slow ? p.kc : p.fkc) + s.l * kv_stride, *vcl = (slow ? p.vc : p.fvc) + s.l * kv_stride;
         const int cache_len = slow ? p.max_len : p.fast_len;
         const int D = kD;
@@ -998,20 +998,20 @@ struct Mega1 {
             K = kHhd;
             if (slow) {
                 const unsigned tg = tag_of(s.frame, 0, s.l, K_ATT);
-                if (LL) ll_wait(tg, min(p.KV * att_chunks(), (int)gridDim.x));
+                if (LL) ll_wait(tg, min(kKV * att_chunks(), (int)gridDim.x));
                 combine_attn(tg);
             } else {
                 if (LL) ll_wait(tag_of(s.frame, s.pass, s.l, K_QKV), (int)gridDim.x);
                 fast_attn(kcl, vcl, cb, s.frame, s.l);
             }
         } else {  // K_W2
-            K = p.I;
+            K = kI;
             if (LL) {
                 const unsigned tg = tag_of(s.frame, s.pass, s.l, K_W13);
                 ll_wait(tg, (int)gridDim.x);
-                stage_plain_ll(ht_rep(my_rep()), p.I, tg);
+                stage_plain_ll(ht_rep(my_rep()), kI, tg);
             } else {
-                stage_plain(h_rep(my_rep()), p.I);
+                stage_plain(h_rep(my_rep()), kI);
             }
         }
         csync();
@@ -1023,7 +1023,7 @@ struct Mega1 {
         const unsigned mytag = tag_of(s.frame, s.pass, kind == K_HEAD ? 31 : s.l, kind);
         if (kind == K_QKV) {
             // pairs of rows -> rope_i (dual_ar.rs:246-247) -> q buffer / K cache; V rows -> V cache (Tensor::cat, :316-324)
-            const int half = kHd / 2, Hhd = kHhd, KVhd = p.KV * kHd;
+            const int half = kHd / 2, Hhd = kHhd, KVhd = kKV * kHd;
             for (int pr = tid; pr < plan.nrows / 2; pr += kM1Threads) {
                 const int r = plan.r0 + 2 * pr;
                 const float v0 = row_val(0, 2 * pr), v1 = row_val(0, 2 * pr + 1);

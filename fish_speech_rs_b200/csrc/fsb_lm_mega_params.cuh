@@ -78,6 +78,7 @@ struct MegaParams {
     float *rep;      // single-row kernel: replicas 1..kM1Rep-1 of x | fx | h  ((kM1Rep-1) * (2 D + I) floats)
     unsigned long long *ll;  // single-row kernel: arena of tagged words (flag-in-data synchronisation), null = grid barriers
     unsigned long long *ll_xt, *ll_ht, *ll_qt, *ll_nkv, *ll_fkv, *ll_pt, *ll_lt, *ll_ct, *ll_fl;  // its regions (LLLayout)
+    size_t slow_kv_stride, fast_kv_stride;  // floats per layer of the slow / fast K (or V) cache
     int sampler_cta; // single-row kernel: CTA that only samples (-1: CTA 0 samples and streams)
     unsigned long long *dbg;  // optional (FSB_MEGA_TIMERS=1): per phase kind {work ns, barrier ns, count} of CTA 0 and the last CTA
 };
