@@ -496,7 +496,8 @@ static bool mega1_eligible(const fsb_lm *lm) {
     const int Hhd = lm->H * lm->hd;
     const SampleParams &sp = lm->h_st.sp;  // the single-row kernel carries the selection sampler only
     if (!sp.greedy && (sp.top_k > (uint32_t)kSelMaxK || std::max(lm->n_slow_logits, lm->CS) > (1 << kSelIdxBits))) return false;
-    return lm->mega_ok && lm->D == kM1Slice && lm->I == 4 * kM1Slice && Hhd == kM1Slice && lm->hd == 64 && lm->KV == 2 && lm->QKV % 2 == 0;
+    return lm->mega_ok && lm->D == kM1Slice && lm->I == 4 * kM1Slice && Hhd == kM1Slice && lm->hd == 64 && lm->KV == 2 && lm->QKV % 2 == 0 &&
+           lm->C == 8 && lm->fast_len == 8 && lm->CS == 1024;
 }
 static size_t mega1_smem_bytes(const fsb_lm *lm, int depth, int *xs_floats, int *kvs_floats) {
     const int n_max = std::max(lm->n_slow_logits, lm->CS);

@@ -99,7 +99,7 @@ template <typename WT, bool LL>
 struct Mega1 {
     // shapes the kernel is specialised for (host-checked in mega1_eligible): compile-time constants keep divisions and
     // index arithmetic out of the per-phase code
-    static constexpr int kD = kM1Slice, kHd = 64, kHhd = kM1Slice, kH = kHhd / kHd, kKV = 2, kI = 4 * kM1Slice;
+    static constexpr int kD = kM1Slice, kHd = 64, kHhd = kM1Slice, kH = kHhd / kHd, kKV = 2, kI = 4 * kM1Slice, kC = 8, kCS = 1024;
     static constexpr int NE = WTraits<WT>::NE;                 // elements per 16 bytes
     static constexpr int TB = kM1Slice * (int)sizeof(WT);      // task bytes
     static constexpr int U = TB / 512;                         // 16-byte units per lane per task
@@ -245,7 +245,7 @@ struct Mega1 {
             case K_HEAD: n.kind = K_SAMPLE; break;
             default:  // K_SAMPLE
                 n.l = 0;
-                if (s.pass < p.C) { n.pass = s.pass + 1; n.kind = p.NFL > 0 ? K_QKV : K_HEAD; }
+                if (s.pass < kC) { n.pass = s.pass + 1; n.kind = p.NFL > 0 ? K_QKV : K_HEAD; }
                 else {
                     n.pass = 0;
                     n.frame = s.frame + 1;
@@ -272,7 +272,7 @@ struct Mega1 {
         if (threadIdx.x < R_COUNT) {
             const int k = threadIdx.x;
             const int rows_total = k == R_QKV ? p.QKV : k == R_W13 ? kI : k == R_HEAD_SLOW ? p.n_slow_logits
-                                 : k == R_HEAD_FAST ? p.CS : kD;
+                                 : k == R_HEAD_FAST ? kCS : kD;
             const int align = k == R_QKV ? 2 : 1;
             const unsigned groups = rows_total / align, nc = (unsigned)n_compute();
             const unsigned g0 = (blockIdx.x * groups) / nc, g1 = ((blockIdx.x + 1) * groups) / nc;
@@ -768,14 +768,14 @@ struct Mega1 {
         const int npos = cb + 1;
         float *qs = xs + Hhd;                          // behind the output row (xs holds >= 2 * Hhd floats)
         float *kss = kvs;                              // KV * fast_len * hd
-        float *vss = kss + kKV * p.fast_len * kHd;   // same
+        float *vss = kss + kKV * kC * kHd;   // same
         if (LL) {
             // q: this phase's QKV; K / V row j: the QKV phase of pass j + 1 of this frame (tagged fast cache)
             const unsigned qtag = tag_of(ll_frame, cb + 1, ll_layer, K_QKV);
             // all of a thread's words are requested before the first tag check (H * hd == 2 * kM1Threads,
             // KV * fast_len * hd <= 2 * kM1Threads: host-checked)
             const unsigned long long *ql = p.ll_qt;
-            const size_t lsz = (size_t)kKV * p.fast_len * kHd;
+            const size_t lsz = (size_t)kKV * kC * kHd;
             const unsigned long long *kl = p.ll_fkv + (size_t)ll_layer * 2 * lsz, *vl = kl + lsz;
             const int nkv = kKV * npos * kHd;
             unsigned long long w[6];
@@ -787,7 +787,7 @@ struct Mega1 {
             for (int u = 0; u < 2; ++u) {
                 const int i = tid + u * kM1Threads;
                 const int r = i / (npos * kHd), rem = i - r * npos * kHd;
-                off[u] = (size_t)r * p.fast_len * kHd + rem;
+                off[u] = (size_t)r * kC * kHd + rem;
                 rtag[u] = tag_of(ll_frame, rem / kHd + 1, ll_layer, K_QKV);
                 if (i < nkv) { w[2 + 2 * u] = ld_ll_raw(kl + off[u]); w[3 + 2 * u] = ld_ll_raw(vl + off[u]); }
             }
@@ -806,7 +806,7 @@ struct Mega1 {
             const int seg = kHd / 4;
             for (int i = tid; i < kKV * npos * seg; i += kM1Threads) {
                 const int r = i / (npos * seg), rem = i - r * npos * seg;
-                const size_t off = (size_t)r * p.fast_len * kHd + rem * 4;
+                const size_t off = (size_t)r * kC * kHd + rem * 4;
                 *reinterpret_cast<float4 *>(kss + off) = __ldcg(reinterpret_cast<const float4 *>(kcache + off));
                 *reinterpret_cast<float4 *>(vss + off) = __ldcg(reinterpret_cast<const float4 *>(vcache + off));
             }
@@ -819,7 +819,7 @@ struct Mega1 {
         for (int h = warp; h < kH; h += kM1Warps) {
             const int kvh = h / n_rep;
             const float *qp = qs + h * kHd + sub * 4;
-            const float *kr = kss + ((size_t)kvh * p.fast_len + (valid ? j : 0)) * kHd + sub * 4;
+            const float *kr = kss + ((size_t)kvh * kC + (valid ? j : 0)) * kHd + sub * 4;
             float dot = 0.f;
 #pragma unroll
             for (int jj = 0; jj < 4; ++jj) {
@@ -840,7 +840,7 @@ struct Mega1 {
             float l = pj;
 #pragma unroll
             for (int off = 4; off < 32; off <<= 1) l += __shfl_xor_sync(0xffffffffu, l, off);
-            const float *vbase = vss + (size_t)kvh * p.fast_len * kHd + lane * 2;
+            const float *vbase = vss + (size_t)kvh * kC * kHd + lane * 2;
             float o0 = 0.f, o1 = 0.f;
 #pragma unroll
             for (int jj = 0; jj < 8; ++jj) {
@@ -904,7 +904,7 @@ struct Mega1 {
         const float *xg = stream_rep(slow, (slow && prefilled) ? 0 : my_rep());
         const size_t kv_stride = slow ? p.slow_kv_stride : p.fast_kv_stride;
         float *kcl = (slow ? p.kc : p.fkc) + s.l * kv_stride, *vcl = (slow ? p.vc : p.fvc) + s.l * kv_stride;
-        const int cache_len = slow ? p.max_len : p.fast_len;
+        const int cache_len = slow ? p.max_len : kC;
         const int D = kD;
         bool with_norm = false;
         int K = D;
@@ -917,7 +917,7 @@ struct Mega1 {
                 if (LL) {
                     // previous frame's codes: tagged words from the sampler (the launch starts at the tail, so
                     // frame >= 1 here); the position advances by one per slow step
-                    if (tid <= p.C) codes_s[tid] = (int)__float_as_uint(ld_ll(p.ll_ct + tid, tag_of(s.frame - 1, tid, 31, K_SAMPLE)));
+                    if (tid <= kC) codes_s[tid] = (int)__float_as_uint(ld_ll(p.ll_ct + tid, tag_of(s.frame - 1, tid, 31, K_SAMPLE)));
                     csync();
                 }
                 if (tid < kHd) {
@@ -935,9 +935,9 @@ struct Mega1 {
                 float ss = 0.f;
                 for (int d = tid; d < D; d += kM1Threads) {
                     float acc = to_f32(emb[(size_t)tok0 * D + d]);
-                    for (int c = 0; c < p.C; ++c) {
+                    for (int c = 0; c < kC; ++c) {
                         const uint32_t code = LL ? (uint32_t)codes_s[1 + c] : __ldcg(t + 1 + c);
-                        acc = __fadd_rn(acc, __fmul_rn(to_f32(cbe[((size_t)c * p.CS + code) * D + d]), mf));
+                        acc = __fadd_rn(acc, __fmul_rn(to_f32(cbe[((size_t)c * kCS + code) * D + d]), mf));
                     }
                     xres[d] = acc;  // scaled into xs below (gpre is laid out for elements 2 * tid, 2 * tid + 1)
                     ss = fmaf(acc, acc, ss);
@@ -953,7 +953,7 @@ struct Mega1 {
                     int *codes_s = reinterpret_cast<int *>(red + 32);
                     if (tid == 0) {
                         if (cb > 0) codes_s[0] = (int)__float_as_uint(ld_ll(p.ll_ct + cb, tag_of(s.frame, cb, 31, K_SAMPLE)));
-                        else *go_frames = (int)__float_as_uint(ld_ll(p.ll_ct + p.C + 1, tag_of(s.frame, 0, 31, K_SAMPLE)));
+                        else *go_frames = (int)__float_as_uint(ld_ll(p.ll_ct + kC + 1, tag_of(s.frame, 0, 31, K_SAMPLE)));
                     }
                     csync();
                     code = (uint32_t)codes_s[0];
@@ -1046,7 +1046,7 @@ struct Mega1 {
                         }
                         if (LL) {
                             unsigned long long *dl = slow ? p.ll_nkv + rk
-                                : p.ll_fkv + (size_t)s.l * 2 * KVhd * p.fast_len + ((size_t)kvh * p.fast_len + pos) * kHd + d;
+                                : p.ll_fkv + (size_t)s.l * 2 * KVhd * kC + ((size_t)kvh * kC + pos) * kHd + d;
                             st_ll(dl, o0, mytag);
                             st_ll(dl + 1, o1, mytag);
                         }
@@ -1060,7 +1060,7 @@ struct Mega1 {
                     }
                     if (LL) {
                         unsigned long long *dl = slow ? p.ll_nkv + KVhd + rv
-                            : p.ll_fkv + ((size_t)s.l * 2 + 1) * KVhd * p.fast_len + ((size_t)kvh * p.fast_len + pos) * kHd + d;
+                            : p.ll_fkv + ((size_t)s.l * 2 + 1) * KVhd * kC + ((size_t)kvh * kC + pos) * kHd + d;
                         st_ll(dl, v0, mytag);
                         st_ll(dl + 1, v1, mytag);
                     }
@@ -1097,7 +1097,7 @@ struct Mega1 {
     // ------------------------------------------------------------ samplers (CTA 0 only; scratch on the K/V staging area)
     __device__ __forceinline__ void load_sampler_state() {
         const GenState &st = p.st;
-        const int C1 = st.C + 1;
+        const int C1 = kC + 1;
         if (tid == 0) {
             s_active[0] = st.active[0];
             s_eos[0] = st.eos[0];
@@ -1109,7 +1109,7 @@ struct Mega1 {
             s_prev[i] = st.prev[i];
         }
         const int words = (int)(sizeof(RepPenState) / 4);
-        for (int i = tid; i < st.C * words; i += kM1Threads)
+        for (int i = tid; i < kC * words; i += kM1Threads)
             reinterpret_cast<uint32_t *>(s_rep)[i] = reinterpret_cast<const uint32_t *>(st.rep)[i];
         csync();
     }
@@ -1129,7 +1129,7 @@ struct Mega1 {
         sampler_scratch(n, &scratch, &vals, &sred);
         if (s_active[0]) {
             const int frame = s_frame[0];
-            const float u = philox_uniform(st.sp.seed, (uint64_t)frame * (st.C + 1), (uint32_t)p.row0);
+            const float u = philox_uniform(st.sp.seed, (uint64_t)frame * (kC + 1), (uint32_t)p.row0);
             uint32_t tok;
             const unsigned htag = tag_of(kframe, 0, 31, K_HEAD);
             if (LL) ll_wait(htag, (int)gridDim.x);
@@ -1156,7 +1156,7 @@ struct Mega1 {
                 s_eos[0] = eos ? 1 : 0;
                 st.eos[0] = eos ? 1 : 0;
                 if (eos)
-                    for (int c = 0; c < st.C; ++c) {
+                    for (int c = 0; c < kC; ++c) {
                         s_cur[1 + c] = 0;
                         st.cur[1 + c] = 0;
                     }
@@ -1167,7 +1167,7 @@ struct Mega1 {
                     // the slow token, and whether frame kframe + 1 runs, as tagged words for every CTA
                     const unsigned stag = tag_of(kframe, 0, 31, K_SAMPLE);
                     st_ll(p.ll_ct, __uint_as_float(tok), stag);
-                    st_ll(p.ll_ct + st.C + 1, __uint_as_float((unsigned)(cont ? kframe + 2 : kframe + 1)), stag);
+                    st_ll(p.ll_ct + kC + 1, __uint_as_float((unsigned)(cont ? kframe + 2 : kframe + 1)), stag);
                 } else if (cont) {
                     p.bar[1] = (unsigned)(frame + 2);
                 }
@@ -1178,7 +1178,7 @@ struct Mega1 {
 
     __device__ __forceinline__ void sample_fast(int cb, int kframe) {
         const GenState &st = p.st;
-        const int n = p.CS, C = st.C;
+        constexpr int n = kCS, C = kC;
         unsigned char *scratch;
         float *vals, *sred;
         sampler_scratch(n, &scratch, &vals, &sred);
@@ -1242,7 +1242,7 @@ struct Mega1 {
     // ------------------------------------------------------------ frame loop (compute warps)
     __device__ __forceinline__ void run() {
         Step cur = first_step();
-        for (int i = tid; i < p.C * kHd; i += kM1Threads) {
+        for (int i = tid; i < kC * kHd; i += kM1Threads) {
             const int row = i / kHd, d = i - row * kHd, half = kHd / 2;
             csf_s[i] = d < half ? p.cosT[(size_t)row * half + d] : p.sinT[(size_t)row * half + d - half];
         }
