@@ -463,7 +463,8 @@ __device__ __noinline__ int block_sample_sel_t(const float *vals, unsigned char 
         const int nj = min(seglen, max(0, k - g * seglen));
         const uint4 *seg = reinterpret_cast<const uint4 *>(list + g * (seglen + 2));
         unsigned cnt = 0;
-        for (int j = 0; j < (nj + 1) / 2; ++j) {
+#pragma unroll 8
+        for (int j = 0; j < (nj + 1) / 2; ++j) {  // (unrolled: the 16-byte loads of 8 steps are in flight together)
             const uint4 q = seg[j];
             const unsigned long long a = ((unsigned long long)q.y << 32) | q.x, b = ((unsigned long long)q.w << 32) | q.z;
             cnt += (a < mine) ? 1u : 0u;
