@@ -895,10 +895,21 @@ struct Mega1 {
         if (g && 2 * tid < kD) gpre = __ldg(reinterpret_cast<const float2 *>(g) + tid);
     }
 
+    // one specialisation per phase kind: the prologue / epilogue variants become straight-line code
     __device__ __forceinline__ void gemv_phase(const Step &s) {
+        switch (s.kind) {
+            case K_QKV: gemv_phase_t<K_QKV>(s); break;
+            case K_WO: gemv_phase_t<K_WO>(s); break;
+            case K_W13: gemv_phase_t<K_W13>(s); break;
+            case K_W2: gemv_phase_t<K_W2>(s); break;
+            default: gemv_phase_t<K_HEAD>(s); break;
+        }
+    }
+    template <int KIND>
+    __device__ __forceinline__ void gemv_phase_t(const Step &s) {
         const bool slow = s.pass == 0;
         const int cb = s.pass - 1;
-        const int kind = s.kind;
+        constexpr int kind = KIND;
         // the slow stream of frame 0 comes from the prefill (canonical copy only) when the launch starts at the tail
         const bool prefilled = s.frame == 0 && p.first_is_tail != 0;
         const float *xg = stream_rep(slow, (slow && prefilled) ? 0 : my_rep());
