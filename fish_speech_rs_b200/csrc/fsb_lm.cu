@@ -82,6 +82,10 @@ struct fsb_lm {
     unsigned int *mega_bar = nullptr;
     unsigned long long *mega_dbg = nullptr;
     cudaEvent_t prof_m0 = nullptr, prof_m1 = nullptr;
+    // wide-batch megakernel (fsb_lm_megab.cuh): 9..32 rows, bf16 weights
+    bool megab_ok = false;
+    MegaBExtra mbx;
+    int megab_rows_cap = 0;  // rows the split-K workspace / attention scratch are sized for
     // profile mode: event pairs around the weight-streaming kernel
     bool profile = false;
     std::vector<cudaEvent_t> prof_ev;
@@ -200,17 +204,18 @@ static int launch_gemv(fsb_lm *lm, const DevTensor &W, const DevTensor *W3, cons
 // ---------------------------------------------------------------- one decode step of a block stack
 // x (nb, D) in place.  pos_ptr (device, per row) or pos_imm.
 static int decode_layer(fsb_lm *lm, const LayerW &L, float *x, int nb, float *kc, float *vc, int cache_len,
-                        const int *pos_ptr, int pos_imm, int rope_delta, const int *n_active, int nsplit) {
+                        const int *pos_ptr, int pos_imm, int rope_delta, const int *n_active, int nsplit,
+                        const int *active = nullptr) {
     const int D = lm->D, H = lm->H, KV = lm->KV, hd = lm->hd, I = lm->I, QKV = lm->QKV;
     Scratch &s = lm->s;
     FSB_TRY(launch_gemv<EPI_STORE>(lm, L.wqkv, nullptr, x, D, (const float *)L.attn_norm.ptr, nullptr, s.qkv, QKV,
                                    QKV, D, nb, n_active));
     rope_append_kernel<<<nb, 256, 0, lm->stream>>>(s.qkv, s.q, kc, vc, lm->cosT, lm->sinT, pos_ptr, pos_imm,
-                                                   rope_delta, H, KV, hd, cache_len, n_active);
+                                                   rope_delta, H, KV, hd, cache_len, n_active, active);
     LAUNCH_CHECK(lm);
     const int n_rep = H / KV;
     attn_decode_split_kernel<<<dim3(nsplit, KV, nb), n_rep * 32, n_rep * hd * sizeof(float), lm->stream>>>(
-        s.q, kc, vc, pos_ptr, pos_imm, H, KV, hd, cache_len, 1.0f / sqrtf((float)hd), s.partial, n_active);
+        s.q, kc, vc, pos_ptr, pos_imm, H, KV, hd, cache_len, 1.0f / sqrtf((float)hd), s.partial, n_active, active);
     LAUNCH_CHECK(lm);
     attn_decode_combine_kernel<<<nb * H, hd, 0, lm->stream>>>(s.partial, nsplit, hd, s.att, n_active);
     LAUNCH_CHECK(lm);
@@ -225,7 +230,8 @@ static int decode_layer(fsb_lm *lm, const LayerW &L, float *x, int nb, float *kc
 // rows as the MMA N dimension (weights stream once per layer instead of once per 8 rows); attention, RoPE
 // and the KV append are the per-op kernels above.
 static int decode_layer_tc(fsb_lm *lm, const LayerW &L, float *x, int nb, float *kc, float *vc, int cache_len,
-                           const int *pos_ptr, int pos_imm, int rope_delta, const int *n_active, int nsplit) {
+                           const int *pos_ptr, int pos_imm, int rope_delta, const int *n_active, int nsplit,
+                           const int *active = nullptr) {
     const int D = lm->D, H = lm->H, KV = lm->KV, hd = lm->hd, I = lm->I, QKV = lm->QKV;
     Scratch &s = lm->s;
     cudaStream_t st = lm->stream;
@@ -235,11 +241,11 @@ static int decode_layer_tc(fsb_lm *lm, const LayerW &L, float *x, int nb, float 
     FSB_TRY(tc_rmsnorm_split3(x, (const float *)L.attn_norm.ptr, eps, nb, D, lm->sp_xn, (size_t)seg * D, st));
     FSB_TRY(tc_gemm(L.m_wqkv, lm->mx_xn[bi], bn, s.qkv, nullptr, nb, QKV, D, seg, QKV, st, lm->tc_ws, lm->tc_ws_floats));
     rope_append_kernel<<<nb, 256, 0, st>>>(s.qkv, s.q, kc, vc, lm->cosT, lm->sinT, pos_ptr, pos_imm, rope_delta, H, KV, hd,
-                                           cache_len, n_active);
+                                           cache_len, n_active, active);
     LAUNCH_CHECK(lm);
     const int n_rep = H / KV;
     attn_decode_split_kernel<<<dim3(nsplit, KV, nb), n_rep * 32, n_rep * hd * sizeof(float), st>>>(
-        s.q, kc, vc, pos_ptr, pos_imm, H, KV, hd, cache_len, 1.0f / sqrtf((float)hd), s.partial, n_active);
+        s.q, kc, vc, pos_ptr, pos_imm, H, KV, hd, cache_len, 1.0f / sqrtf((float)hd), s.partial, n_active, active);
     LAUNCH_CHECK(lm);
     attn_decode_combine_kernel<<<nb * H, hd, 0, st>>>(s.partial, nsplit, hd, s.att, n_active);
     LAUNCH_CHECK(lm);
@@ -255,10 +261,11 @@ static int decode_layer_tc(fsb_lm *lm, const LayerW &L, float *x, int nb, float 
 }
 
 static int decode_layer_any(fsb_lm *lm, const LayerW &L, float *x, int nb, float *kc, float *vc, int cache_len,
-                            const int *pos_ptr, int pos_imm, int rope_delta, const int *n_active, int nsplit) {
+                            const int *pos_ptr, int pos_imm, int rope_delta, const int *n_active, int nsplit,
+                            const int *active) {
     if (lm->tc_ok && nb > 8)
-        return decode_layer_tc(lm, L, x, nb, kc, vc, cache_len, pos_ptr, pos_imm, rope_delta, n_active, nsplit);
-    return decode_layer(lm, L, x, nb, kc, vc, cache_len, pos_ptr, pos_imm, rope_delta, n_active, nsplit);
+        return decode_layer_tc(lm, L, x, nb, kc, vc, cache_len, pos_ptr, pos_imm, rope_delta, n_active, nsplit, active);
+    return decode_layer(lm, L, x, nb, kc, vc, cache_len, pos_ptr, pos_imm, rope_delta, n_active, nsplit, active);
 }
 
 template <typename WT>
@@ -405,7 +412,7 @@ static int frame_tail(fsb_lm *lm, int nb) {
     for (int cb = 0; cb < lm->C; ++cb) {
         for (int l = 0; l < lm->NFL; ++l)
             FSB_TRY(decode_layer_any(lm, lm->fast_layers[l], s.fast_x, nb, fast_k(lm, l), fast_v(lm, l), lm->fast_len,
-                                     nullptr, cb, 0, na, 1));
+                                     nullptr, cb, 0, na, 1, nullptr));
         FSB_TRY(launch_gemv<EPI_STORE>(lm, lm->fast_out, nullptr, s.fast_x, lm->D, (const float *)lm->fast_norm.ptr,
                                        nullptr, s.fast_logits, lm->CS, lm->CS, lm->D, nb, na));
         if (lm->wdt == FSB_F32)
@@ -426,7 +433,7 @@ static int decode_frame(fsb_lm *lm, int nb) {
     FSB_TRY(embed(lm, lm->h_st.prev, nb, 1, s.hidden, na));
     for (int l = 0; l < lm->NL; ++l)
         FSB_TRY(decode_layer_any(lm, lm->layers[l], s.hidden, nb, slow_k(lm, l), slow_v(lm, l), lm->max_len,
-                                 lm->h_st.pos, 0, 0, na, lm->nsplit));
+                                 lm->h_st.pos, 0, 0, na, lm->nsplit, lm->h_st.active));
     return frame_tail(lm, nb);
 }
 
@@ -670,6 +677,73 @@ static int tc_setup(fsb_lm *lm) {
     return FSB_OK;
 }
 
+
+// ---- wide-batch kernel (fsb_lm_megab.cuh): tensor maps of every weight matrix + scratch
+static bool megab_shapes_ok(const fsb_lm *lm) {
+    return lm->mega_ok && lm->tc_ok && lm->wdt == FSB_BF16 && lm->D == 1024 && lm->I == 4096 && lm->H * lm->hd == 1024 &&
+           lm->hd == 64 && lm->KV == 2 && lm->C == 8 && lm->fast_len == 8 && lm->CS == 1024 && lm->QKV == 1280 &&
+           lm->n_slow_logits <= (1 << kSelIdxBits) && lm->NL >= 1 && lm->NFL >= 1 && lm->mega_grid >= 64;
+}
+static int megab_setup(fsb_lm *lm) {
+    lm->megab_ok = false;
+    memset(&lm->mbx, 0, sizeof(lm->mbx));
+    if (!megab_shapes_ok(lm) || lm->max_batch < 2 || getenv("FSB_NO_MEGAB")) return FSB_OK;
+    const int nl = lm->NL + lm->NFL;
+    std::vector<TcMap> maps((size_t)5 * nl + 2);
+    for (int i = 0; i < nl; ++i) {
+        const LayerW &L = i < lm->NL ? lm->layers[i] : lm->fast_layers[i - lm->NL];
+        FSB_TRY(tc_make_map_bf16(&maps[5 * i + 0], L.wqkv.ptr, lm->QKV, lm->D, 128));
+        FSB_TRY(tc_make_map_bf16(&maps[5 * i + 1], L.wo.ptr, lm->D, lm->H * lm->hd, 128));
+        FSB_TRY(tc_make_map_bf16(&maps[5 * i + 2], L.w1.ptr, lm->I, lm->D, 64));  // a W13 tile = 64 rows of w1 | 64 rows of w3
+        FSB_TRY(tc_make_map_bf16(&maps[5 * i + 3], L.w3.ptr, lm->I, lm->D, 64));
+        FSB_TRY(tc_make_map_bf16(&maps[5 * i + 4], L.w2.ptr, lm->D, lm->I, 128));
+    }
+    FSB_TRY(tc_make_map_bf16(&maps[5 * nl + 0], lm->out_w.ptr, lm->V, lm->D, 128));
+    FSB_TRY(tc_make_map_bf16(&maps[5 * nl + 1], lm->fast_out.ptr, lm->CS, lm->D, 128));
+    TcMap *d_maps = nullptr;
+    FSB_TRY(dev_alloc(lm, &d_maps, maps.size()));
+    FSB_CUDA_OK(cudaMemcpy(d_maps, maps.data(), maps.size() * sizeof(TcMap), cudaMemcpyHostToDevice));
+    MegaBExtra &x = lm->mbx;
+    x.maps = reinterpret_cast<const CUtensorMap *>(d_maps);
+    const int B = std::min(lm->max_batch, 32);
+    lm->megab_rows_cap = B;
+    const int npad = B <= 16 ? 16 : 32;
+    FSB_TRY(dev_alloc(lm, &x.ws, (size_t)256 * npad * 128));  // W13: 64 tiles x 4 slices
+    FSB_TRY(dev_alloc(lm, &x.cnt, (size_t)6 * kMBCntStride + 2 * 32 + 4));
+    x.att_cnt = x.cnt + 6 * kMBCntStride;
+    x.go = x.att_cnt + 2 * 32;
+    FSB_TRY(dev_alloc(lm, &x.att, (size_t)B * lm->D));
+    FSB_TRY(dev_alloc(lm, &x.apart, (size_t)B * lm->H * kMBMaxSplit * (lm->hd + 4)));
+    FSB_TRY(dev_alloc(lm, &x.ssq_x, (size_t)B * kMBSsq));
+    FSB_TRY(dev_alloc(lm, &x.ssq_fx, (size_t)B * kMBSsq));
+    x.head_tiles = (lm->n_slow_logits + 127) / 128;
+    x.head_extra = lm->slow_row0 != lm->slow_rest_base - 1 ? 1 : 0;
+    int nst = kMBMaxStages;
+    while (nst > 4 && megab_smem_bytes(nst) > lm->smem_optin) --nst;
+    if (megab_smem_bytes(nst) > lm->smem_optin) return FSB_OK;
+    if (const char *v = getenv("FSB_MEGAB_STAGES")) nst = std::max(2, std::min(nst, atoi(v)));
+    x.nstages = nst;
+    lm->megab_ok = true;
+    return FSB_OK;
+}
+
+// all rows of the batch in one launch (bsz <= 32)
+static int megab_launch_rows(fsb_lm *lm, int nb, int nframes) {
+    MegaParams mp = lm->mp;
+    mp.nb = nb;
+    mp.nframes = nframes;
+    mp.first_is_tail = 1;
+    mp.row0 = 0;
+    mp.st = lm->h_st;
+    const size_t cnt_words = (size_t)6 * kMBCntStride + 2 * 32 + 4;
+    FSB_CUDA_OK(cudaMemsetAsync(lm->mega_bar, 0, 4 * sizeof(unsigned int), lm->stream));
+    FSB_CUDA_OK(cudaMemsetAsync(lm->mbx.cnt, 0, cnt_words * sizeof(unsigned), lm->stream));
+    const int npad = lm->megab_rows_cap <= 16 ? 16 : 32;
+    FSB_CUDA_OK(megab_launch(mp, lm->mbx, npad, lm->mega_grid, megab_smem_bytes(lm->mbx.nstages), lm->stream));
+    lm->launches++;
+    return FSB_OK;
+}
+
 static void precompute_freqs(const fsb_model_args &c, int max_len, std::vector<float> *cosv, std::vector<float> *sinv) {
     // dual_ar.rs:168-186: theta_i = 1 / base^(i/n) in f32, idx_theta = pos * theta (f32 product), cos/sin.
     // Transcendentals in f64 rounded once to f32 (== correctly rounded f32), as in oracle/dual_ar.py.
@@ -800,6 +874,7 @@ static int lm_create_impl(fsb_lm *lm, const fsb_tensor *w, size_t n) {
     FSB_CUDA_OK(init_gemv_attrs(std::max(lm->D, lm->I)));
     FSB_TRY(mega_setup(lm));
     FSB_TRY(tc_setup(lm));
+    FSB_TRY(megab_setup(lm));
     FSB_CUDA_OK(cudaStreamSynchronize(st));
     return FSB_OK;
 }
@@ -866,10 +941,24 @@ static int generate_impl(fsb_lm *lm, const uint32_t *const *prompts, const int32
     FSB_REQUIRE(!fixed || fixed_len >= 1, FSB_ERR_INVALID, "FSB_GEN_FIXED_LEN needs fixed_len >= 1");
     if (!(flags & FSB_GEN_KEEP_SLOW_KV))
         for (int b = 0; b < bsz; ++b) lm->kv_len[b] = 0;
+    // sampling/mod.rs: WeightedIndex over an empty candidate set is an error in the reference too
+    FSB_REQUIRE(std::isfinite(sa->temp) && sa->temp >= 0.0 && std::isfinite(sa->top_p), FSB_ERR_INVALID,
+                "sampling: temp %g / top_p %g must be finite and temp >= 0", sa->temp, sa->top_p);
+    FSB_REQUIRE(sa->temp <= 1e-7 || sa->top_k >= 1, FSB_ERR_INVALID, "sampling: top_k must be >= 1 when temp > 0");
+    FSB_REQUIRE(std::isfinite(sa->repetition_penalty) && sa->repetition_penalty != 0.f, FSB_ERR_INVALID,
+                "sampling: repetition_penalty must be finite and non-zero");
     std::vector<int> max_frames(bsz);
     for (int b = 0; b < bsz; ++b) {
         const int P = prompt_lens[b];
         FSB_REQUIRE(P >= 1 && prompts[b], FSB_ERR_INVALID, "prompt %d is empty", b);
+        for (int i = 0; i < P; ++i)
+            FSB_REQUIRE(prompts[b][i] < (uint32_t)lm->V, FSB_ERR_INVALID, "prompt %d: token id %u at column %d >= vocab_size %d",
+                        b, prompts[b][i], i, lm->V);
+        for (int c = 1; c <= C; ++c)
+            for (int i = 0; i < P; ++i)
+                FSB_REQUIRE(prompts[b][(size_t)c * P + i] < (uint32_t)lm->CS, FSB_ERR_INVALID,
+                            "prompt %d: code %u (codebook %d, column %d) >= codebook_size %d", b,
+                            prompts[b][(size_t)c * P + i], c - 1, i, lm->CS);
         // Q3: `input_pos > max_new_tokens + n_cached` stops the iterator (single_batch.rs:61,77)
         long long lim = (long long)max_new_tokens - P + 2;
         if (lim < 1) lim = 1;
@@ -924,7 +1013,16 @@ static int generate_impl(fsb_lm *lm, const uint32_t *const *prompts, const int32
     for (int b = 0; b < bsz; ++b) total_max = std::max(total_max, max_frames[b]);
     bool use_mega = lm->mega_ok && lm->opt.decode_mode != 1 && !lm->profile;
     int group = 8;  // rows per megakernel launch: the largest batch template whose shared memory fits
-    if (use_mega) {
+    // wide batches (cfg3 / cfg5): ONE tcgen05 megakernel launch for all rows (fsb_lm_megab.cuh)
+    int megab_min = 9;
+    if (const char *v = getenv("FSB_MEGAB_MIN_ROWS")) megab_min = std::max(2, atoi(v));
+    const bool use_megab = use_mega && lm->megab_ok && bsz >= megab_min && bsz <= lm->megab_rows_cap &&
+                           (g.sp.greedy || g.sp.top_k <= (uint32_t)kSelMaxK);
+    if (use_megab) {
+        group = bsz;
+        FSB_CUDA_OK(cudaEventRecord(lm->ev1, st));
+        FSB_TRY(megab_launch_rows(lm, bsz, total_max));
+    } else if (use_mega) {
         int xf, vf;  // (the opt-in limit is cached at setup: cudaGetDeviceProperties costs ~200 ms per call)
         while (group > 1 && mega_smem_bytes(lm, group, &xf, &vf) > lm->smem_optin) group /= 2;
         use_mega = mega_smem_bytes(lm, group, &xf, &vf) <= lm->smem_optin;
@@ -932,8 +1030,10 @@ static int generate_impl(fsb_lm *lm, const uint32_t *const *prompts, const int32
         if (lm->opt.decode_mode == 0 && bsz > group) use_mega = false;
     }
     FSB_REQUIRE(use_mega || lm->opt.decode_mode != 2 || lm->profile, FSB_ERR_UNSUPPORTED,
-                "decode_mode 2 (megakernel) needs bsz <= 8 and cooperative launch support");
-    if (use_mega) {
+                "decode_mode 2 (megakernel) needs bsz <= 8 (<= 32 with bf16 Fish shapes) and cooperative launch support");
+    if (use_megab) {
+        // launched above
+    } else if (use_mega) {
         // frame 0 = tail on the prefilled hidden state, then whole frames; the kernel leaves its
         // loop by itself once every row is finished (no host polling).  The prefill event sits
         // right before the launch, so frame 0's tail is accounted to the frame loop here.
@@ -1307,6 +1407,24 @@ int fsb_lm_generate_static_batch(fsb_lm *lm, const uint32_t *const *prompts, con
     FSB_TRY(check_handle(lm));
     return finish(lm, generate_impl(lm, prompts, prompt_lens, bsz, max_new_tokens, sampling, flags, fixed_len,
                                     out_codes, cap, out_lens));
+}
+
+int fsb_lm_last_frames(fsb_lm *lm, int32_t row, uint32_t *out, size_t cap, size_t *out_len) {
+    FSB_TRY(check_handle(lm));
+    FSB_REQUIRE(out && out_len && row >= 0 && row < lm->max_batch, FSB_ERR_INVALID, "last_frames: bad arguments");
+    const int C1 = lm->C + 1;
+    int nf = 0;
+    FSB_CUDA_OK(cudaMemcpy(&nf, lm->h_st.frame + row, sizeof(int), cudaMemcpyDeviceToHost));
+    FSB_REQUIRE(nf >= 0 && nf <= lm->h_st.out_cap, FSB_ERR_STATE, "last_frames: no generation on row %d", row);
+    FSB_REQUIRE((size_t)nf <= cap, FSB_ERR_INVALID, "last_frames: %d frames exceed the capacity %zu", nf, cap);
+    std::vector<uint32_t> h((size_t)nf * C1);
+    if (nf > 0)
+        FSB_CUDA_OK(cudaMemcpy(h.data(), lm->h_st.out + (size_t)row * lm->h_st.out_cap * C1, h.size() * sizeof(uint32_t),
+                               cudaMemcpyDeviceToHost));
+    for (int f = 0; f < nf; ++f)
+        for (int c = 0; c < C1; ++c) out[(size_t)c * cap + f] = h[(size_t)f * C1 + c];
+    *out_len = (size_t)nf;
+    return FSB_OK;
 }
 
 int fsb_lm_set_profile(fsb_lm *lm, int on) {

@@ -175,9 +175,12 @@ __global__ void __launch_bounds__(kGemvThreads) gemv_kernel(GemvArgs a) {
 __global__ void rope_append_kernel(const float *__restrict__ qkv, float *__restrict__ q, float *__restrict__ kc,
                                    float *__restrict__ vc, const float *__restrict__ cosT,
                                    const float *__restrict__ sinT, const int *pos_ptr, int pos_imm, int rope_delta,
-                                   int H, int KV, int hd, int max_len, const int *n_active) {
+                                   int H, int KV, int hd, int max_len, const int *n_active,
+                                   const int *active = nullptr) {
     if (n_active && *n_active == 0) return;
     const int b = blockIdx.x;
+    // a finished row of a ragged batch sits at pos == its budget (possibly == max_len): it must not append
+    if (active && !active[b]) return;
     const int pos = pos_ptr ? pos_ptr[b] : pos_imm;  // cache slot
     const int rpos = pos + rope_delta;                // RoPE row (== input_pos)
     const int half = hd / 2;
@@ -213,8 +216,9 @@ constexpr int kAttnMaxRep = 8;
 __global__ void attn_decode_split_kernel(const float *__restrict__ q, const float *__restrict__ kc,
                                          const float *__restrict__ vc, const int *pos_ptr, int pos_imm, int H,
                                          int KV, int hd, int max_len, float scale, float *__restrict__ partial,
-                                         const int *n_active) {
+                                         const int *n_active, const int *active = nullptr) {
     if (n_active && *n_active == 0) return;
+    if (active && !active[blockIdx.z]) return;  // finished row: nothing cached at `pos` (see rope_append_kernel)
     extern __shared__ float qs[];  // n_rep * hd
     const int split = blockIdx.x, nsplit = gridDim.x, kvh = blockIdx.y, b = blockIdx.z;
     const int n_rep = H / KV;

@@ -498,7 +498,7 @@ struct Mega {
                     }
                     M = Mn;
                 }
-                v = o / Lsum;
+                v = ns > 0 ? o / Lsum : 0.f;
             }
             xs[i] = v;
         }
@@ -664,9 +664,12 @@ struct Mega {
                 // once per frame: this frame's slow positions and their RoPE rows -> smem
                 for (int i = tid; i < NB * p.hd; i += kMegaThreads) {
                     const int b = i / p.hd, d = i - b * p.hd, half = p.hd / 2;
-                    const int pos = b < p.nb ? __ldcg(p.st.pos + b) : 0;
+                    // a finished row of a ragged batch (pos == its budget, possibly == max_len) is parked at
+                    // pos -1: no attention item, no K/V append, RoPE row 0
+                    const bool live = b < p.nb && __ldcg(p.st.active + b) != 0;
+                    const int pos = live ? __ldcg(p.st.pos + b) : 0;
                     cs_s[i] = d < half ? p.cosT[(size_t)pos * half + d] : p.sinT[(size_t)pos * half + d - half];
-                    if (d == 0) pos_s[b] = pos;
+                    if (d == 0) pos_s[b] = live ? pos : -1;
                 }
                 // DualARTransformer::embed, dual_ar.rs:532-567, on the previous frame's codes
                 const WT *emb = reinterpret_cast<const WT *>(p.emb), *cbe = reinterpret_cast<const WT *>(p.cb_emb);
@@ -743,6 +746,7 @@ struct Mega {
                 const int r = plan.r0 + 2 * pr;
                 const float v0 = row_val(0, 2 * pr, b), v1 = row_val(0, 2 * pr + 1, b);
                 const int pos = slow ? pos_s[b] : cb;
+                if (pos < 0) continue;  // finished row
                 if (r < Hhd + KVhd) {
                     const int pi = (r % p.hd) / 2;
                     const float *cs = slow ? cs_s + b * p.hd : csf_s + cb * p.hd;

@@ -1,5 +1,7 @@
 // Parameters of the persistent decode megakernel (fsb_lm_mega.cuh) shared with the host code.
 #pragma once
+#include <cuda.h>
+
 #include "fsb_common.cuh"
 #include "fsb_sample.cuh"
 
@@ -83,11 +85,43 @@ struct MegaParams {
     unsigned long long *dbg;  // optional (FSB_MEGA_TIMERS=1): per phase kind {work ns, barrier ns, count} of CTA 0 and the last CTA
 };
 
+// ---- wide-batch kernel (fsb_lm_megab.cuh): 9..32 rows, bf16 weights, tcgen05 + TMA weight ring
+constexpr int kMBWorkers = 256;               // worker threads (warps 0-7, named barrier 1)
+constexpr int kMBThreads = kMBWorkers + 64;   // + TMA producer warp + MMA warp
+constexpr int kMBStage = 16384;               // one ring stage: 128 rows x 64 k bf16
+constexpr int kMBXsBytes = 49152;             // activation operand | K/V staging | sampler scratch
+constexpr int kMBMaxStages = 10;
+constexpr int kMBChunk = 64;                  // cached positions staged at once
+constexpr int kMBKvStride = 80;               // floats per staged K/V row
+constexpr int kMBMaxSplit = 16;               // position ranges per (row, kv head)
+constexpr int kMBSsq = 32;                    // sum-of-squares slots per row
+constexpr int kMBCntStride = 80;              // arrival counters per phase kind
+constexpr long long kMBSpinLimit = 6000000000ll;  // ~3 s: a broken protocol traps instead of hanging the GPU
+
+struct MegaBExtra {
+    const CUtensorMap *maps;  // 5 per layer (wqkv, wo, w1, w3, w2), slow then fast, then out_w, fast_out
+    float *ws;                // split-K partials [tile][slice][NPAD][128]
+    unsigned *cnt;            // [6][kMBCntStride] arrival counters (monotonic), then [B * KV] attention counters
+    unsigned *att_cnt;
+    unsigned *go;             // [4] "some row continues into frame f" flags
+    float *att;               // (B, H * hd) attention output
+    float *apart;             // (B, H, kMBMaxSplit, hd + 4) partial attention (o, m, l)
+    float *ssq_x, *ssq_fx;    // (B, kMBSsq) partial sums of squares of the slow / fast stream
+    int nstages;
+    int head_tiles;           // 128-row tiles of the constrained slow head (without the extra <|im_end|> tile)
+    int head_extra;           // 1: <|im_end|> is not adjacent to the semantic range -> one more tile for logit 0
+};
+
+
 // Launchers, one translation unit per weight dtype (fsb_lm_mega_{bf16,f32}.cu).  NB in {1,2,4,8}.
 cudaError_t mega_launch_bf16(int NB, const MegaParams &mp, int grid, size_t smem, cudaStream_t st);
 cudaError_t mega_launch_f32(int NB, const MegaParams &mp, int grid, size_t smem, cudaStream_t st);
 // single-row kernel with the TMA weight ring (fsb_lm_mega1.cuh)
 cudaError_t mega1_launch_bf16(const MegaParams &mp, int grid, size_t smem, cudaStream_t st);
 cudaError_t mega1_launch_f32(const MegaParams &mp, int grid, size_t smem, cudaStream_t st);
+
+// wide-batch kernel; npad in {16, 32}
+cudaError_t megab_launch(const MegaParams &mp, const MegaBExtra &ex, int npad, int grid, size_t smem, cudaStream_t st);
+size_t megab_smem_bytes(int nstages);
 
 }  // namespace fsb

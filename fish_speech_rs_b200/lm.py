@@ -113,6 +113,15 @@ class DualARTransformer:
         F.check(F.lib().fsb_lm_curr_kv_size(self._h, C.byref(n)))
         return n.value
 
+    def last_frames(self, row: int = 0, cap: int = 0) -> np.ndarray:
+        """Frames of the last generate call for `row` as `SingleBatchGenerator::next` yields them: u32 (C+1, T),
+        slow token in row 0, <|im_end|> frames included (single_batch.rs:76-214)."""
+        cap = cap or (self.cfg["max_seq_len"] + 2)
+        out = np.zeros((self.cfg["num_codebooks"] + 1, cap), np.uint32)
+        n = C.c_size_t()
+        F.check(F.lib().fsb_lm_last_frames(self._h, int(row), out.ctypes.data, cap, C.byref(n)))
+        return out[:, : n.value].copy()
+
     def set_profile(self, on: bool):
         F.check(F.lib().fsb_lm_set_profile(self._h, int(on)))
 

@@ -103,7 +103,7 @@ typedef struct fsb_sampling_args {
 typedef struct fsb_lm_options {
     int32_t device;        /* CUDA ordinal (reference: Device::cuda_if_available(0), server/src/main.rs:25) */
     void *stream;          /* cudaStream_t to run on; NULL == the handle creates its own */
-    int32_t weight_dtype;  /* FSB_F32 (parity mode) or FSB_BF16 (weights+KV stored bf16, fp32 math) */
+    int32_t weight_dtype;  /* FSB_F32 (parity mode) or FSB_BF16 (weights stored bf16; activations, KV cache and all math stay fp32) */
     int32_t max_batch;     /* rows the KV arena is sized for (>= 1) */
     int32_t max_seq_len;   /* positions per row in the KV arena; 0 == model max_seq_len */
     int32_t fish_version;  /* fsb_fish_version */
@@ -176,6 +176,12 @@ int fsb_lm_generate_static_batch(fsb_lm *lm, const uint32_t *const *prompts, con
                                  int32_t bsz, size_t max_new_tokens, const fsb_sampling_args *sampling,
                                  uint32_t flags, int32_t fixed_len, uint32_t *const *out_codes, size_t cap,
                                  size_t *out_lens);
+
+/* Every frame the last generate call emitted for batch row `row`, as `SingleBatchGenerator::next` yields them
+ * (single_batch.rs:76-214: a (C+1, 1) column per frame: the slow/semantic token, then the C codes), INCLUDING
+ * <|im_end|> frames that generate_blocking drops (single_batch.rs:262-266).  out: u32 (C+1, cap) row-major with row
+ * stride `cap`; *out_len = frames written.  Lets a caller (and the parity tests) replay a generation step by step. */
+int fsb_lm_last_frames(fsb_lm *lm, int32_t row, uint32_t *out, size_t cap, size_t *out_len);
 
 int fsb_lm_get_stats(fsb_lm *lm, fsb_lm_stats *out);
 /* Profiling switch (the reference's only instrumentation is Instant + println!, single_batch.rs:233-303).
