@@ -3,9 +3,12 @@
 
 One "step" = one pass of the hot path over one batch of synthetic utterances per GPU:
 prompt (C+1, P) -> prefill -> N frames of dual-AR decode (slow step + 8 fast steps, device-side
-sampling) -> Firefly vocoder -> PCM.  Default workload = BASELINE.json configs[1] ("cfg2":
-Fish 1.5, batch 1, temp 0.7 / top_p 0.8, 10 s utterance = 216 frames, P = 384).  Utterances are
-independent, so N GPUs run N shards with no collective on the data path ("weak" scaling).
+sampling) -> Firefly vocoder -> PCM.  Default workload = BASELINE.json configs[4] ("cfg5": Fish 1.5,
+long-form 60 s utterances = 1292 frames, P = 384, temp 0.7 / top_p 0.8), 32 utterances per GPU: the
+largest single-GPU configuration, and the per-GPU shard of the 8-GPU batch of 256.  With N GPUs the
+32 N utterances are assigned to ranks by fish_speech_rs_b200.shard.assign (independent utterances, no
+collective on the data path, "weak" scaling).  At N = 1 the line also carries two short secondary
+blocks on the same handle: `cfg3` (B = 16 mixed prompts, 216 frames) and `latency_b1` (cfg2, B = 1).
 
   value  : frames/s from device time only (CUDA events on the library's stream: prefill + frame loop
            + vocoder kernels), inputs resident in HBM
@@ -31,11 +34,16 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
 CONFIGS = {
-    # name: (fish_version, batch per GPU, prompt lens fn, frames, temp, top_p)
+    # name: fish version, utterances per GPU, prompt lengths, frames, sampling
+    "cfg1": dict(version="1.5", batch=1, prompt_lens=lambda b: [330] * b, frames=40, temp=0.0, top_p=0.8,
+                 desc="Fish 1.5 greedy, single short utterance, default voice (P=330, N=40): the reference's CPU plumbing case"),
     "cfg2": dict(version="1.5", batch=1, prompt_lens=lambda b: [384] * b, frames=216, temp=0.7, top_p=0.8,
                  desc="Fish 1.5 B=1 temp=0.7 top_p=0.8 10 s utterance (P=384, N=216)"),
-    "cfg3": dict(version="1.5", batch=16, prompt_lens=lambda b: [300 + 28 * i for i in range(b)], frames=216,
+    "cfg3": dict(version="1.5", batch=16, prompt_lens=lambda b: [300 + 28 * (i % 16) for i in range(b)], frames=216,
                  temp=0.7, top_p=0.8, desc="Fish 1.5 B=16 mixed prompts 300..720, N=216 each"),
+    "cfg4": dict(version="1.4", batch=1, prompt_lens=lambda b: [274 + 110] * b, frames=216, temp=0.7, top_p=0.8,
+                 clip_samples=562265,
+                 desc="Fish 1.4 voice clone: 12.75 s clip -> log-mel -> encoder -> 274 code frames -> conditioned decode (N=216) -> vocoder"),
     "b2": dict(version="1.5", batch=2, prompt_lens=lambda b: [384] * b, frames=64, temp=0.7, top_p=0.8,
                desc="tuning probe: B=2, P=384, N=64"),
     "b4": dict(version="1.5", batch=4, prompt_lens=lambda b: [384] * b, frames=64, temp=0.7, top_p=0.8,
@@ -43,8 +51,9 @@ CONFIGS = {
     "b8": dict(version="1.5", batch=8, prompt_lens=lambda b: [384] * b, frames=64, temp=0.7, top_p=0.8,
                desc="tuning probe: B=8, P=384, N=64"),
     "cfg5": dict(version="1.5", batch=32, prompt_lens=lambda b: [384] * b, frames=1292, temp=0.7, top_p=0.8,
-                 desc="Fish 1.5 B=32/GPU long-form 60 s (P=384, N=1292)"),
+                 desc="Fish 1.5 long-form 60 s utterances (P=384, N=1292), 32 per GPU (256 on 8 GPUs), sharded data-parallel"),
 }
+VOCODER_FLOP_PER_FRAME = 2.646e9  # 1323.2 M MAC per code frame
 FRAME_RATE = 44100.0 / 2048.0  # 21.533 frames/s (reference prints with 21.535, single_batch.rs:292-295)
 
 
@@ -95,15 +104,18 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def build_inputs(cfgname, rank):
-    from fish_speech_rs_b200 import synth
+def build_inputs(cfgname, rank, world=1):
+    """This rank's utterances of the global batch (batch-per-GPU x world utterances, seeds by GLOBAL index),
+    assigned by the length-balanced static partition of fish_speech_rs_b200.shard."""
+    from fish_speech_rs_b200 import shard, synth
     c = CONFIGS[cfgname]
     mcfg = dict(synth.FISH15 if c["version"] == "1.5" else synth.FISH14)
     tok = dict(synth.FISH15_TOKENS if c["version"] == "1.5" else synth.FISH14_TOKENS)
-    voice = np.load(os.path.join(ROOT, "tests", "golden", "default_voice.npy"))
-    B = c["batch"]
-    prompts = [synth.make_prompt(mcfg, tok, P, seed=1000 + rank * B + i, voice=voice)
-               for i, P in enumerate(c["prompt_lens"](B))]
+    voice = np.load(os.path.join(ROOT, "tests", "golden", "default_voice.npy"))  # make_prompt stores codes + 1 for <= 1.4
+    total = c["batch"] * world
+    lens = c["prompt_lens"](total)
+    mine = shard.my_shard([P + c["frames"] for P in lens], rank, world)
+    prompts = [synth.make_prompt(mcfg, tok, lens[i], seed=1000 + i, voice=voice) for i in mine]
     return c, mcfg, tok, prompts
 
 
@@ -123,7 +135,8 @@ def cpu_reference_sample(cfgname, lm_w, codec_w, sample_frames, threads):
     args = osamp.SamplingArgs(c["temp"], c["top_p"], 256, 1.4, seed=1)
     prompt = torch.from_numpy(prompts[0].astype(np.int64))
     with torch.no_grad():
-        gen = ogen.SingleBatchGenerator(model, prompt, 100000, args, True, 0, fixed_len=sample_frames)
+        gen = ogen.SingleBatchGenerator(model, prompt, 100000, args, True, 0, fixed_len=sample_frames,
+                                        force_slow=None if c["version"] == "1.5" else [tok["pad_id"]])
         t0 = time.perf_counter()
         frames = [gen.next()]
         t1 = time.perf_counter()
@@ -141,15 +154,15 @@ def cpu_reference_sample(cfgname, lm_w, codec_w, sample_frames, threads):
     total = B * (t_prefill + (N - 1) * t_frame + N * t_voc)
     desc = (f"oracle on 1 utterance: prefill P={prompt.shape[1]} ({t_prefill:.2f}s) + {sample_frames - 1} decode frames "
             f"({t_frame * 1e3:.0f} ms/frame) + vocoder on {sample_frames} frames ({t_voc * 1e3:.0f} ms/frame); "
-            f"scaled to B={B} x {N} frames")
+            f"scaled to B={B} x {N} frames (decode cost taken at the prompt's context length: favours the CPU for long utterances)")
     return B * N / total, desc
 
 
-def make_weights(version, want_lm=True, want_codec=True):
+def make_weights(version, want_lm=True, want_codec=True, with_encoder=False):
     from fish_speech_rs_b200 import synth
     mcfg = synth.FISH15 if version == "1.5" else synth.FISH14
     lm_w = synth.make_lm_weights(mcfg, seed=1234) if want_lm else None
-    codec_w = synth.make_codec_weights(seed=4321, with_encoder=False) if want_codec else None
+    codec_w = synth.make_codec_weights(seed=4321, with_encoder=with_encoder) if want_codec else None
     return lm_w, codec_w
 
 
@@ -179,10 +192,95 @@ def run_reference(a):
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
+def fp32_peak():
+    """FP32 FMA peak measured on this pool's B200 by tools/fp32_peak.cu (profiles/r02_fp32_peak.json), else nominal."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "r02_fp32_peak.json")))
+        return float(d["fp32_tflops"]), "measured (tools/fp32_peak.cu)"
+    except Exception:
+        return 148 * 128 * 2 * 1.965e9 / 1e12, "nominal 148 SM x 128 lanes x 2 x 1.965 GHz"
+
+
+class Workload:
+    """One configuration bound to a (possibly shared) LM + codec handle: `step()` is one pass of the hot path."""
+
+    def __init__(self, name, lm, codec, rank, world, seed):
+        import torch
+        from fish_speech_rs_b200 import SamplingArgs
+        self.name, self.lm, self.codec = name, lm, codec
+        self.c, self.mcfg, self.tok, self.prompts = build_inputs(name, rank, world)
+        c = self.c
+        self.B, self.N = len(self.prompts), c["frames"]
+        self.sargs = SamplingArgs(c["temp"], c["top_p"], 256, 1.4, seed=seed)
+        self.clip = None
+        if "clip_samples" in c:  # cfg4: the voice comes out of the GPU encoder (FireflyCodec::encode)
+            rng = np.random.default_rng(17)
+            self.clip = (0.1 * rng.standard_normal(c["clip_samples"])).astype(np.float32)
+        self.pin_prompts = []
+        for p in self.prompts:
+            t = torch.empty(p.shape, dtype=torch.int32).pin_memory()
+            v = t.numpy().view(np.uint32)
+            v[...] = p
+            self.pin_prompts.append(v)
+        self.pcm_pin = [torch.empty((1, 1, 2048 * self.N), dtype=torch.float32).pin_memory().numpy() for _ in range(self.B)]
+        self.h2d = sum(p.nbytes for p in self.prompts) + self.B * 8 * self.N * 4 + (self.clip.nbytes if self.clip is not None else 0)
+        self.d2h = self.B * 8 * self.N * 4 + self.B * 2048 * self.N * 4
+
+    def step(self):
+        from fish_speech_rs_b200 import generate_static_batch
+        import torch
+        enc_ms = 0.0
+        if self.clip is not None:
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            codes = self.codec.encode(self.clip)  # (1, 8, 274); timed: mel front-end + ConvNeXt encoder + FSQ
+            enc_ms = (time.perf_counter() - t0) * 1e3
+            assert codes.shape[2] == 274
+        codes = generate_static_batch(self.lm, self.pin_prompts, 100000, self.sargs, fixed_len=self.N)
+        st = self.lm.stats()
+        # synthetic-weight LMs emit codes >= 1000 that the FSQ table rejects (Q11): harness-side clamp
+        cl = [np.minimum(x, 999) for x in codes]
+        self.codec.decode_batch(cl, out=self.pcm_pin)
+        cs = self.codec.stats()
+        dev_ms = st["prefill_ms"] + st["decode_ms"] + cs["device_ms"] + enc_ms
+        return dev_ms, st, cs, sum(x.shape[1] for x in codes), enc_ms
+
+
+def time_workload(wl, steps, warmup, barrier):
+    for _ in range(warmup):
+        wl.step()
+    barrier()
+    t0 = time.perf_counter()
+    acc = dict(dev=0.0, frames=0, launches=0, pre=0.0, dec=0.0, voc=0.0, enc=0.0, dom_ms=0.0, dom_n=0, dom_bytes=0)
+    for _ in range(steps):
+        dev_ms, st, cs, nf, enc = wl.step()
+        acc["dev"] += dev_ms
+        acc["frames"] += nf
+        acc["launches"] += st["kernel_launches"] + cs["kernel_launches"]
+        acc["pre"] += st["prefill_ms"]
+        acc["dec"] += st["decode_ms"]
+        acc["voc"] += cs["device_ms"]
+        acc["enc"] += enc
+        acc["dom_ms"] += st["dominant_kernel_ms"]
+        acc["dom_n"] += st["dominant_kernel_launches"]
+        acc["dom_bytes"] += st["dominant_kernel_bytes"]
+    barrier()
+    acc["wall_ms"] = (time.perf_counter() - t0) * 1e3
+    return acc
+
+
+def secondary_block(wl, steps, warmup, barrier):
+    a = time_workload(wl, steps, warmup, barrier)
+    return {"workload": wl.name, "desc": wl.c["desc"], "utterances": wl.B, "frames": wl.N, "steps": steps, "warmup": warmup,
+            "value": a["frames"] / (a["dev"] / 1e3), "e2e": a["frames"] / (a["wall_ms"] / 1e3), "unit": "frames/s",
+            "ms_per_step": a["dev"] / steps,
+            "breakdown_ms_per_step": {"lm_prefill": a["pre"] / steps, "lm_decode": a["dec"] / steps, "vocoder": a["voc"] / steps}}
+
+
 def run_ours(a):
     import torch
     import torch.distributed as dist
-    from fish_speech_rs_b200 import DualARTransformer, FireflyCodec, SamplingArgs, generate_static_batch
+    from fish_speech_rs_b200 import DualARTransformer, FireflyCodec
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -190,36 +288,22 @@ def run_ours(a):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    c, mcfg, tok, prompts = build_inputs(a.config, rank)
+    c = CONFIGS[a.config]
+    extras = [] if (world > 1 or not a.extras or a.config != "cfg5" or a.frames) else ["cfg3", "cfg2"]
+    lm_w, codec_w = make_weights(c["version"], with_encoder="clip_samples" in c)
     B, N = c["batch"], c["frames"]
-    lm_w, codec_w = make_weights(c["version"])
-    max_len = max(p.shape[1] for p in prompts) + N + 8
-    lm = DualARTransformer(lm_w, mcfg, tok, fish_version=c["version"], device=local, dtype=a.dtype, max_batch=B,
-                           max_seq_len=max_len, decode_mode=a.decode_mode)
-    codec = FireflyCodec(codec_w, fish_version=c["version"], device=local, max_frames=N)
+    max_len = max(c["prompt_lens"](B * world)) + N + 8
+    for x in extras:
+        max_len = max(max_len, max(CONFIGS[x]["prompt_lens"](CONFIGS[x]["batch"])) + CONFIGS[x]["frames"] + 8)
+    from fish_speech_rs_b200 import synth
+    v15 = c["version"] == "1.5"
+    lm = DualARTransformer(lm_w, dict(synth.FISH15 if v15 else synth.FISH14),
+                           dict(synth.FISH15_TOKENS if v15 else synth.FISH14_TOKENS), fish_version=c["version"],
+                           device=local, dtype=a.dtype, max_batch=B, max_seq_len=max_len, decode_mode=a.decode_mode)
+    codec = FireflyCodec(codec_w, fish_version=c["version"], device=local, max_frames=N, with_encoder="clip_samples" in c)
     if not (a.cpu_baseline and rank == 0):
         del lm_w
-    sargs = SamplingArgs(c["temp"], c["top_p"], 256, 1.4, seed=1234 + rank)
-    # pinned host buffers for the e2e leg
-    pin_prompts = []
-    for p in prompts:
-        t = torch.empty(p.shape, dtype=torch.int32).pin_memory()
-        v = t.numpy().view(np.uint32)
-        v[...] = p
-        pin_prompts.append(v)
-    pcm_pin = [torch.empty((1, 1, 2048 * N), dtype=torch.float32).pin_memory().numpy() for _ in range(B)]
-    h2d = sum(p.nbytes for p in prompts) + B * 8 * N * 4
-    d2h = B * 8 * N * 4 + B * 2048 * N * 4
-
-    def step():
-        codes = generate_static_batch(lm, pin_prompts, 100000, sargs, fixed_len=N)
-        st = lm.stats()
-        # synthetic-weight LMs emit codes >= 1000 that the FSQ table rejects (Q11): harness-side clamp
-        cl = [np.minimum(x, 999) for x in codes]
-        codec.decode_batch(cl, out=pcm_pin)
-        cs = codec.stats()
-        dev_ms = st["prefill_ms"] + st["decode_ms"] + cs["device_ms"]
-        return dev_ms, st, cs, sum(x.shape[1] for x in codes)
+    wl = Workload(a.config, lm, codec, rank, world, seed=1234 + rank)
 
     def barrier():
         if world > 1:
@@ -227,46 +311,34 @@ def run_ours(a):
         torch.cuda.synchronize()
 
     for _ in range(a.warmup):
-        step()
+        wl.step()
     sampler = ClockSampler(local)
     barrier()
     if rank == 0:
         sampler.start()
-    t0 = time.perf_counter()
-    dev_ms_tot, frames_tot, launches = 0.0, 0, 0
-    lm_pre, lm_dec, voc = 0.0, 0.0, 0.0
-    dom_ms, dom_n, dom_bytes = 0.0, 0, 0
-    for _ in range(a.steps):
-        dev_ms, st, cs, nf = step()
-        dev_ms_tot += dev_ms
-        frames_tot += nf
-        launches += st["kernel_launches"] + cs["kernel_launches"]
-        lm_pre += st["prefill_ms"]
-        lm_dec += st["decode_ms"]
-        voc += cs["device_ms"]
-        dom_ms += st["dominant_kernel_ms"]
-        dom_n += st["dominant_kernel_launches"]
-        dom_bytes += st["dominant_kernel_bytes"]
-    barrier()
-    wall = time.perf_counter() - t0
+    acc = time_workload(wl, a.steps, 0, barrier)
     clocks = sampler.stop() if rank == 0 else None
     wb = lm.stats()["weight_bytes_per_frame"]
+    dom_ms, dom_n, dom_bytes = acc["dom_ms"], acc["dom_n"], acc["dom_bytes"]
     if dom_n > 0:
-        dom_kernel = (("mega1_decode_kernel (single-row persistent frame loop: TMA weight ring + register-resident "
-                       "activations; GEMV phases + GQA attention + samplers" if B == 1 else
-                       "mega_decode_kernel (persistent frame loop: weight-streaming GEMV phases + GQA attention + samplers")
-                      + "; one launch per utterance batch, timed by CUDA events on its stream in the timed region)")
+        kname = ("megab_decode_kernel (wide-batch persistent frame loop: TMA weight ring -> tcgen05.mma with the batch rows as "
+                 "the N dimension, split-K fixups, GQA attention, per-row samplers" if wl.B > 8 else
+                 "mega1_decode_kernel (single-row persistent frame loop: TMA weight ring + register-resident activations; GEMV "
+                 "phases + GQA attention + samplers" if wl.B == 1 else
+                 "mega_decode_kernel (persistent frame loop: weight-streaming GEMV phases + GQA attention + samplers")
+        dom_kernel = kname + "; one launch per utterance batch, timed by CUDA events on its stream in the timed region)"
     else:
         # per-op decode path: one extra, untimed, profiled step with per-launch CUDA events around the GEMV
+        from fish_speech_rs_b200 import generate_static_batch
         lm.set_profile(True)
-        generate_static_batch(lm, pin_prompts, 100000, sargs, fixed_len=min(N, 12))
+        generate_static_batch(lm, wl.pin_prompts, 100000, wl.sargs, fixed_len=min(N, 12))
         pst = lm.stats()
         lm.set_profile(False)
         dom_ms, dom_n, dom_bytes = pst["dominant_kernel_ms"], pst["dominant_kernel_launches"], pst["dominant_kernel_bytes"]
         dom_kernel = "gemv_kernel (weight-streaming GEMV, fused rmsnorm/residual/swiglu; extra profiled step)"
 
-    t = torch.tensor([dev_ms_tot, wall * 1e3], dtype=torch.float64, device="cuda")
-    fr = torch.tensor([float(frames_tot), float(launches)], dtype=torch.float64, device="cuda")
+    t = torch.tensor([acc["dev"], acc["wall_ms"]], dtype=torch.float64, device="cuda")
+    fr = torch.tensor([float(acc["frames"]), float(acc["launches"])], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(fr, op=dist.ReduceOp.SUM)
@@ -278,28 +350,33 @@ def run_ours(a):
         e2e = frames_all / (wall_ms_max / 1e3)
         traffic, traffic_note = None, None
         try:
-            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_mega1_traffic.json" if B == 1 else "r01_mega_traffic.json")))
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r02_megab_traffic.json" if wl.B > 8 else
+                                             ("r01_mega1_traffic.json" if wl.B == 1 else "r01_mega_traffic.json"))))
             if dom_n > 0 and a.dtype == "bf16":
                 # DRAM bytes per frame from the committed ncu capture x frames in this launch
                 traffic = (tr["dram_bytes_read"] + tr["dram_bytes_write"]) / tr["frames_in_launch"] * N
-                traffic_note = "ncu dram bytes per frame (%s) x %d frames; below the algorithmic bytes: fast-stack weights partly L2-resident (lts hit %.0f%%)" % (tr["source"], N, tr["lts_hit_rate_pct"])
+                traffic_note = "ncu dram bytes per frame (%s) x %d frames" % (tr["source"], N)
         except Exception:
             pass
         n_l = max(dom_n, 1)
         avg_ms = dom_ms / n_l
         bytes_per_launch = dom_bytes / n_l
         achieved = bytes_per_launch / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
+        fpk, fpk_kind = fp32_peak()
+        voc_tf = VOCODER_FLOP_PER_FRAME * acc["frames"] / (acc["voc"] / 1e3) / 1e12 if acc["voc"] > 0 else 0.0
+        steps = a.steps
         out = {
-            "metric": "codec_tokens_per_sec", "value": value, "unit": "frames/s", "n_gpus": world, "steps": a.steps,
-            "warmup": a.warmup, "ms_per_step": dev_ms_max / a.steps, "higher_is_better": True, "scaling": "weak",
+            "metric": "codec_tokens_per_sec", "value": value, "unit": "frames/s", "n_gpus": world, "steps": steps,
+            "warmup": a.warmup, "ms_per_step": dev_ms_max / steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": a.dtype, "data": "synthetic",
-            "config": {"workload": a.config, "desc": c["desc"], "utterances_per_gpu": B, "frames": N,
-                       "weights": "seeded random init, Fish 1.5 shapes", "codec_dtype": "f32",
+            "config": {"workload": a.config, "desc": c["desc"], "utterances_per_gpu": wl.B, "utterances_total": c["batch"] * world,
+                       "frames": N, "sharding": "fish_speech_rs_b200.shard.assign (length-balanced static partition, no collective)",
+                       "weights": "seeded random init, Fish %s shapes" % c["version"], "codec_dtype": "f32",
                        "l2": "no flush: per-frame weight stream (%.0f MB) >> 126 MB L2" % (wb / 1e6)},
             "audio_samples_per_sec": value * 2048, "rtf": value / FRAME_RATE,
-            "breakdown_ms_per_step": {"lm_prefill": lm_pre / a.steps, "lm_decode": lm_dec / a.steps,
-                                      "vocoder": voc / a.steps},
-            "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+            "breakdown_ms_per_step": {"lm_prefill": acc["pre"] / steps, "lm_decode": acc["dec"] / steps,
+                                      "vocoder": acc["voc"] / steps, "encoder": acc["enc"] / steps},
+            "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": wl.h2d, "d2h_bytes_per_step": wl.d2h,
                     "audio_samples_per_sec": e2e * 2048, "rtf": e2e / FRAME_RATE},
             "gpu_launches": int(launches_all),
             "roofline": {"bound": "hbm", "kernel": dom_kernel,
@@ -308,9 +385,15 @@ def run_ours(a):
                          "launches_timed": int(dom_n),
                          "avg_launch_us": avg_ms * 1e3, "algorithmic_bytes_per_launch": bytes_per_launch,
                          "frame_bytes": wb,
-                         "frame_level_frac": (wb * (N - 1) * a.steps / (lm_dec / 1e3) / 1e9) / peaks["hbm_gbs"]},
+                         "frame_level_frac": (wb * (N - 1) * steps / (acc["dec"] / 1e3) / 1e9) / peaks["hbm_gbs"]},
+            "vocoder_roofline": {"bound": "fp32", "kernel": "conv1d_kernel family (Firefly decoder: FP32 FMA implicit GEMM)",
+                                 "achieved": voc_tf, "peak": fpk, "peak_kind": fpk_kind, "unit": "TFLOP/s",
+                                 "frac": voc_tf / fpk, "flop_per_frame": VOCODER_FLOP_PER_FRAME},
             "clocks": clocks,
         }
+        for x in extras:  # short secondary blocks on the same handles (not the headline)
+            w2 = Workload(x, lm, codec, 0, 1, seed=1234)
+            out["latency_b1" if x == "cfg2" else x] = secondary_block(w2, 2 if x == "cfg2" else 1, 1, barrier)
         if a.cpu_baseline:
             threads = os.cpu_count() or 1
             v, desc = cpu_reference_sample(a.config, lm_w, codec_w, a.cpu_sample_frames, threads)
@@ -326,10 +409,12 @@ def run_ours(a):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS))
+    ap.add_argument("--config", default="cfg5", choices=sorted(CONFIGS))
+    ap.add_argument("--no-extras", dest="extras", action="store_false",
+                    help="skip the secondary cfg3 / latency_b1 blocks of the default N=1 run")
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     ap.add_argument("--cpu-sample-frames", type=int, default=16)

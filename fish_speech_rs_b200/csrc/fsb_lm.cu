@@ -616,8 +616,8 @@ static int mega_setup(fsb_lm *lm) {
     }
     FSB_TRY(dev_alloc(lm, &lm->mega_bar, 4));  // [0] grid barrier, [1] frames confirmed (single-row kernel)
     if (getenv("FSB_MEGA_TIMERS")) {
-        FSB_TRY(dev_alloc(lm, &lm->mega_dbg, 128));
-        FSB_CUDA_OK(cudaMemset(lm->mega_dbg, 0, 128 * sizeof(unsigned long long)));
+        FSB_TRY(dev_alloc(lm, &lm->mega_dbg, 256));
+        FSB_CUDA_OK(cudaMemset(lm->mega_dbg, 0, 256 * sizeof(unsigned long long)));
     }
     MegaParams &m = lm->mp;
     memset(&m, 0, sizeof(m));
@@ -738,7 +738,7 @@ static int megab_launch_rows(fsb_lm *lm, int nb, int nframes) {
     const size_t cnt_words = (size_t)6 * kMBCntStride + 2 * 32 + 4;
     FSB_CUDA_OK(cudaMemsetAsync(lm->mega_bar, 0, 4 * sizeof(unsigned int), lm->stream));
     FSB_CUDA_OK(cudaMemsetAsync(lm->mbx.cnt, 0, cnt_words * sizeof(unsigned), lm->stream));
-    const int npad = lm->megab_rows_cap <= 16 ? 16 : 32;
+    const int npad = nb <= 16 ? 16 : 32;  // the workspace is sized for the capacity; the tile width follows the batch
     FSB_CUDA_OK(megab_launch(mp, lm->mbx, npad, lm->mega_grid, megab_smem_bytes(lm->mbx.nstages), lm->stream));
     lm->launches++;
     return FSB_OK;
@@ -1128,10 +1128,17 @@ static int generate_impl(fsb_lm *lm, const uint32_t *const *prompts, const int32
     lm->stats.dominant_kernel_launches = 0;
     lm->stats.dominant_kernel_bytes = 0;
     if (use_mega && lm->mega_dbg) {
-        unsigned long long h[128];
+        unsigned long long h[256];
         FSB_CUDA_OK(cudaMemcpy(h, lm->mega_dbg, sizeof(h), cudaMemcpyDeviceToHost));
         FSB_CUDA_OK(cudaMemset(lm->mega_dbg, 0, sizeof(h)));
         static const char *kn[7] = {"qkv", "attn", "wo", "w13", "w2", "head", "sample"};
+        for (int k = 0; k < 7; ++k) {  // wide-batch kernel: sub-steps of a projection phase on CTA 0
+            const unsigned long long *u = h + 128 + k * 8;
+            if (u[5])
+                fprintf(stderr, "[megab cta 0] %-6s n=%6llu stage %5.2f  acc-wait %5.2f  drain+arrive %5.2f  group-wait %5.2f  fixup %5.2f us/phase\n",
+                        kn[k], u[5], u[0] / 1965.0 / u[5], u[1] / 1965.0 / u[5], u[2] / 1965.0 / u[5], u[3] / 1965.0 / u[5],
+                        u[4] / 1965.0 / u[5]);
+        }
         if (h[103])
             fprintf(stderr, "[sample_fast] rep-pen %.2f  logits %.2f  block_sample %.2f us (n=%llu)\n", h[100] / 1965.0 / h[103],
                     h[101] / 1965.0 / h[103], h[102] / 1965.0 / h[103], h[103]);

@@ -122,9 +122,13 @@ template <int NPAD>
 struct MegaB {
     static constexpr int kD = 1024, kHd = 64, kH = 16, kKV = 2, kRep = 8, kI = 4096, kC = 8, kCS = 1024, kQKV = 1280;
     static constexpr int kKs = 256;                   // K slice of a work unit
-    static constexpr int kXTile = NPAD * 128;         // bytes of one (term, k-block) tile of the activation operand
-    static constexpr int kTmemCols = 2 * NPAD;        // two accumulator buffers
-    static_assert(3 * 4 * kXTile <= kMBXsBytes, "activation operand does not fit");
+    // activation operand of one 64-wide k-block: [3 * NPAD rows][64 k] -- rows [0, NPAD) hold the hi terms of the batch
+    // rows, [NPAD, 2 NPAD) the mid terms, [2 NPAD, 3 NPAD) the lo terms, so ONE MMA of N = 3 * NPAD multiplies a weight
+    // tile with all three terms; the three column groups of the accumulator are added when it is drained
+    static constexpr int kXKb = 3 * NPAD * 128;       // bytes per k-block
+    static constexpr int kAccCols = 3 * NPAD;         // accumulator columns of one buffer
+    static constexpr int kTmemCols = NPAD == 16 ? 128 : 256;  // two buffers, power of two
+    static_assert(4 * kXKb <= kMBXsBytes, "activation operand does not fit");
     static_assert(2 * kMBChunk * kMBKvStride * 4 <= kMBXsBytes, "K/V staging does not fit");
 
     enum { K_QKV = 0, K_ATT = 1, K_WO = 2, K_W13 = 3, K_W2 = 4, K_HEAD = 5, K_SAMPLE = 6, K_END = 7 };
@@ -274,7 +278,7 @@ struct MegaB {
         Step s = first_step();
         if (s.kind == K_ATT || s.kind == K_SAMPLE) s = next_weight_step(s);
         const int depth = e.nstages;
-        unsigned int issued = 0;
+        unsigned int slot = 0, epar = 1;  // parity of the `empty` phase to wait for (first lap: passes immediately)
         while (s.kind != K_END) {
             // frames beyond the last confirmed one are not streamed (no bulk copy may be in flight at exit)
             if (s.frame >= *go_frames) {
@@ -290,8 +294,7 @@ struct MegaB {
             for (int i = 0; i < u.n; ++i) {
                 const int row = tile_row(s, u.j + i * u.ns);
                 for (int kb = 0; kb < kKs / 64; ++kb) {
-                    const unsigned slot = issued % depth, use = issued / depth;
-                    if (use > 0) mb_wait(empty + slot, (use - 1) & 1);
+                    mb_wait(empty + slot, epar);  // a fresh mbarrier reports the phase before its first one as complete
                     m1_mbar_expect_tx(full + slot, kMBStage);
                     unsigned char *dst = ring + (size_t)slot * kMBStage;
                     const int k0 = u.s * kKs + kb * 64;
@@ -301,20 +304,34 @@ struct MegaB {
                     } else {
                         mb_tma_2d(dst, e.maps + g.map0, full + slot, k0, row);
                     }
-                    ++issued;
+                    if (++slot == (unsigned)depth) { slot = 0; epar ^= 1; }
                 }
             }
             s = next_weight_step(s);
         }
     }
 
-    // ------------------------------------------------------------ MMA issuer (warp 9, lane 0)
+    // ------------------------------------------------------------ MMA issuer (warp 9, converged; one elected lane issues)
+    static __device__ __forceinline__ bool elect_one() {
+        uint32_t pred;
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "elect.sync _|p, 0xffffffff;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}\n"
+            : "=r"(pred));
+        return pred != 0;
+    }
     __device__ __forceinline__ void mma_loop() {
         const uint32_t tmem_base = *tmem_slot;
-        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NPAD >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kAccCols >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
         const int depth = e.nstages;
-        unsigned int consumed = 0, units = 0, xphase = 0;
-        const uint32_t xs_addr = m1_smem_u32(xs);
+        unsigned int slot = 0, spar = 0, units = 0, xphase = 0;  // ring slot / parity advance without divisions
+        // descriptors differ only in the 14-bit start-address field (bytes >> 4): base + constant offsets
+        const uint64_t desc_hi = ((uint64_t)((1024 >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+        const uint64_t b_base = desc_hi | (uint64_t)((m1_smem_u32(xs) >> 4) & 0x3FFF);
+        const uint64_t a_base = desc_hi | (uint64_t)((m1_smem_u32(ring) >> 4) & 0x3FFF);
         for (;;) {
             mb_wait(x_ready, xphase & 1);
             ++xphase;
@@ -327,24 +344,22 @@ struct MegaB {
                     mb_wait(acc_empty + buf, (use - 1) & 1);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 }
-                const uint32_t acc = tmem_base + buf * NPAD;
+                const uint32_t acc = tmem_base + buf * kAccCols;
+#pragma unroll
                 for (int kb = 0; kb < kKs / 64; ++kb) {
-                    const unsigned slot = consumed % depth;
-                    mb_wait(full + slot, (consumed / depth) & 1);
+                    mb_wait(full + slot, spar);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t a_addr = m1_smem_u32(ring + (size_t)slot * kMBStage);
+                    if (elect_one()) {
+                        const uint64_t ad = a_base + (uint64_t)(slot * (kMBStage >> 4));
+                        const uint64_t bd = b_base + (uint64_t)(kb * (kXKb >> 4));
 #pragma unroll
-                    for (int term = 0; term < 3; ++term) {
-                        const uint32_t b_addr = xs_addr + (uint32_t)((term * 4 + kb) * kXTile);
-#pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            mb_umma(acc, mb_desc_sw128(a_addr + k * 32), mb_desc_sw128(b_addr + k * 32), idesc,
-                                    (kb | term | k) != 0 ? 1u : 0u);
+                        for (int k = 0; k < 4; ++k) mb_umma(acc, ad + 2 * k, bd + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                        mb_commit(empty + slot);  // frees the ring stage once these MMAs have read it
+                        if (kb == kKs / 64 - 1) mb_commit(acc_full + buf);
                     }
-                    mb_commit(empty + slot);  // frees the ring stage once these MMAs have read it
-                    ++consumed;
+                    __syncwarp();
+                    if (++slot == (unsigned)depth) { slot = 0; spar ^= 1; }
                 }
-                mb_commit(acc_full + buf);
                 ++units;
             }
         }
@@ -372,8 +387,8 @@ struct MegaB {
 
     // ------------------------------------------------------------ activation operand
     // rows [0, nb) x columns [k0, k0 + 256) of a row-major fp32 activation (leading dimension ld) -> three bf16
-    // terms in the UMMA K-major layout: tile (term, kb) = [NPAD rows][64 k] with 128-byte rows, 16-byte chunk c of
-    // row r stored at chunk c ^ (r & 7) (the 128-byte swizzle TMA would produce).  Rows >= nb are zero.
+    // terms in the UMMA K-major layout: k-block kb = [3 NPAD rows][64 k] with 128-byte rows (hi | mid | lo row groups),
+    // 16-byte chunk c of row r stored at chunk c ^ (r & 7) (the 128-byte swizzle TMA would produce).  Rows >= nb are zero.
     __device__ __forceinline__ void stage_x(const float *src, int ld, bool with_norm) {
         const int c32 = tid & 31;           // 16-byte chunk (8 columns) of the 256-column slice
         const int kb = c32 >> 3, c = c32 & 7;
@@ -396,14 +411,14 @@ struct MegaB {
             unsigned short h[8], m[8], l[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) mb_split3(v[j], h[j], m[j], l[j]);
-            const uint32_t off = (uint32_t)(kb * kXTile + b * 128 + ((c ^ (b & 7)) << 4));
+            const uint32_t off = (uint32_t)(kb * kXKb + b * 128 + ((c ^ (b & 7)) << 4));
             auto pack = [](const unsigned short (&q)[8]) {
                 return make_uint4((uint32_t)q[0] | ((uint32_t)q[1] << 16), (uint32_t)q[2] | ((uint32_t)q[3] << 16),
                                   (uint32_t)q[4] | ((uint32_t)q[5] << 16), (uint32_t)q[6] | ((uint32_t)q[7] << 16));
             };
             *reinterpret_cast<uint4 *>(xs + off) = pack(h);
-            *reinterpret_cast<uint4 *>(xs + 4 * kXTile + off) = pack(m);
-            *reinterpret_cast<uint4 *>(xs + 8 * kXTile + off) = pack(l);
+            *reinterpret_cast<uint4 *>(xs + NPAD * 128 + off) = pack(m);
+            *reinterpret_cast<uint4 *>(xs + 2 * NPAD * 128 + off) = pack(l);
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> tensor-core (async proxy) reads
     }
@@ -452,6 +467,9 @@ struct MegaB {
         float *ssq = slow ? e.ssq_x : e.ssq_fx;
         const bool with_norm = kind == K_QKV || kind == K_W13 || kind == K_HEAD;
         const int epoch = ++epoch_reg[g.gk];
+        const bool tm = p.dbg != nullptr && tid == 0 && blockIdx.x == 0 && u.n > 0;
+        unsigned long long *td = p.dbg + 128 + kind * 8;
+        long long c0 = tm ? clock64() : 0, c1 = 0;
         if (u.n > 0) {
             const float *src = kind == K_WO ? e.att : kind == K_W2 ? p.h : stream;
             stage_x(src + u.s * kKs, kind == K_W2 ? kI : kD, with_norm);
@@ -460,6 +478,7 @@ struct MegaB {
                 *cmd = u.n;
                 m1_mbar_arrive(x_ready);
             }
+            if (tm) { c1 = clock64(); td[0] += c1 - c0; c0 = c1; }
             // 1 / sqrt(mean(x^2) + eps) of every row (candle_nn::RmsNorm), from the partial sums the producer of x left
             if (with_norm && tid < p.nb) {
                 const float4 *q4 = reinterpret_cast<const float4 *>(ssq + (size_t)tid * kMBSsq);
@@ -479,27 +498,37 @@ struct MegaB {
             const unsigned buf = ucount & 1, use = ucount >> 1;
             mb_wait(acc_full + buf, use & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const int qd = warp & 3, c0 = (warp >> 2) * (NPAD / 2);
-            uint32_t r[16];
-            const uint32_t taddr = tmem_base + buf * NPAD + ((uint32_t)(qd * 32) << 16) + (uint32_t)c0;
-            if (NPAD == 32) mb_tmem_ld16(taddr, r);
-            else mb_tmem_ld8(taddr, r);
+            if (tm) { c1 = clock64(); td[1] += c1 - c0; c0 = c1; }
+            const int qd = warp & 3, cc0 = (warp >> 2) * (NPAD / 2);
+            float r[NPAD / 2];
+#pragma unroll
+            for (int term = 0; term < 3; ++term) {
+                uint32_t q[16];
+                const uint32_t taddr = tmem_base + buf * kAccCols + term * NPAD + ((uint32_t)(qd * 32) << 16) + (uint32_t)cc0;
+                if (NPAD == 32) mb_tmem_ld16(taddr, q);
+                else mb_tmem_ld8(taddr, q);
+#pragma unroll
+                for (int j = 0; j < NPAD / 2; ++j) r[j] = term == 0 ? __uint_as_float(q[j]) : r[j] + __uint_as_float(q[j]);
+            }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             m1_mbar_arrive(acc_empty + buf);
-            float *dst = e.ws + (((size_t)t * g.S + u.s) * NPAD + c0) * 128 + qd * 32 + lane;
+            float *dst = e.ws + (((size_t)t * g.S + u.s) * NPAD + cc0) * 128 + qd * 32 + lane;
 #pragma unroll
             for (int j = 0; j < NPAD / 2; ++j)
-                if (c0 + j < p.nb) dst[j * 128] = __uint_as_float(r[j]);
+                if (cc0 + j < p.nb) dst[j * 128] = r[j];
             ++ucount;
             wsync();
             if (tid == 0) mb_red_release(e.cnt + g.gk * kMBCntStride + t, 1u);
+            if (tm) { c1 = clock64(); td[2] += c1 - c0; c0 = c1; }
         }
         // ---- split-K fixup: the CTA of slice s reduces batch rows [b_lo, b_hi) of each of its tiles
         const int per = (p.nb + g.S - 1) / g.S;
         const int b_lo = u.s * per, b_hi = min(p.nb, b_lo + per);
+        if (tm) td[5] += 1;
         if (b_lo >= b_hi) return;
         for (int i = 0; i < u.n; ++i) {
             const int t = u.j + i * u.ns;
+            if (tm) c0 = clock64();
             if (tid == 0) {
                 const unsigned want = (unsigned)(g.S * epoch);
                 const unsigned *c = e.cnt + g.gk * kMBCntStride + t;
@@ -510,6 +539,7 @@ struct MegaB {
                 }
             }
             wsync();
+            if (tm) { c1 = clock64(); td[3] += c1 - c0; c0 = c1; }
             const float *wt = e.ws + (size_t)t * g.S * NPAD * 128;
             if (kind == K_WO || kind == K_W2) {
                 // residual add (dual_ar.rs:436-440) + this tile's share of sum(x^2) for the next RMSNorm
@@ -567,6 +597,7 @@ struct MegaB {
                 for (int b = b_lo + (tid >> 7); b < b_hi; b += 2)
                     if (ok) p.logits[(size_t)b * p.ldl + r] = psum(wt, g.S, b, ln) * invd[b];
             }
+            if (tm) td[4] += clock64() - c0;
         }
     }
     int epoch_reg[G_COUNT];
@@ -1052,7 +1083,7 @@ megab_decode_kernel(const __grid_constant__ MegaParams p, const __grid_constant_
     if (!idle) {
         if (warp < 8) m.run();
         else if (warp == 8) { if ((threadIdx.x & 31) == 0) m.producer(); }
-        else if ((threadIdx.x & 31) == 0) m.mma_loop();
+        else m.mma_loop();  // whole warp, converged: an elected lane issues
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
