@@ -89,8 +89,8 @@ struct MegaParams {
 constexpr int kMBWorkers = 256;               // worker threads (warps 0-7, named barrier 1)
 constexpr int kMBThreads = kMBWorkers + 64;   // + TMA producer warp + MMA warp
 constexpr int kMBStage = 16384;               // one ring stage: 128 rows x 64 k bf16
-constexpr int kMBXsBytes = 49152;             // activation operand | K/V staging | sampler scratch
-constexpr int kMBMaxStages = 10;
+constexpr int kMBXsBytes = 81920;             // activation operand | two K/V chunk buffers | sampler scratch
+constexpr int kMBMaxStages = 8;
 constexpr int kMBChunk = 64;                  // cached positions staged at once
 constexpr int kMBKvStride = 80;               // floats per staged K/V row
 constexpr int kMBMaxSplit = 16;               // position ranges per (row, kv head)

@@ -129,7 +129,7 @@ struct MegaB {
     static constexpr int kAccCols = 3 * NPAD;         // accumulator columns of one buffer
     static constexpr int kTmemCols = NPAD == 16 ? 128 : 256;  // two buffers, power of two
     static_assert(4 * kXKb <= kMBXsBytes, "activation operand does not fit");
-    static_assert(2 * kMBChunk * kMBKvStride * 4 <= kMBXsBytes, "K/V staging does not fit");
+    static_assert(2 * 2 * kMBChunk * kMBKvStride * 4 <= kMBXsBytes, "two K/V chunk buffers do not fit");
 
     enum { K_QKV = 0, K_ATT = 1, K_WO = 2, K_W13 = 3, K_W2 = 4, K_HEAD = 5, K_SAMPLE = 6, K_END = 7 };
     enum { G_QKV = 0, G_WO = 1, G_W13 = 2, G_W2 = 3, G_HEAD_S = 4, G_HEAD_F = 5, G_COUNT = 6 };
@@ -609,29 +609,46 @@ struct MegaB {
                                               int j0, int j1, float &m, float &l, float (&o)[16]) {
         const int g = lane >> 2, sub = lane & 3;
         const int h = kvh * kRep + warp;
-        float *ks = reinterpret_cast<float *>(xs), *vs = ks + kMBChunk * kMBKvStride;
+        constexpr int kBuf = 2 * kMBChunk * kMBKvStride;  // floats of one chunk buffer (K rows then V rows)
+        float *kvb = reinterpret_cast<float *>(xs);
         float4 qv[4];
         const float *qp = p.q + (size_t)b * kD + (size_t)h * kHd + sub * 4;
+        // 1 / sqrt(head_dim) is a power of two: scaling q instead of every K row (dual_ar.rs:258-260) is bit-identical
 #pragma unroll
-        for (int jj = 0; jj < 4; ++jj) qv[jj] = __ldcg(reinterpret_cast<const float4 *>(qp + jj * 16));
+        for (int jj = 0; jj < 4; ++jj) {
+            qv[jj] = __ldcg(reinterpret_cast<const float4 *>(qp + jj * 16));
+            qv[jj].x *= 0.125f; qv[jj].y *= 0.125f; qv[jj].z *= 0.125f; qv[jj].w *= 0.125f;
+        }
         m = -INFINITY;
         l = 0.f;
 #pragma unroll
         for (int i = 0; i < 16; ++i) o[i] = 0.f;
-        const float scale = 0.125f;  // 1 / sqrt(head_dim), applied to K first like the reference (dual_ar.rs:258-260)
         const float *kb = kcache + ((size_t)b * kKV + kvh) * cache_len * kHd;
         const float *vb = vcache + ((size_t)b * kKV + kvh) * cache_len * kHd;
-        for (int c0 = j0; c0 < j1; c0 += kMBChunk) {
+        auto stage = [&](int c0, int buf) {  // positions [c0, min(c0 + 64, j1)) -> chunk buffer `buf`
             const int n = min(kMBChunk, j1 - c0);
-            wsync();  // the previous chunk's reads are done
+            float *ks = kvb + buf * kBuf, *vs = ks + kMBChunk * kMBKvStride;
             for (int i = tid; i < n * 16; i += kMBWorkers) {
                 const int j = i >> 4, sg = i & 15;
                 cp_async16(ks + j * kMBKvStride + sg * 4, kb + (size_t)(c0 + j) * kHd + sg * 4);
                 cp_async16(vs + j * kMBKvStride + sg * 4, vb + (size_t)(c0 + j) * kHd + sg * 4);
             }
             cp_async_commit();
-            cp_async_wait_all();
+        };
+        wsync();  // both buffers are free (previous item / previous user of the region)
+        stage(j0, 0);
+        int buf = 0;
+        for (int c0 = j0; c0 < j1; c0 += kMBChunk, buf ^= 1) {
+            const int n = min(kMBChunk, j1 - c0);
+            // the next chunk streams in while this one is consumed
+            if (c0 + kMBChunk < j1) {
+                stage(c0 + kMBChunk, buf ^ 1);
+                asm volatile("cp.async.wait_group 1;" ::: "memory");
+            } else {
+                cp_async_wait_all();
+            }
             wsync();
+            const float *ks = kvb + buf * kBuf, *vs = ks + kMBChunk * kMBKvStride;
             for (int jb = 0; jb < n; jb += 8) {  // warp-uniform trip count (the shuffles need all lanes)
                 const int j = jb + g;
                 const bool valid = j < n;
@@ -641,10 +658,10 @@ struct MegaB {
 #pragma unroll
                 for (int jj = 0; jj < 4; ++jj) {
                     const float4 kk = *reinterpret_cast<const float4 *>(kr + jj * 16);
-                    dot = fmaf(qv[jj].x, kk.x * scale, dot);
-                    dot = fmaf(qv[jj].y, kk.y * scale, dot);
-                    dot = fmaf(qv[jj].z, kk.z * scale, dot);
-                    dot = fmaf(qv[jj].w, kk.w * scale, dot);
+                    dot = fmaf(qv[jj].x, kk.x, dot);
+                    dot = fmaf(qv[jj].y, kk.y, dot);
+                    dot = fmaf(qv[jj].z, kk.z, dot);
+                    dot = fmaf(qv[jj].w, kk.w, dot);
                 }
                 dot += __shfl_xor_sync(0xffffffffu, dot, 1);
                 dot += __shfl_xor_sync(0xffffffffu, dot, 2);
@@ -664,6 +681,7 @@ struct MegaB {
                     m = m_new;
                 }
             }
+            wsync();  // this buffer is overwritten by the chunk after next
         }
         // merge the 8 position groups (lanes with equal `sub`)
 #pragma unroll
