@@ -682,7 +682,7 @@ static int tc_setup(fsb_lm *lm) {
 static bool megab_shapes_ok(const fsb_lm *lm) {
     return lm->mega_ok && lm->tc_ok && lm->wdt == FSB_BF16 && lm->D == 1024 && lm->I == 4096 && lm->H * lm->hd == 1024 &&
            lm->hd == 64 && lm->KV == 2 && lm->C == 8 && lm->fast_len == 8 && lm->CS == 1024 && lm->QKV == 1280 &&
-           lm->n_slow_logits <= (1 << kSelIdxBits) && lm->NL >= 1 && lm->NFL >= 1 && lm->mega_grid >= 64;
+           lm->n_slow_logits <= (1 << kSelIdxBits) && lm->NL >= 1 && lm->NFL >= 1 && lm->mega_grid >= 128;
 }
 static int megab_setup(fsb_lm *lm) {
     lm->megab_ok = false;
@@ -708,9 +708,9 @@ static int megab_setup(fsb_lm *lm) {
     const int B = std::min(lm->max_batch, 32);
     lm->megab_rows_cap = B;
     const int npad = B <= 16 ? 16 : 32;
-    FSB_TRY(dev_alloc(lm, &x.ws, (size_t)256 * npad * 128));  // W13: 64 tiles x 4 slices
-    FSB_TRY(dev_alloc(lm, &x.cnt, (size_t)6 * kMBCntStride + 2 * 32 + 4));
-    x.att_cnt = x.cnt + 6 * kMBCntStride;
+    FSB_TRY(dev_alloc(lm, &x.ws, (size_t)64 * npad * lm->D));  // fused FFN: 64 column blocks x NPAD rows x dim
+    FSB_TRY(dev_alloc(lm, &x.cnt, (size_t)2 * 32 + 4));
+    x.att_cnt = x.cnt;
     x.go = x.att_cnt + 2 * 32;
     FSB_TRY(dev_alloc(lm, &x.att, (size_t)B * lm->D));
     FSB_TRY(dev_alloc(lm, &x.apart, (size_t)B * lm->H * kMBMaxSplit * (lm->hd + 4)));
@@ -718,11 +718,9 @@ static int megab_setup(fsb_lm *lm) {
     FSB_TRY(dev_alloc(lm, &x.ssq_fx, (size_t)B * kMBSsq));
     x.head_tiles = (lm->n_slow_logits + 127) / 128;
     x.head_extra = lm->slow_row0 != lm->slow_rest_base - 1 ? 1 : 0;
-    int nst = kMBMaxStages;
-    while (nst > 4 && megab_smem_bytes(nst) > lm->smem_optin) --nst;
-    if (megab_smem_bytes(nst) > lm->smem_optin) return FSB_OK;
-    if (const char *v = getenv("FSB_MEGAB_STAGES")) nst = std::max(2, std::min(nst, atoi(v)));
-    x.nstages = nst;
+    if (megab_smem_bytes(32, megab_max_stages(32)) > lm->smem_optin || megab_smem_bytes(16, megab_max_stages(16)) > lm->smem_optin)
+        return FSB_OK;
+    x.nstages = 0;  // per launch (depends on the tile width)
     lm->megab_ok = true;
     return FSB_OK;
 }
@@ -735,11 +733,14 @@ static int megab_launch_rows(fsb_lm *lm, int nb, int nframes) {
     mp.first_is_tail = 1;
     mp.row0 = 0;
     mp.st = lm->h_st;
-    const size_t cnt_words = (size_t)6 * kMBCntStride + 2 * 32 + 4;
+    const size_t cnt_words = (size_t)2 * 32 + 4;
     FSB_CUDA_OK(cudaMemsetAsync(lm->mega_bar, 0, 4 * sizeof(unsigned int), lm->stream));
     FSB_CUDA_OK(cudaMemsetAsync(lm->mbx.cnt, 0, cnt_words * sizeof(unsigned), lm->stream));
     const int npad = nb <= 16 ? 16 : 32;  // the workspace is sized for the capacity; the tile width follows the batch
-    FSB_CUDA_OK(megab_launch(mp, lm->mbx, npad, lm->mega_grid, megab_smem_bytes(lm->mbx.nstages), lm->stream));
+    MegaBExtra ex = lm->mbx;
+    ex.nstages = megab_max_stages(npad);
+    if (const char *v = getenv("FSB_MEGAB_STAGES")) ex.nstages = std::max(2, std::min(ex.nstages, atoi(v)));
+    FSB_CUDA_OK(megab_launch(mp, ex, npad, lm->mega_grid, megab_smem_bytes(npad, ex.nstages), lm->stream));
     lm->launches++;
     return FSB_OK;
 }
@@ -1131,13 +1132,19 @@ static int generate_impl(fsb_lm *lm, const uint32_t *const *prompts, const int32
         unsigned long long h[256];
         FSB_CUDA_OK(cudaMemcpy(h, lm->mega_dbg, sizeof(h), cudaMemcpyDeviceToHost));
         FSB_CUDA_OK(cudaMemset(lm->mega_dbg, 0, sizeof(h)));
-        static const char *kn[7] = {"qkv", "attn", "wo", "w13", "w2", "head", "sample"};
-        for (int k = 0; k < 7; ++k) {  // wide-batch kernel: sub-steps of a projection phase on CTA 0
-            const unsigned long long *u = h + 128 + k * 8;
+        static const char *kn[7] = {"qkv", "attn", "wo", "w13|ffn", "w2|fred", "head", "sample"};
+        for (int k = 0; k < 7; ++k) {  // wide-batch kernel: sub-steps of a projection phase on its owner CTA
+            const unsigned long long *u = h + 192 + k * 8;
             if (u[5])
-                fprintf(stderr, "[megab cta 0] %-6s n=%6llu stage %5.2f  acc-wait %5.2f  drain+arrive %5.2f  group-wait %5.2f  fixup %5.2f us/phase\n",
+                fprintf(stderr, "[megab owner] %-7s n=%6llu stage %5.2f  acc-wait %5.2f  epilogue|swiglu %5.2f  acc2-wait %5.2f  epilogue2 %5.2f us/phase\n",
                         kn[k], u[5], u[0] / 1965.0 / u[5], u[1] / 1965.0 / u[5], u[2] / 1965.0 / u[5], u[3] / 1965.0 / u[5],
                         u[4] / 1965.0 / u[5]);
+        }
+        for (int k = 0; k < 7; ++k) {  // wide-batch kernel: third timed CTA (74: owns a WO tile)
+            const unsigned long long *e = h + 128 + k * 4;
+            if (e[3])
+                fprintf(stderr, "[mega cta 74] %-7s n=%6llu work %7.2f  barrier %7.2f us/phase\n", kn[k], e[3], e[0] / 1965.0 / e[3],
+                        e[2] / 1965.0 / e[3]);
         }
         if (h[103])
             fprintf(stderr, "[sample_fast] rep-pen %.2f  logits %.2f  block_sample %.2f us (n=%llu)\n", h[100] / 1965.0 / h[103],

@@ -89,7 +89,8 @@ struct MegaParams {
 constexpr int kMBWorkers = 256;               // worker threads (warps 0-7, named barrier 1)
 constexpr int kMBThreads = kMBWorkers + 64;   // + TMA producer warp + MMA warp
 constexpr int kMBStage = 16384;               // one ring stage: 128 rows x 64 k bf16
-constexpr int kMBXsBytes = 81920;             // activation operand | two K/V chunk buffers | sampler scratch
+constexpr int kMBXsBytes16 = 81920;           // NPAD 16: two activation slice buffers | two K/V chunk buffers | sampler scratch
+constexpr int kMBXsBytes32 = 98304;           // NPAD 32 (two 48 KB slice buffers)
 constexpr int kMBMaxStages = 8;
 constexpr int kMBChunk = 64;                  // cached positions staged at once
 constexpr int kMBKvStride = 80;               // floats per staged K/V row
@@ -100,8 +101,8 @@ constexpr long long kMBSpinLimit = 6000000000ll;  // ~3 s: a broken protocol tra
 
 struct MegaBExtra {
     const CUtensorMap *maps;  // 5 per layer (wqkv, wo, w1, w3, w2), slow then fast, then out_w, fast_out
-    float *ws;                // split-K partials [tile][slice][NPAD][128]
-    unsigned *cnt;            // [6][kMBCntStride] arrival counters (monotonic), then [B * KV] attention counters
+    float *ws;                // partial outputs of the fused FFN [64 blocks][NPAD][dim]
+    unsigned *cnt;            // scratch counters: [B * KV] attention arrival counters, "go" flags
     unsigned *att_cnt;
     unsigned *go;             // [4] "some row continues into frame f" flags
     float *att;               // (B, H * hd) attention output
@@ -122,6 +123,7 @@ cudaError_t mega1_launch_f32(const MegaParams &mp, int grid, size_t smem, cudaSt
 
 // wide-batch kernel; npad in {16, 32}
 cudaError_t megab_launch(const MegaParams &mp, const MegaBExtra &ex, int npad, int grid, size_t smem, cudaStream_t st);
-size_t megab_smem_bytes(int nstages);
+size_t megab_smem_bytes(int npad, int nstages);
+int megab_max_stages(int npad);
 
 }  // namespace fsb

@@ -14,10 +14,14 @@
 //   * warps 0-7 are workers: they stage the activation slice (fp32 from L2 -> x * g -> three bf16 terms hi + mid +
 //     lo = 24 mantissa bits, written straight into the UMMA K-major 128B-swizzle layout), drain TMEM, and run the
 //     fused epilogues, attention and the samplers;
-//   * a work unit is (128-row tile, 256-wide K slice): a CTA only ever stages a 256-column slice of the
-//     activations (B x 256 x 4 B from L2 instead of B x 1024), and the K-slices of a tile are summed in a FIXED
-//     order by a split-K fixup that is spread over the CTAs of the tile (each reduces its share of the batch rows
-//     after a per-tile arrival counter says all partials have landed) -- deterministic, no atomics on data;
+//   * no split-K on QKV / WO / heads: one CTA owns a 128-row weight tile and streams its full K; the activation
+//     arrives as four 256-column slices that alternate between two shared-memory operand buffers (the MMAs of
+//     slice s run while slice s + 1 is staged), and the epilogue runs straight out of TMEM (no partial buffers,
+//     no cross-CTA reduction, no second synchronisation per phase);
+//   * the feed-forward is ONE phase: CTA t owns 64 columns of the intermediate dimension, computes w1/w3 for them
+//     (one M = 128 tile: 64 w1 rows | 64 w3 rows), applies SwiGLU in shared memory, and multiplies the 64-wide h
+//     slice with its K-slice of w2 right away (8 more accumulators in TMEM); a short reduce phase sums the 64
+//     partial outputs in a fixed order (deterministic, no atomics on data), adds the residual and leaves sum(x^2);
 //   * RMSNorm is folded: the staged operand is x * g, sum(x^2) is produced by whoever writes x (residual fixups,
 //     embedding gathers) and 1 / sqrt(mean + eps) scales the reduced sums; RoPE + KV append, SwiGLU, residual adds
 //     and the constrained head are the fixups of their phases;
@@ -121,30 +125,34 @@ __device__ __forceinline__ void mb_split3(float v, unsigned short &hi, unsigned 
 template <int NPAD>
 struct MegaB {
     static constexpr int kD = 1024, kHd = 64, kH = 16, kKV = 2, kRep = 8, kI = 4096, kC = 8, kCS = 1024, kQKV = 1280;
-    static constexpr int kKs = 256;                   // K slice of a work unit
+    static constexpr int kKs = 256;                   // columns of one activation slice
     // activation operand of one 64-wide k-block: [3 * NPAD rows][64 k] -- rows [0, NPAD) hold the hi terms of the batch
     // rows, [NPAD, 2 NPAD) the mid terms, [2 NPAD, 3 NPAD) the lo terms, so ONE MMA of N = 3 * NPAD multiplies a weight
     // tile with all three terms; the three column groups of the accumulator are added when it is drained
     static constexpr int kXKb = 3 * NPAD * 128;       // bytes per k-block
-    static constexpr int kAccCols = 3 * NPAD;         // accumulator columns of one buffer
-    static constexpr int kTmemCols = NPAD == 16 ? 128 : 256;  // two buffers, power of two
-    static_assert(4 * kXKb <= kMBXsBytes, "activation operand does not fit");
-    static_assert(2 * 2 * kMBChunk * kMBKvStride * 4 <= kMBXsBytes, "two K/V chunk buffers do not fit");
+    static constexpr int kXBuf = 4 * kXKb;            // one slice buffer (4 k-blocks); two of them alternate
+    static constexpr int kAccCols = 3 * NPAD;         // accumulator columns of one term-stacked tile
+    // second GEMM of the fused FFN: 8 accumulators (one per 128 output columns).  NPAD 16: term-stacked (8 x 48 columns);
+    // NPAD 32: the three terms accumulate into the same 32 columns (8 x 96 would not fit the 512 TMEM columns)
+    static constexpr bool kStack2 = NPAD == 16;
+    static constexpr int kAcc2Cols = kStack2 ? kAccCols : NPAD;
+    static constexpr int kTmemCols = 512;
+    static constexpr int kXsBytes = NPAD == 16 ? kMBXsBytes16 : kMBXsBytes32;
+    static_assert(2 * kXBuf <= kXsBytes, "two activation slice buffers do not fit");
+    static_assert(2 * 2 * kMBChunk * kMBKvStride * 4 <= kXsBytes, "two K/V chunk buffers do not fit");
+    static_assert(kAccCols + 8 * kAcc2Cols <= kTmemCols, "TMEM columns");
 
-    enum { K_QKV = 0, K_ATT = 1, K_WO = 2, K_W13 = 3, K_W2 = 4, K_HEAD = 5, K_SAMPLE = 6, K_END = 7 };
-    enum { G_QKV = 0, G_WO = 1, G_W13 = 2, G_W2 = 3, G_HEAD_S = 4, G_HEAD_F = 5, G_COUNT = 6 };
+    enum { K_QKV = 0, K_ATT = 1, K_WO = 2, K_FFN = 3, K_FRED = 4, K_HEAD = 5, K_SAMPLE = 6, K_END = 7 };
     struct Step { int frame, pass, l, kind; };  // pass 0 = slow stack, pass c + 1 = fast step of codebook c
-    struct Gemm { int map0, map1, T, S, off, gk; };
-    struct Units { int s, j, ns, n; };
 
     const MegaParams &p;
     const MegaBExtra &e;
     // shared memory
     unsigned char *ring, *xs;
-    uint64_t *full, *empty, *x_ready, *acc_full, *acc_empty;
+    uint64_t *full, *empty, *cmd_ready, *xr, *xf, *acc_full, *hr, *a2f;
     uint32_t *tmem_slot;
     volatile int *cmd, *go_frames, *done_flag;
-    int *pos_s, *act_s, *ibase_s, *nsplit_s, *prange_s, *epoch_s, *bcast_s;
+    int *pos_s, *act_s, *ibase_s, *nsplit_s, *prange_s, *bcast_s;
     float *invd, *red;
     const float **normtab;
     int *s_active, *s_eos, *s_frame, *s_maxf;
@@ -152,18 +160,20 @@ struct MegaB {
     RepPenState *s_rep;
     int tid, lane, warp;
     unsigned int target;     // grid barrier
-    unsigned int ucount;     // units processed so far (accumulator buffer / parity)
-    float gpre[8];           // norm weights of the coming phase for this thread's 8 columns
+    unsigned int pacc, pa2f; // parities of acc_full / a2f (workers)
 
     __device__ MegaB(const MegaParams &pp, const MegaBExtra &ee, unsigned char *smem) : p(pp), e(ee) {
         ring = smem;
         xs = smem + (size_t)ee.nstages * kMBStage;
-        unsigned char *q = xs + kMBXsBytes;
+        unsigned char *q = xs + kXsBytes;
         full = reinterpret_cast<uint64_t *>(q); q += 8 * kMBMaxStages;
         empty = reinterpret_cast<uint64_t *>(q); q += 8 * kMBMaxStages;
-        x_ready = reinterpret_cast<uint64_t *>(q); q += 8;
-        acc_full = reinterpret_cast<uint64_t *>(q); q += 16;
-        acc_empty = reinterpret_cast<uint64_t *>(q); q += 16;
+        cmd_ready = reinterpret_cast<uint64_t *>(q); q += 8;
+        xr = reinterpret_cast<uint64_t *>(q); q += 16;
+        xf = reinterpret_cast<uint64_t *>(q); q += 16;
+        acc_full = reinterpret_cast<uint64_t *>(q); q += 8;
+        hr = reinterpret_cast<uint64_t *>(q); q += 8;
+        a2f = reinterpret_cast<uint64_t *>(q); q += 8;
         tmem_slot = reinterpret_cast<uint32_t *>(q); q += 8;
         cmd = reinterpret_cast<volatile int *>(q); q += 4;
         go_frames = reinterpret_cast<volatile int *>(q); q += 4;
@@ -173,7 +183,6 @@ struct MegaB {
         ibase_s = reinterpret_cast<int *>(q); q += 4 * 36;
         nsplit_s = reinterpret_cast<int *>(q); q += 4 * 32;
         prange_s = reinterpret_cast<int *>(q); q += 4 * 32;
-        epoch_s = reinterpret_cast<int *>(q); q += 4 * 8;
         bcast_s = reinterpret_cast<int *>(q); q += 4 * 8;
         invd = reinterpret_cast<float *>(q); q += 4 * 32;
         red = reinterpret_cast<float *>(q); q += 4 * 128;
@@ -189,12 +198,8 @@ struct MegaB {
         lane = tid & 31;
         warp = tid >> 5;
         target = 0;
-        ucount = 0;
-    }
-    static __host__ __device__ size_t smem_bytes(int nstages, int NL, int NFL) {
-        return (size_t)nstages * kMBStage + kMBXsBytes + 8 * kMBMaxStages * 2 + 8 + 16 + 16 + 8 + 4 + 4 + 8 +
-               4 * (32 + 32 + 36 + 32 + 32 + 8 + 8 + 32 + 128) + 8 * (2 * (NL + NFL) + 2) + 16 + 4 * 24 +
-               sizeof(RepPenState) * 8 + 1024 /* alignment slack */;
+        pacc = 0;
+        pa2f = 0;
     }
 
     static __device__ __forceinline__ void wsync() { MBSync::sync(); }
@@ -203,7 +208,7 @@ struct MegaB {
     __device__ __forceinline__ Step first_step() const {
         Step s;
         s.frame = 0; s.pass = 0; s.l = 0;
-        s.kind = (p.first_is_tail || p.NL == 0) ? K_HEAD : K_QKV;
+        s.kind = K_HEAD;  // the launch starts at the slow head of frame 0 (the hidden rows come from the prefill)
         return s;
     }
     __device__ __forceinline__ Step advance(const Step &s) const {
@@ -212,73 +217,90 @@ struct MegaB {
         switch (s.kind) {
             case K_QKV: n.kind = K_ATT; break;
             case K_ATT: n.kind = K_WO; break;
-            case K_WO: n.kind = K_W13; break;
-            case K_W13: n.kind = K_W2; break;
-            case K_W2:
+            case K_WO: n.kind = K_FFN; break;
+            case K_FFN: n.kind = K_FRED; break;
+            case K_FRED:
                 if (s.l + 1 < (slow ? p.NL : p.NFL)) { n.l = s.l + 1; n.kind = K_QKV; }
                 else n.kind = K_HEAD;
                 break;
             case K_HEAD: n.kind = K_SAMPLE; break;
             default:  // K_SAMPLE
                 n.l = 0;
-                if (s.pass < kC) { n.pass = s.pass + 1; n.kind = p.NFL > 0 ? K_QKV : K_HEAD; }
+                if (s.pass < kC) { n.pass = s.pass + 1; n.kind = K_QKV; }
                 else {
                     n.pass = 0;
                     n.frame = s.frame + 1;
-                    n.kind = n.frame < p.nframes ? (p.NL > 0 ? K_QKV : K_HEAD) : K_END;
+                    n.kind = n.frame < p.nframes ? K_QKV : K_END;
                 }
         }
         return n;
     }
     __device__ __forceinline__ Step next_weight_step(Step s) const {
-        do { s = advance(s); } while (s.kind == K_ATT || s.kind == K_SAMPLE);
+        do { s = advance(s); } while (s.kind == K_ATT || s.kind == K_SAMPLE || s.kind == K_FRED);
         return s;
     }
-    __device__ __forceinline__ Gemm gemm_of(const Step &s) const {
-        Gemm g;
-        const bool slow = s.pass == 0;
+    // The 128-row weight tile this CTA owns in a projection phase (-1: none).  No split-K: the owner streams the
+    // tile's full K.  Disjoint CTA ranges per phase kind, so a CTA's share of the weight stream stays even over a layer:
+    // FFN column blocks on CTAs [0, 64), QKV tiles on [64, 74), WO tiles on [74, 82), head tiles from 82.
+    __device__ __forceinline__ int unit_of(const Step &s) const {
         const int G = (int)gridDim.x;
-        const int lb = 5 * (slow ? s.l : p.NL + s.l);
-        g.map1 = -1;
-        g.S = 4;
-        g.off = 0;
+        int T, off;
         switch (s.kind) {
-            case K_QKV: g.map0 = lb; g.T = kQKV / 128; g.gk = G_QKV; g.off = G > 40 ? G - 40 : 0; break;
-            case K_WO: g.map0 = lb + 1; g.T = kD / 128; g.gk = G_WO; g.off = G > 20 ? G - 20 : 0; break;
-            case K_W13: g.map0 = lb + 2; g.map1 = lb + 3; g.T = kI / 64; g.gk = G_W13; break;
-            case K_W2: g.map0 = lb + 4; g.T = kD / 128; g.S = kI / kKs; g.gk = G_W2; break;
-            default:
-                g.map0 = 5 * (p.NL + p.NFL) + (slow ? 0 : 1);
-                g.T = slow ? e.head_tiles + e.head_extra : kCS / 128;
-                g.gk = slow ? G_HEAD_S : G_HEAD_F;
+            case K_QKV: T = kQKV / 128; off = 64; break;
+            case K_WO: T = kD / 128; off = 74; break;
+            case K_FFN: T = kI / 64; off = 0; break;
+            case K_HEAD: T = s.pass == 0 ? e.head_tiles + e.head_extra : kCS / 128; off = 82; break;
+            default: return -1;
         }
-        return g;
-    }
-    // units of this CTA: all of one K slice s, tiles j, j + ns, ... < T
-    __device__ __forceinline__ Units units_of(const Gemm &g) const {
-        Units u;
-        const int G = (int)gridDim.x;
-        int v = (int)blockIdx.x - g.off;
+        int v = (int)blockIdx.x - (off % G);
         if (v < 0) v += G;
-        u.s = v % g.S;
-        u.j = v / g.S;
-        u.ns = (G - u.s + g.S - 1) / g.S;
-        u.n = u.j < g.T ? (g.T - 1 - u.j) / u.ns + 1 : 0;
-        return u;
+        return v < T ? v : -1;
+    }
+    __device__ __forceinline__ int map_of(const Step &s) const {
+        const int lb = 5 * (s.pass == 0 ? s.l : p.NL + s.l);
+        switch (s.kind) {
+            case K_QKV: return lb;
+            case K_WO: return lb + 1;
+            case K_FFN: return lb + 2;  // w1; w3 = +1, w2 = +2
+            default: return 5 * (p.NL + p.NFL) + (s.pass == 0 ? 0 : 1);
+        }
     }
     // first weight row of tile t (TMA coordinate)
     __device__ __forceinline__ int tile_row(const Step &s, int t) const {
-        if (s.kind == K_W13) return 64 * t;
         if (s.kind == K_HEAD && s.pass == 0) return t < e.head_tiles ? p.slow_rest_base - 1 + 128 * t : p.slow_row0;
         return 128 * t;
     }
 
     // ------------------------------------------------------------ TMA producer (warp 8, lane 0)
+    static __device__ __forceinline__ void tma_prefetch_l2(const CUtensorMap *map, int c0, int c1) {
+        asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
+    }
+    __device__ __forceinline__ void prefetch_unit(const Step &s) const {
+        const int t = unit_of(s);
+        const CUtensorMap *m0 = e.maps + map_of(s);
+        if (s.kind == K_FFN) {
+            for (int kb = 0; kb < kD / 64; ++kb) {
+                tma_prefetch_l2(m0, kb * 64, 64 * t);
+                tma_prefetch_l2(m0 + 1, kb * 64, 64 * t);
+            }
+            for (int r = 0; r < kD / 128; ++r) tma_prefetch_l2(m0 + 2, 64 * t, 128 * r);
+        } else {
+            const int row = tile_row(s, t);
+            for (int kb = 0; kb < kD / 64; ++kb) tma_prefetch_l2(m0, kb * 64, row);
+        }
+    }
     __device__ __forceinline__ void producer() {
         Step s = first_step();
-        if (s.kind == K_ATT || s.kind == K_SAMPLE) s = next_weight_step(s);
         const int depth = e.nstages;
         unsigned int slot = 0, epar = 1;  // parity of the `empty` phase to wait for (first lap: passes immediately)
+        auto next_slot = [&]() {
+            mb_wait(empty + slot, epar);  // a fresh mbarrier reports the phase before its first one as complete
+            m1_mbar_expect_tx(full + slot, kMBStage);
+            return ring + (size_t)slot * kMBStage;
+        };
+        auto advance_slot = [&]() {
+            if (++slot == (unsigned)depth) { slot = 0; epar ^= 1; }
+        };
         while (s.kind != K_END) {
             // frames beyond the last confirmed one are not streamed (no bulk copy may be in flight at exit)
             if (s.frame >= *go_frames) {
@@ -289,22 +311,37 @@ struct MegaB {
                     if (clock64() - t0 > kMBSpinLimit) __trap();
                 }
             }
-            const Gemm g = gemm_of(s);
-            const Units u = units_of(g);
-            for (int i = 0; i < u.n; ++i) {
-                const int row = tile_row(s, u.j + i * u.ns);
-                for (int kb = 0; kb < kKs / 64; ++kb) {
-                    mb_wait(empty + slot, epar);  // a fresh mbarrier reports the phase before its first one as complete
-                    m1_mbar_expect_tx(full + slot, kMBStage);
-                    unsigned char *dst = ring + (size_t)slot * kMBStage;
-                    const int k0 = u.s * kKs + kb * 64;
-                    if (g.map1 >= 0) {
-                        mb_tma_2d(dst, e.maps + g.map0, full + slot, k0, row);
-                        mb_tma_2d(dst + kMBStage / 2, e.maps + g.map1, full + slot, k0, row);
-                    } else {
-                        mb_tma_2d(dst, e.maps + g.map0, full + slot, k0, row);
+            const int t = unit_of(s);
+            if (t >= 0) {
+                // the unit AFTER this one goes to L2 now (TMA prefetch, no shared memory involved): the ring only holds
+                // half a tile, so the second half of every tile is fetched while the phase runs -- from L2, not from HBM
+                {
+                    Step q = next_weight_step(s);
+                    for (int guard = 0; guard < 12 && q.kind != K_END && unit_of(q) < 0; ++guard) q = next_weight_step(q);
+                    if (q.kind != K_END && unit_of(q) >= 0) prefetch_unit(q);
+                }
+                const CUtensorMap *m0 = e.maps + map_of(s);
+                if (s.kind == K_FFN) {
+                    // GEMM 1: rows [64 t, +64) of w1 and of w3, K = 1024 -> 16 stages of (64 + 64 rows) x 64 k
+                    for (int kb = 0; kb < kD / 64; ++kb) {
+                        unsigned char *dst = next_slot();
+                        mb_tma_2d(dst, m0, full + slot, kb * 64, 64 * t);
+                        mb_tma_2d(dst + kMBStage / 2, m0 + 1, full + slot, kb * 64, 64 * t);
+                        advance_slot();
                     }
-                    if (++slot == (unsigned)depth) { slot = 0; epar ^= 1; }
+                    // GEMM 2: columns [64 t, +64) of w2, all 1024 rows -> 8 stages of 128 rows x 64 k
+                    for (int r = 0; r < kD / 128; ++r) {
+                        unsigned char *dst = next_slot();
+                        mb_tma_2d(dst, m0 + 2, full + slot, 64 * t, 128 * r);
+                        advance_slot();
+                    }
+                } else {
+                    const int row = tile_row(s, t);
+                    for (int kb = 0; kb < kD / 64; ++kb) {
+                        unsigned char *dst = next_slot();
+                        mb_tma_2d(dst, m0, full + slot, kb * 64, row);
+                        advance_slot();
+                    }
                 }
             }
             s = next_weight_step(s);
@@ -325,42 +362,73 @@ struct MegaB {
     }
     __device__ __forceinline__ void mma_loop() {
         const uint32_t tmem_base = *tmem_slot;
-        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kAccCols >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint32_t idesc1 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kAccCols >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint32_t idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kAcc2Cols >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
         const int depth = e.nstages;
-        unsigned int slot = 0, spar = 0, units = 0, xphase = 0;  // ring slot / parity advance without divisions
+        unsigned int slot = 0, spar = 0, pcmd = 0, pxr0 = 0, pxr1 = 0, phr = 0;  // ring slot + barrier parities
         // descriptors differ only in the 14-bit start-address field (bytes >> 4): base + constant offsets
         const uint64_t desc_hi = ((uint64_t)((1024 >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
         const uint64_t b_base = desc_hi | (uint64_t)((m1_smem_u32(xs) >> 4) & 0x3FFF);
         const uint64_t a_base = desc_hi | (uint64_t)((m1_smem_u32(ring) >> 4) & 0x3FFF);
         for (;;) {
-            mb_wait(x_ready, xphase & 1);
-            ++xphase;
-            const int n = *cmd;
-            if (n < 0) break;
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            for (int i = 0; i < n; ++i) {
-                const unsigned buf = units & 1, use = units >> 1;
-                if (use > 0) {
-                    mb_wait(acc_empty + buf, (use - 1) & 1);
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                }
-                const uint32_t acc = tmem_base + buf * kAccCols;
+            // (no spin limit here: a CTA that owns no weight tile idles on this barrier for the whole launch)
+            while (!mb_try_wait(cmd_ready, pcmd)) {}
+            pcmd ^= 1;
+            const int c = *cmd;
+            if (c < 0) break;
+            // GEMM 1 (every projection): four 256-column activation slices alternate between the two operand buffers
+#pragma unroll 1
+            for (int s = 0; s < 4; ++s) {
+                const int i = s & 1;
+                if (i == 0) { mb_wait(xr, pxr0); pxr0 ^= 1; }
+                else { mb_wait(xr + 1, pxr1); pxr1 ^= 1; }
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
-                for (int kb = 0; kb < kKs / 64; ++kb) {
+                for (int kb = 0; kb < 4; ++kb) {
                     mb_wait(full + slot, spar);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     if (elect_one()) {
                         const uint64_t ad = a_base + (uint64_t)(slot * (kMBStage >> 4));
-                        const uint64_t bd = b_base + (uint64_t)(kb * (kXKb >> 4));
+                        const uint64_t bd = b_base + (uint64_t)((i * 4 + kb) * (kXKb >> 4));
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) mb_umma(acc, ad + 2 * k, bd + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                        for (int k = 0; k < 4; ++k) mb_umma(tmem_base, ad + 2 * k, bd + 2 * k, idesc1, (s | kb | k) != 0 ? 1u : 0u);
                         mb_commit(empty + slot);  // frees the ring stage once these MMAs have read it
-                        if (kb == kKs / 64 - 1) mb_commit(acc_full + buf);
+                        if (kb == 3) mb_commit(xf + i);  // ... and the slice buffer
+                        if (kb == 3 && s == 3) mb_commit(acc_full);
                     }
                     __syncwarp();
                     if (++slot == (unsigned)depth) { slot = 0; spar ^= 1; }
                 }
-                ++units;
+            }
+            if (c == 2) {
+                // GEMM 2 of the fused FFN: y[:, 128 r .. +128) += w2[128 r .. , 64 t .. +64) . h^T, h staged by the workers
+                mb_wait(hr, phr);
+                phr ^= 1;
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+                for (int r = 0; r < kD / 128; ++r) {
+                    mb_wait(full + slot, spar);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    if (elect_one()) {
+                        const uint64_t ad = a_base + (uint64_t)(slot * (kMBStage >> 4));
+                        const uint32_t acc = tmem_base + kAccCols + r * kAcc2Cols;
+                        if (kStack2) {
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) mb_umma(acc, ad + 2 * k, b_base + 2 * k, idesc2, k != 0 ? 1u : 0u);
+                        } else {
+#pragma unroll
+                            for (int term = 0; term < 3; ++term)
+#pragma unroll
+                                for (int k = 0; k < 4; ++k)
+                                    mb_umma(acc, ad + 2 * k, b_base + (uint64_t)(term * (NPAD * 128 >> 4)) + 2 * k, idesc2,
+                                            (term | k) != 0 ? 1u : 0u);
+                        }
+                        mb_commit(empty + slot);
+                        if (r == kD / 128 - 1) mb_commit(a2f);
+                    }
+                    __syncwarp();
+                    if (++slot == (unsigned)depth) { slot = 0; spar ^= 1; }
+                }
             }
         }
     }
@@ -386,221 +454,321 @@ struct MegaB {
     }
 
     // ------------------------------------------------------------ activation operand
-    // rows [0, nb) x columns [k0, k0 + 256) of a row-major fp32 activation (leading dimension ld) -> three bf16
-    // terms in the UMMA K-major layout: k-block kb = [3 NPAD rows][64 k] with 128-byte rows (hi | mid | lo row groups),
-    // 16-byte chunk c of row r stored at chunk c ^ (r & 7) (the 128-byte swizzle TMA would produce).  Rows >= nb are zero.
-    __device__ __forceinline__ void stage_x(const float *src, int ld, bool with_norm) {
-        const int c32 = tid & 31;           // 16-byte chunk (8 columns) of the 256-column slice
-        const int kb = c32 >> 3, c = c32 & 7;
+    // A 256-column slice of rows [0, nb) of a row-major fp32 activation -> three bf16 terms in the UMMA K-major layout:
+    // k-block kb = [3 NPAD rows][64 k] with 128-byte rows (hi | mid | lo row groups), 16-byte chunk c of row r stored
+    // at chunk c ^ (r & 7) (the 128-byte swizzle TMA would produce).  Rows >= nb are zero.  The global loads of slice
+    // s + 1 are in flight while slice s is converted, and the MMAs of slice s run while slice s + 1 is staged.
+    struct XRegs {
+        float4 v[NPAD / 8][2];
+        float4 g[2];
+    };
+    __device__ __forceinline__ void load_slice(XRegs &r, const float *src, int ld, const float *gw) const {
+        const int c32 = tid & 31;  // 16-byte chunk (8 columns) of the slice
 #pragma unroll
         for (int i = 0; i < NPAD / 8; ++i) {
             const int b = (tid >> 5) + i * 8;
-            float v[8];
             if (b < p.nb) {
-                const float4 a0 = __ldcg(reinterpret_cast<const float4 *>(src + (size_t)b * ld + c32 * 8));
-                const float4 a1 = __ldcg(reinterpret_cast<const float4 *>(src + (size_t)b * ld + c32 * 8 + 4));
-                v[0] = a0.x; v[1] = a0.y; v[2] = a0.z; v[3] = a0.w; v[4] = a1.x; v[5] = a1.y; v[6] = a1.z; v[7] = a1.w;
-                if (with_norm) {
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) v[j] = __fmul_rn(v[j], gpre[j]);
-                }
+                r.v[i][0] = __ldcg(reinterpret_cast<const float4 *>(src + (size_t)b * ld + c32 * 8));
+                r.v[i][1] = __ldcg(reinterpret_cast<const float4 *>(src + (size_t)b * ld + c32 * 8 + 4));
             } else {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] = 0.f;
+                r.v[i][0] = make_float4(0.f, 0.f, 0.f, 0.f);
+                r.v[i][1] = make_float4(0.f, 0.f, 0.f, 0.f);
             }
+        }
+        if (gw) {
+            r.g[0] = __ldg(reinterpret_cast<const float4 *>(gw + c32 * 8));
+            r.g[1] = __ldg(reinterpret_cast<const float4 *>(gw + c32 * 8 + 4));
+        } else {
+            r.g[0] = r.g[1] = make_float4(1.f, 1.f, 1.f, 1.f);
+        }
+    }
+    __device__ __forceinline__ void store_slice(const XRegs &r, int buf) {
+        const int c32 = tid & 31;
+        const int kb = c32 >> 3, c = c32 & 7;
+        unsigned char *base = xs + buf * kXBuf + kb * kXKb;
+#pragma unroll
+        for (int i = 0; i < NPAD / 8; ++i) {
+            const int b = (tid >> 5) + i * 8;
+            const float v[8] = {__fmul_rn(r.v[i][0].x, r.g[0].x), __fmul_rn(r.v[i][0].y, r.g[0].y), __fmul_rn(r.v[i][0].z, r.g[0].z),
+                                __fmul_rn(r.v[i][0].w, r.g[0].w), __fmul_rn(r.v[i][1].x, r.g[1].x), __fmul_rn(r.v[i][1].y, r.g[1].y),
+                                __fmul_rn(r.v[i][1].z, r.g[1].z), __fmul_rn(r.v[i][1].w, r.g[1].w)};
             unsigned short h[8], m[8], l[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) mb_split3(v[j], h[j], m[j], l[j]);
-            const uint32_t off = (uint32_t)(kb * kXKb + b * 128 + ((c ^ (b & 7)) << 4));
+            const uint32_t off = (uint32_t)(b * 128 + ((c ^ (b & 7)) << 4));
             auto pack = [](const unsigned short (&q)[8]) {
                 return make_uint4((uint32_t)q[0] | ((uint32_t)q[1] << 16), (uint32_t)q[2] | ((uint32_t)q[3] << 16),
                                   (uint32_t)q[4] | ((uint32_t)q[5] << 16), (uint32_t)q[6] | ((uint32_t)q[7] << 16));
             };
-            *reinterpret_cast<uint4 *>(xs + off) = pack(h);
-            *reinterpret_cast<uint4 *>(xs + NPAD * 128 + off) = pack(m);
-            *reinterpret_cast<uint4 *>(xs + 2 * NPAD * 128 + off) = pack(l);
+            *reinterpret_cast<uint4 *>(base + off) = pack(h);
+            *reinterpret_cast<uint4 *>(base + NPAD * 128 + off) = pack(m);
+            *reinterpret_cast<uint4 *>(base + 2 * NPAD * 128 + off) = pack(l);
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> tensor-core (async proxy) reads
     }
-
-    // norm weights of the coming phase for this thread's 8 columns (issued before the grid-barrier wait)
-    __device__ __forceinline__ void prep_step(const Step &s) {
-        if (s.kind == K_END || s.kind == K_ATT || s.kind == K_SAMPLE || s.kind == K_WO || s.kind == K_W2) return;
-        const Gemm g = gemm_of(s);
-        const Units u = units_of(g);
-        if (u.n == 0) return;
-        const bool slow = s.pass == 0;
-        const int li = slow ? s.l : p.NL + s.l;
-        const float *gw = s.kind == K_QKV ? normtab[2 * li] : s.kind == K_W13 ? normtab[2 * li + 1]
-                                                                              : normtab[2 * (p.NL + p.NFL) + (slow ? 0 : 1)];
-        const float4 a = __ldg(reinterpret_cast<const float4 *>(gw + u.s * kKs + (tid & 31) * 8));
-        const float4 b = __ldg(reinterpret_cast<const float4 *>(gw + u.s * kKs + (tid & 31) * 8 + 4));
-        gpre[0] = a.x; gpre[1] = a.y; gpre[2] = a.z; gpre[3] = a.w; gpre[4] = b.x; gpre[5] = b.y; gpre[6] = b.z; gpre[7] = b.w;
-    }
-
-    // sum of the S partials of (tile, batch row b, accumulator lane), fixed order
-    __device__ __forceinline__ float psum(const float *wt, int S, int b, int ln) const {
-        float a = __ldcg(wt + b * 128 + ln);
-#pragma unroll 4
-        for (int sp = 1; sp < S; ++sp) a += __ldcg(wt + ((size_t)sp * NPAD + b) * 128 + ln);
-        return a;
-    }
-    __device__ __forceinline__ float2 psum2(const float *wt, int S, int b, int ln) const {
-        float2 a = __ldcg(reinterpret_cast<const float2 *>(wt + b * 128 + ln));
-#pragma unroll 4
-        for (int sp = 1; sp < S; ++sp) {
-            const float2 q = __ldcg(reinterpret_cast<const float2 *>(wt + ((size_t)sp * NPAD + b) * 128 + ln));
-            a.x += q.x;
-            a.y += q.y;
+    // all four slices of a K = 1024 activation; gw: norm weights (x * g is what gets multiplied) or null
+    __device__ __forceinline__ void stage_all(const float *src, const float *gw, const float *ssq = nullptr) {
+        XRegs ra, rb;
+        load_slice(ra, src, kD, gw);
+        if (ssq) compute_invd(ssq);  // its L2 round trip overlaps the slice loads already in flight
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+            XRegs &cur = (s & 1) ? rb : ra;
+            XRegs &nxt = (s & 1) ? ra : rb;
+            if (s + 1 < 4) load_slice(nxt, src + (s + 1) * kKs, kD, gw ? gw + (s + 1) * kKs : nullptr);
+            // buffer s & 1 was read by the MMAs of slice s - 2: its first completion of this phase (the barrier
+            // completes exactly twice per phase, so that one always has parity 0)
+            if (s >= 2) mb_wait(xf + (s & 1), 0);
+            store_slice(cur, s & 1);
+            wsync();
+            if (tid == 0) m1_mbar_arrive(xr + (s & 1));
         }
-        return a;
+    }
+    // 1 / sqrt(mean(x^2) + eps) of every row (candle_nn::RmsNorm), from the partial sums the producer of x left
+    __device__ __forceinline__ void compute_invd(const float *ssq) {
+        if (tid < p.nb) {
+            const float4 *q4 = reinterpret_cast<const float4 *>(ssq + (size_t)tid * kMBSsq);
+            float t = 0.f;
+#pragma unroll
+            for (int i = 0; i < kMBSsq / 4; ++i) {
+                const float4 q = __ldcg(q4 + i);
+                t += (q.x + q.y) + (q.z + q.w);
+            }
+            invd[tid] = 1.0f / sqrtf(t / (float)kD + p.eps);
+        }
+    }
+    // this thread's accumulator row (TMEM lane quadrant * 32 + lane) x its half of the batch columns, terms added
+    __device__ __forceinline__ void drain_stacked(uint32_t col_base, float (&r)[NPAD / 2]) const {
+        const uint32_t tmem_base = *tmem_slot;
+        const int qd = warp & 3, cc0 = (warp >> 2) * (NPAD / 2);
+#pragma unroll
+        for (int term = 0; term < 3; ++term) {
+            uint32_t q[16];
+            const uint32_t taddr = tmem_base + col_base + term * NPAD + ((uint32_t)(qd * 32) << 16) + (uint32_t)cc0;
+            if (NPAD == 32) mb_tmem_ld16(taddr, q);
+            else mb_tmem_ld8(taddr, q);
+#pragma unroll
+            for (int j = 0; j < NPAD / 2; ++j) r[j] = term == 0 ? __uint_as_float(q[j]) : r[j] + __uint_as_float(q[j]);
+        }
     }
 
-    // ------------------------------------------------------------ one projection phase
-    __device__ __forceinline__ void gemm_phase(const Step &s) {
-        const Gemm g = gemm_of(s);
-        const Units u = units_of(g);
+    // ------------------------------------------------------------ projection with a direct epilogue (QKV, WO, heads)
+    __device__ __forceinline__ void fullk_phase(const Step &s) {
+        const int t = unit_of(s);
+        if (t < 0) return;
         const bool slow = s.pass == 0;
         const int cb = s.pass - 1;
         const int kind = s.kind;
         float *stream = slow ? p.x : p.fx;
         float *ssq = slow ? e.ssq_x : e.ssq_fx;
-        const bool with_norm = kind == K_QKV || kind == K_W13 || kind == K_HEAD;
-        const int epoch = ++epoch_reg[g.gk];
-        const bool tm = p.dbg != nullptr && tid == 0 && blockIdx.x == 0 && u.n > 0;
-        unsigned long long *td = p.dbg + 128 + kind * 8;
+        if (tid == 0) {
+            *cmd = 1;
+            m1_mbar_arrive(cmd_ready);
+        }
+        const bool tm = p.dbg != nullptr && tid == 0 && (blockIdx.x == 64 || blockIdx.x == 74 || blockIdx.x == 82);
+        unsigned long long *td = p.dbg + 192 + kind * 8;
         long long c0 = tm ? clock64() : 0, c1 = 0;
-        if (u.n > 0) {
-            const float *src = kind == K_WO ? e.att : kind == K_W2 ? p.h : stream;
-            stage_x(src + u.s * kKs, kind == K_W2 ? kI : kD, with_norm);
-            wsync();
-            if (tid == 0) {
-                *cmd = u.n;
-                m1_mbar_arrive(x_ready);
-            }
-            if (tm) { c1 = clock64(); td[0] += c1 - c0; c0 = c1; }
-            // 1 / sqrt(mean(x^2) + eps) of every row (candle_nn::RmsNorm), from the partial sums the producer of x left
-            if (with_norm && tid < p.nb) {
-                const float4 *q4 = reinterpret_cast<const float4 *>(ssq + (size_t)tid * kMBSsq);
-                float t = 0.f;
+        const int li = slow ? s.l : p.NL + s.l;
+        const float *gw = kind == K_QKV ? normtab[2 * li] : kind == K_HEAD ? normtab[2 * (p.NL + p.NFL) + (slow ? 0 : 1)] : nullptr;
+        stage_all(kind == K_WO ? e.att : stream, gw, gw ? ssq : nullptr);
+        if (tm) { c1 = clock64(); td[0] += c1 - c0; c0 = c1; }
+        mb_wait(acc_full, pacc);
+        pacc ^= 1;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (tm) { c1 = clock64(); td[1] += c1 - c0; c0 = c1; }
+        float r[NPAD / 2];
+        drain_stacked(0, r);
+        const int qd = warp & 3, cc0 = (warp >> 2) * (NPAD / 2);
+        const int row = qd * 32 + lane;
+        if (kind == K_WO) {
+            // residual add (dual_ar.rs:436-440) + this warp's share of sum(x^2) for the next RMSNorm
+            float xo[NPAD / 2];
 #pragma unroll
-                for (int i = 0; i < kMBSsq / 4; ++i) {
-                    const float4 q = __ldcg(q4 + i);
-                    t += (q.x + q.y) + (q.z + q.w);
-                }
-                invd[tid] = 1.0f / sqrtf(t / (float)kD + p.eps);
-            }
-        }
-        // ---- drain the accumulators: partial[tile][slice][b][lane]
-        const uint32_t tmem_base = *tmem_slot;
-        for (int i = 0; i < u.n; ++i) {
-            const int t = u.j + i * u.ns;
-            const unsigned buf = ucount & 1, use = ucount >> 1;
-            mb_wait(acc_full + buf, use & 1);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            if (tm) { c1 = clock64(); td[1] += c1 - c0; c0 = c1; }
-            const int qd = warp & 3, cc0 = (warp >> 2) * (NPAD / 2);
-            float r[NPAD / 2];
+            for (int j = 0; j < NPAD / 2; ++j)  // (all loads in flight before the first use)
+                xo[j] = cc0 + j < p.nb ? __ldcg(stream + (size_t)(cc0 + j) * kD + 128 * t + row) : 0.f;
 #pragma unroll
-            for (int term = 0; term < 3; ++term) {
-                uint32_t q[16];
-                const uint32_t taddr = tmem_base + buf * kAccCols + term * NPAD + ((uint32_t)(qd * 32) << 16) + (uint32_t)cc0;
-                if (NPAD == 32) mb_tmem_ld16(taddr, q);
-                else mb_tmem_ld8(taddr, q);
-#pragma unroll
-                for (int j = 0; j < NPAD / 2; ++j) r[j] = term == 0 ? __uint_as_float(q[j]) : r[j] + __uint_as_float(q[j]);
-            }
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            m1_mbar_arrive(acc_empty + buf);
-            float *dst = e.ws + (((size_t)t * g.S + u.s) * NPAD + cc0) * 128 + qd * 32 + lane;
-#pragma unroll
-            for (int j = 0; j < NPAD / 2; ++j)
-                if (cc0 + j < p.nb) dst[j * 128] = r[j];
-            ++ucount;
-            wsync();
-            if (tid == 0) mb_red_release(e.cnt + g.gk * kMBCntStride + t, 1u);
-            if (tm) { c1 = clock64(); td[2] += c1 - c0; c0 = c1; }
-        }
-        // ---- split-K fixup: the CTA of slice s reduces batch rows [b_lo, b_hi) of each of its tiles
-        const int per = (p.nb + g.S - 1) / g.S;
-        const int b_lo = u.s * per, b_hi = min(p.nb, b_lo + per);
-        if (tm) td[5] += 1;
-        if (b_lo >= b_hi) return;
-        for (int i = 0; i < u.n; ++i) {
-            const int t = u.j + i * u.ns;
-            if (tm) c0 = clock64();
-            if (tid == 0) {
-                const unsigned want = (unsigned)(g.S * epoch);
-                const unsigned *c = e.cnt + g.gk * kMBCntStride + t;
-                if (mb_ld_acquire(c) < want) {
-                    const long long t0 = clock64();
-                    while (mb_ld_acquire(c) < want)
-                        if (clock64() - t0 > kMBSpinLimit) __trap();
-                }
-            }
-            wsync();
-            if (tm) { c1 = clock64(); td[3] += c1 - c0; c0 = c1; }
-            const float *wt = e.ws + (size_t)t * g.S * NPAD * 128;
-            if (kind == K_WO || kind == K_W2) {
-                // residual add (dual_ar.rs:436-440) + this tile's share of sum(x^2) for the next RMSNorm
-                const int ln = tid & 127;
-                for (int b = b_lo + (tid >> 7); b < b_hi; b += 2) {
-                    float *xp = stream + (size_t)b * kD + 128 * t + ln;
-                    const float nv = __fadd_rn(__ldcg(xp), psum(wt, g.S, b, ln));
-                    *xp = nv;
+            for (int j = 0; j < NPAD / 2; ++j) {
+                const int b = cc0 + j;
+                if (b < p.nb) {
+                    const float nv = __fadd_rn(xo[j], r[j]);
+                    stream[(size_t)b * kD + 128 * t + row] = nv;
                     const float q = warp_sum(nv * nv);
-                    if (lane == 0) ssq[(size_t)b * kMBSsq + t * 4 + (ln >> 5)] = q;
+                    if (lane == 0) ssq[(size_t)b * kMBSsq + t * 4 + qd] = q;
                 }
-            } else if (kind == K_W13) {
-                // silu(w1 x) * (w3 x), dual_ar.rs:160-165: accumulator lanes [0, 64) = w1 rows, [64, 128) = w3 rows
-                const int ii = tid & 63;
-                for (int b = b_lo + (tid >> 6); b < b_hi; b += 4) {
-                    const float g1 = psum(wt, g.S, b, ii) * invd[b], g3 = psum(wt, g.S, b, 64 + ii) * invd[b];
-                    p.h[(size_t)b * kI + 64 * t + ii] = __fmul_rn(silu_f(g1), g3);
-                }
-            } else if (kind == K_QKV) {
-                // rope_i on row pairs (dual_ar.rs:246-247) -> q buffer / K cache; V rows -> V cache (Tensor::cat, :316-324)
-                const int pr = tid & 63;
-                const size_t kv_stride = slow ? p.slow_kv_stride : p.fast_kv_stride;
-                float *kcl = (slow ? p.kc : p.fkc) + s.l * kv_stride, *vcl = (slow ? p.vc : p.fvc) + s.l * kv_stride;
-                const int cache_len = slow ? p.max_len : kC;
-                for (int b = b_lo + (tid >> 6); b < b_hi; b += 4) {
-                    float2 v = psum2(wt, g.S, b, 2 * pr);
-                    v.x *= invd[b];
-                    v.y *= invd[b];
-                    const int pos = slow ? (act_s[b] ? pos_s[b] : 0) : cb;  // a finished row may sit at max_len
-                    const int r = 128 * t + 2 * pr;
-                    if (r < kD + kKV * kHd) {
-                        const int pi = (r & 63) >> 1;
-                        const float c = __ldg(p.cosT + (size_t)pos * 32 + pi), sn = __ldg(p.sinT + (size_t)pos * 32 + pi);
-                        const float o0 = __fsub_rn(__fmul_rn(v.x, c), __fmul_rn(v.y, sn));
-                        const float o1 = __fadd_rn(__fmul_rn(v.x, sn), __fmul_rn(v.y, c));
-                        if (r < kD) {
-                            *reinterpret_cast<float2 *>(p.q + (size_t)b * kD + r) = make_float2(o0, o1);
+            }
+        } else if (kind == K_QKV) {
+            // rope_i on row pairs (dual_ar.rs:246-247; adjacent rows = adjacent lanes) -> q buffer / K cache; V rows ->
+            // V cache (Tensor::cat, :316-324)
+            const size_t kv_stride = slow ? p.slow_kv_stride : p.fast_kv_stride;
+            float *kcl = (slow ? p.kc : p.fkc) + s.l * kv_stride, *vcl = (slow ? p.vc : p.fvc) + s.l * kv_stride;
+            const int cache_len = slow ? p.max_len : kC;
+            const int rr = 128 * t + row;
+            const int pi = (rr & 63) >> 1;
+            const bool roped = rr < kD + kKV * kHd;
+            float cs[NPAD / 2], sn[NPAD / 2];
+#pragma unroll
+            for (int j = 0; j < NPAD / 2; ++j) {
+                const int b = min(cc0 + j, p.nb - 1);
+                const int pos = slow ? (act_s[b] ? pos_s[b] : 0) : cb;  // a finished row may sit at max_len
+                cs[j] = roped ? __ldg(p.cosT + (size_t)pos * 32 + pi) : 1.f;
+                sn[j] = roped ? __ldg(p.sinT + (size_t)pos * 32 + pi) : 0.f;
+            }
+#pragma unroll
+            for (int j = 0; j < NPAD / 2; ++j) {
+                const int b = cc0 + j;
+                if (b < p.nb) {
+                    const float v = r[j] * invd[b];
+                    const float w = __shfl_xor_sync(0xffffffffu, v, 1);
+                    const int pos = slow ? (act_s[b] ? pos_s[b] : 0) : cb;
+                    if (roped) {
+                        const float o = (lane & 1) ? __fadd_rn(__fmul_rn(w, sn[j]), __fmul_rn(v, cs[j]))
+                                                   : __fsub_rn(__fmul_rn(v, cs[j]), __fmul_rn(w, sn[j]));
+                        if (rr < kD) {
+                            p.q[(size_t)b * kD + rr] = o;
                         } else if (act_s[b]) {
-                            const int rk = r - kD, kvh = rk >> 6, d = rk & 63;
-                            *reinterpret_cast<float2 *>(kcl + (((size_t)b * kKV + kvh) * cache_len + pos) * kHd + d) = make_float2(o0, o1);
+                            const int rk = rr - kD, kvh = rk >> 6, d = rk & 63;
+                            kcl[(((size_t)b * kKV + kvh) * cache_len + pos) * kHd + d] = o;
                         }
                     } else if (act_s[b]) {
-                        const int rv = r - kD - kKV * kHd, kvh = rv >> 6, d = rv & 63;
-                        *reinterpret_cast<float2 *>(vcl + (((size_t)b * kKV + kvh) * cache_len + pos) * kHd + d) = v;
+                        const int rv = rr - kD - kKV * kHd, kvh = rv >> 6, d = rv & 63;
+                        vcl[(((size_t)b * kKV + kvh) * cache_len + pos) * kHd + d] = v;
                     }
                 }
-            } else {  // K_HEAD: logits of the constrained slow head (generate/utils.rs:6-33) or of fast_output
-                const int ln = tid & 127;
-                int r = 128 * t + ln;
-                bool ok = r < (slow ? p.n_slow_logits : kCS);
-                if (slow && e.head_extra) {
-                    if (t == e.head_tiles) { r = 0; ok = ln == 0; }   // the extra tile starts at the <|im_end|> row
-                    else if (r == 0) ok = false;
-                }
-                for (int b = b_lo + (tid >> 7); b < b_hi; b += 2)
-                    if (ok) p.logits[(size_t)b * p.ldl + r] = psum(wt, g.S, b, ln) * invd[b];
             }
-            if (tm) td[4] += clock64() - c0;
+        } else {  // K_HEAD: logits of the constrained slow head (generate/utils.rs:6-33) or of fast_output
+            int rr = 128 * t + row;
+            bool ok = rr < (slow ? p.n_slow_logits : kCS);
+            if (slow && e.head_extra) {
+                if (t == e.head_tiles) { rr = 0; ok = row == 0; }  // the extra tile starts at the <|im_end|> row
+                else if (rr == 0) ok = false;
+            }
+#pragma unroll
+            for (int j = 0; j < NPAD / 2; ++j) {
+                const int b = cc0 + j;
+                if (b < p.nb && ok) p.logits[(size_t)b * p.ldl + rr] = r[j] * invd[b];
+            }
         }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        if (tm) { td[2] += clock64() - c0; td[5] += 1; }
     }
-    int epoch_reg[G_COUNT];
+
+    // ------------------------------------------------------------ fused feed-forward (dual_ar.rs:160-165)
+    // CTA t owns 64 columns of the intermediate dimension: h[:, 64 t .. +64) = silu(w1 x) * (w3 x) stays in shared
+    // memory and is multiplied with w2[:, 64 t .. +64) right away; the 64 partial outputs are summed by fred_phase.
+    __device__ __forceinline__ void ffn_phase(const Step &s) {
+        const int t = unit_of(s);
+        if (t < 0) return;
+        const bool slow = s.pass == 0;
+        float *stream = slow ? p.x : p.fx;
+        if (tid == 0) {
+            *cmd = 2;
+            m1_mbar_arrive(cmd_ready);
+        }
+        const bool tm = p.dbg != nullptr && tid == 0 && blockIdx.x == 0;
+        unsigned long long *td = p.dbg + 192 + K_FFN * 8;
+        long long c0 = tm ? clock64() : 0, c1 = 0;
+        const int li = slow ? s.l : p.NL + s.l;
+        stage_all(stream, normtab[2 * li + 1], slow ? e.ssq_x : e.ssq_fx);
+        if (tm) { c1 = clock64(); td[0] += c1 - c0; c0 = c1; }
+        mb_wait(acc_full, pacc);
+        pacc ^= 1;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (tm) { c1 = clock64(); td[1] += c1 - c0; c0 = c1; }
+        const int qd = warp & 3, cc0 = (warp >> 2) * (NPAD / 2);
+        {
+            // accumulator lanes [0, 64) = w1 rows, [64, 128) = w3 rows of the block: pair them through shared memory
+            float r[NPAD / 2];
+            drain_stacked(0, r);
+            float *exch = reinterpret_cast<float *>(xs + kXBuf);  // [NPAD][64]; both slice buffers are idle now
+            if (qd >= 2) {
+#pragma unroll
+                for (int j = 0; j < NPAD / 2; ++j) exch[(cc0 + j) * 64 + (qd - 2) * 32 + lane] = r[j];
+            }
+            wsync();
+            if (qd < 2) {
+                const int i = qd * 32 + lane;  // column of the block == k index of the second GEMM
+#pragma unroll
+                for (int j = 0; j < NPAD / 2; ++j) {
+                    const int b = cc0 + j;
+                    const float g1 = r[j] * invd[b < p.nb ? b : 0], g3 = exch[b * 64 + i] * invd[b < p.nb ? b : 0];
+                    const float hv = b < p.nb ? __fmul_rn(silu_f(g1), g3) : 0.f;
+                    unsigned short hh, hm, hl;
+                    mb_split3(hv, hh, hm, hl);
+                    // k-block layout: row (term * NPAD + b), 16-byte chunk (i / 8) ^ (row & 7), element i % 8
+                    const uint32_t off = (uint32_t)(b * 128 + (((i >> 3) ^ (b & 7)) << 4) + (i & 7) * 2);
+                    *reinterpret_cast<unsigned short *>(xs + off) = hh;
+                    *reinterpret_cast<unsigned short *>(xs + NPAD * 128 + off) = hm;
+                    *reinterpret_cast<unsigned short *>(xs + 2 * NPAD * 128 + off) = hl;
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            wsync();
+            if (tid == 0) m1_mbar_arrive(hr);
+        }
+        if (tm) { c1 = clock64(); td[2] += c1 - c0; c0 = c1; }
+        mb_wait(a2f, pa2f);
+        pa2f ^= 1;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (tm) { c1 = clock64(); td[3] += c1 - c0; c0 = c1; }
+        // partial y[t][b][128 r + row] (summed over the 64 blocks by fred_phase)
+        float *yp = e.ws + (size_t)t * NPAD * kD + qd * 32 + lane;
+#pragma unroll 1
+        for (int r8 = 0; r8 < kD / 128; ++r8) {
+            float r[NPAD / 2];
+            if (kStack2) {
+                drain_stacked(kAccCols + r8 * kAcc2Cols, r);
+            } else {
+                uint32_t q[16];
+                const uint32_t taddr = *tmem_slot + kAccCols + r8 * kAcc2Cols + ((uint32_t)(qd * 32) << 16) + (uint32_t)cc0;
+                mb_tmem_ld16(taddr, q);
+#pragma unroll
+                for (int j = 0; j < NPAD / 2; ++j) r[j] = __uint_as_float(q[j]);
+            }
+#pragma unroll
+            for (int j = 0; j < NPAD / 2; ++j)
+                if (cc0 + j < p.nb) yp[(size_t)(cc0 + j) * kD + 128 * r8] = r[j];
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        if (tm) { td[4] += clock64() - c0; td[5] += 1; }
+    }
+
+    // x += sum over the 64 blocks of the FFN partials (fixed order), and the sums of squares the next RMSNorm needs.
+    // CTA c < 4 nb: batch row c / 4, columns [(c % 4) * 256, +256); warp = 32 columns; 4 lanes per column quad, each
+    // summing 16 blocks, combined by a fixed shuffle tree.
+    __device__ __forceinline__ void fred_phase(const Step &s) {
+        const int c = blockIdx.x;
+        if (c >= 4 * p.nb) return;
+        const bool slow = s.pass == 0;
+        float *stream = slow ? p.x : p.fx;
+        float *ssq = slow ? e.ssq_x : e.ssq_fx;
+        const int b = c >> 2, sub = lane & 3;
+        const int col = (c & 3) * 256 + warp * 32 + (lane >> 2) * 4;
+        const float *yp = e.ws + ((size_t)(sub * 16) * NPAD + b) * kD + col;
+        float4 a = __ldcg(reinterpret_cast<const float4 *>(yp));
+#pragma unroll
+        for (int j = 1; j < 16; ++j) {
+            const float4 q = __ldcg(reinterpret_cast<const float4 *>(yp + (size_t)j * NPAD * kD));
+            a.x += q.x; a.y += q.y; a.z += q.z; a.w += q.w;
+        }
+#pragma unroll
+        for (int o = 1; o < 4; o <<= 1) {
+            a.x += __shfl_xor_sync(0xffffffffu, a.x, o);
+            a.y += __shfl_xor_sync(0xffffffffu, a.y, o);
+            a.z += __shfl_xor_sync(0xffffffffu, a.z, o);
+            a.w += __shfl_xor_sync(0xffffffffu, a.w, o);
+        }
+        float sq = 0.f;
+        if (sub == 0) {
+            float4 *xp = reinterpret_cast<float4 *>(stream + (size_t)b * kD + col);
+            const float4 xo = __ldcg(xp);
+            const float4 nv = make_float4(__fadd_rn(xo.x, a.x), __fadd_rn(xo.y, a.y), __fadd_rn(xo.z, a.z), __fadd_rn(xo.w, a.w));
+            *xp = nv;
+            sq = nv.x * nv.x + nv.y * nv.y + nv.z * nv.z + nv.w * nv.w;
+        }
+        sq = warp_sum(sq);
+        if (lane == 0) ssq[(size_t)b * kMBSsq + (c & 3) * 8 + warp] = sq;
+    }
 
     // ------------------------------------------------------------ attention
     // positions [j0, j1) of (row b, kv head kvh) for the 8 query heads of the group (warp = head); returns this
@@ -989,8 +1157,6 @@ struct MegaB {
 
     // ------------------------------------------------------------ frame loop (workers)
     __device__ __forceinline__ void run() {
-#pragma unroll
-        for (int i = 0; i < G_COUNT; ++i) epoch_reg[i] = 0;
         Step cur = first_step();
         const bool samples = (int)blockIdx.x < p.nb;
         if (samples) load_sampler_state();
@@ -1001,35 +1167,32 @@ struct MegaB {
         }
         frame_prep();
         grid_arrive();
-        prep_step(cur);
         grid_wait();
-        const bool timed = p.dbg != nullptr && tid == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1);
-        unsigned long long *dbg = p.dbg + (blockIdx.x == 0 ? 0 : 32);
+        const bool timed = p.dbg != nullptr && tid == 0 && (blockIdx.x == 0 || blockIdx.x == 64 || blockIdx.x == 74);
+        unsigned long long *dbg = p.dbg + (blockIdx.x == 0 ? 0 : blockIdx.x == 64 ? 32 : 128);
         while (cur.kind != K_END) {
-            unsigned long long t0 = 0, t1 = 0, t2 = 0;
+            unsigned long long t0 = 0, t1 = 0;
             if (timed) t0 = clock64();
-            if (cur.kind == K_SAMPLE) {
-                if (samples) {
-                    if (cur.pass == 0) sample_slow(cur.frame);
-                    else sample_fast(cur.pass - 1);
-                }
-            } else if (cur.kind == K_ATT) {
-                attn_phase(cur);
-            } else {
-                gemm_phase(cur);
+            switch (cur.kind) {
+                case K_SAMPLE:
+                    if (samples) {
+                        if (cur.pass == 0) sample_slow(cur.frame);
+                        else sample_fast(cur.pass - 1);
+                    }
+                    break;
+                case K_ATT: attn_phase(cur); break;
+                case K_FFN: ffn_phase(cur); break;
+                case K_FRED: fred_phase(cur); break;
+                default: fullk_phase(cur);
             }
             const Step nxt = advance(cur);
             if (timed) t1 = clock64();
             grid_arrive();
-            if (nxt.kind == K_SAMPLE) prep_step(advance(nxt));
-            else if (cur.kind != K_SAMPLE) prep_step(nxt);
-            if (timed) t2 = clock64();
             grid_wait();
             if (timed) {
-                const unsigned long long t3 = clock64();
+                const unsigned long long t2 = clock64();
                 dbg[cur.kind * 4 + 0] += t1 - t0;
-                dbg[cur.kind * 4 + 1] += t2 - t1;
-                dbg[cur.kind * 4 + 2] += t3 - t2;
+                dbg[cur.kind * 4 + 2] += t2 - t1;
                 dbg[cur.kind * 4 + 3] += 1;
             }
             if (cur.kind == K_SAMPLE && cur.pass == 0) {
@@ -1047,7 +1210,7 @@ struct MegaB {
         if (tid == 0) {
             *done_flag = 1;
             *cmd = -1;
-            m1_mbar_arrive(x_ready);
+            m1_mbar_arrive(cmd_ready);
         }
     }
 };
@@ -1065,18 +1228,21 @@ megab_decode_kernel(const __grid_constant__ MegaParams p, const __grid_constant_
             m1_mbar_init(m.full + i, 1);
             m1_mbar_init(m.empty + i, 1);
         }
-        m1_mbar_init(m.x_ready, 1);
+        m1_mbar_init(m.cmd_ready, 1);
         for (int i = 0; i < 2; ++i) {
-            m1_mbar_init(m.acc_full + i, 1);
-            m1_mbar_init(m.acc_empty + i, kMBWorkers);
+            m1_mbar_init(m.xr + i, 1);
+            m1_mbar_init(m.xf + i, 1);
         }
+        m1_mbar_init(m.acc_full, 1);
+        m1_mbar_init(m.hr, 1);
+        m1_mbar_init(m.a2f, 1);
         *m.go_frames = 1;
         *m.done_flag = 0;
         *m.cmd = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     {
-        // norm-weight pointers of every layer (chased by prep_step every phase)
+        // norm-weight pointers of every layer (chased every phase)
         const int nl = p.NL + p.NFL;
         for (int i = threadIdx.x; i < nl; i += blockDim.x) {
             const MegaLayer *L = i < p.NL ? p.slow + i : p.fast + (i - p.NL);
