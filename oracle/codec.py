@@ -197,3 +197,23 @@ def convnext_encoder(mel, w, prefix="backbone."):
 def encode_mel(mel, w):
     """FireflyEncoder::encode, encoder.rs:38-42."""
     return quantizer_encode(convnext_encoder(mel, w), w)
+
+
+def encode_mel_preround(mel, w):
+    """Same chain as `encode_mel`, but returns what FSQ rounds: the twice-bounded projections (G, L, 4) right before
+    `round()` (fsq.rs:68-130), next to the indices.  Lets a test prove that an index that differs on another
+    implementation differs only because a pre-round value sits within float noise of a rounding boundary (x.5)."""
+    z = convnext_encoder(mel, w)
+    prefix = "quantizer."
+    for i in range(2):
+        z = fish_conv(z, w[f"{prefix}downsample.{i}.0.conv.weight"], w[f"{prefix}downsample.{i}.0.conv.bias"], stride=2)
+        z = convnext_block(z, w, f"{prefix}downsample.{i}.1.")
+    zt = z[0].transpose(0, 1)  # (L, 512)
+    pre, idx = [], []
+    for g in range(N_GROUPS):
+        p = f"{prefix}residual_fsq.rvqs.{g}."
+        x = zt[:, g * 64:(g + 1) * 64]
+        zz = F.linear(x, w[p + "project_in.weight"], w[p + "project_in.bias"])
+        pre.append(fsq_bound(fsq_bound(zz)))
+        idx.append(fsq_encode_group(x, w, p))
+    return torch.stack(pre), torch.stack(idx)[None]

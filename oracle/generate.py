@@ -229,7 +229,8 @@ def _classify(logits: torch.Tensor, args: SamplingArgs, draw: int, row: int, tok
 
 
 def replay_frames(model: DualARTransformer, prompt: torch.Tensor, frames, args: SamplingArgs, row: int = 0,
-                  fixed_len: Optional[int] = None, tol_logit: float = 2e-3, force_slow: bool = False):
+                  fixed_len: Optional[int] = None, tol_logit: float = 2e-3, force_slow: bool = False,
+                  keep_slow_kv: bool = False):
     """frames: int array (C+1, T) as `fsb_lm_last_frames` returns them.  Returns a dict of counts and the list of
     (frame, slot, oracle_pick_class) for every non-exact decision.  The oracle model's slow KV is cleared first."""
     import numpy as np
@@ -237,11 +238,12 @@ def replay_frames(model: DualARTransformer, prompt: torch.Tensor, frames, args: 
     C = m.cfg.num_codebooks
     frames = np.asarray(frames).astype(np.int64)
     T = frames.shape[1]
-    m.clear_slow_layer_caches()
+    if not keep_slow_kv:  # keep_slow_kv: the prompt continues on top of a kept prefix (speech.rs:40)
+        m.clear_slow_layer_caches()
     rep = [RepPenProcessor(m.cfg.codebook_size, REP_PEN_WINDOW, args.repetition_penalty) for _ in range(C)]
     stats = {"decisions": 0, "exact": 0, "near_tie": 0, "violation": 0, "events": []}
     im_end = m.token_config.im_end_id
-    pos = 0
+    pos = m.curr_kv_size()
     x = prompt.clone()
     prev = None
     with torch.no_grad():
@@ -286,5 +288,6 @@ def replay_frames(model: DualARTransformer, prompt: torch.Tensor, frames, args: 
                     xh = m.fast_embeddings[a].reshape(1, 1, -1)
             prev = [int(v) for v in frames[:, f]]
             x = torch.tensor(prev, dtype=torch.int64).unsqueeze(-1)
-    m.clear_slow_layer_caches()
+    if not keep_slow_kv:
+        m.clear_slow_layer_caches()
     return stats

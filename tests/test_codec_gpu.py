@@ -128,3 +128,58 @@ def test_block_decode_is_bit_identical_to_the_whole_utterance(codec, codec_weigh
         np.testing.assert_array_equal(codec.decode_block_s16(codes, t0, t1), ao.to_i16(blk))
         np.testing.assert_array_equal(codec.decode_block_s16(codes, t0, t1, to_rate=24000),
                                       ao.to_i16(ao.resample(blk, 44100, 24000)))
+
+
+def _digits(idx):
+    idx = np.asarray(idx)
+    return np.stack([idx % 8, (idx // 8) % 5, (idx // 40) % 5, (idx // 200) % 5], -1)
+
+
+def assert_index_mismatches_are_rounding_ties(got, pre, exp, tol=2e-3):
+    """E3 bar (integer output): every index that differs from the oracle's must differ by exactly +-1 in digits whose
+    pre-round value (the oracle's twice-bounded projection, fsq.rs:68-130) lies within `tol` of a rounding boundary x.5;
+    all other digits must agree.  `pre`: (G, L, 4); got/exp: (1, G, L)."""
+    bad = np.argwhere(got != exp)
+    for _, g, l in bad:
+        dg, de = _digits(got[0, g, l]), _digits(exp[0, g, l])
+        for d in range(4):
+            if dg[d] != de[d]:
+                v = float(pre[g, l, d])
+                frac = abs(v - np.floor(v) - 0.5)
+                assert abs(int(dg[d]) - int(de[d])) == 1 and frac <= tol, \
+                    f"group {g} frame {l} digit {d}: {dg[d]} vs {de[d]}, pre-round {v:.6f} is not a tie"
+    return len(bad)
+
+
+def test_fsq_encode_mismatches_are_proven_rounding_ties(codec, codec_weights):
+    """Replaces the blanket mismatch budget of the tests above with a proof per mismatch."""
+    total = 0
+    for Lm in (37, 203, 611):
+        rng = np.random.default_rng(100 + Lm)
+        mel = (rng.standard_normal((1, 160, Lm)) * 2.0 - 4.0).astype(np.float32)
+        with torch.no_grad():
+            pre, exp = ocodec.encode_mel_preround(torch.from_numpy(mel), codec_weights)
+        got = codec.encode_mel(mel)
+        assert got.shape == tuple(exp.shape)
+        n = assert_index_mismatches_are_rounding_ties(got, pre.numpy(), exp.numpy())
+        assert n <= 0.005 * got.size
+        total += got.size
+    assert total > 1500
+
+
+def test_sky_wav_through_the_gpu_front_end(codec, codec_weights):
+    """tests/golden/sky.wav (the reference's tests/resources/sky.wav) through `FireflyCodec::encode` on the GPU: log-mel
+    (160 x 1099) against oracle.mel, codes (1, 8, 274) against the oracle encoder on the oracle's mel."""
+    import wave
+    from oracle import mel as omel
+    with wave.open(os.path.join(os.path.dirname(__file__), "golden", "sky.wav")) as w:
+        pcm = np.frombuffer(w.readframes(w.getnframes()), dtype="<i2").astype(np.float32) / 32768.0
+    exp_mel = omel.log_mel(pcm)
+    got_mel = codec.log_mel(pcm)
+    assert got_mel.shape == (1, 160, 1099)
+    np.testing.assert_allclose(got_mel[0], exp_mel, atol=5e-4, rtol=0)
+    with torch.no_grad():
+        pre, exp = ocodec.encode_mel_preround(torch.from_numpy(exp_mel[None]), codec_weights)
+    got = codec.encode(pcm)
+    assert got.shape == (1, 8, 274)
+    assert_index_mismatches_are_rounding_ties(got, pre.numpy(), exp.numpy())

@@ -225,3 +225,94 @@ def test_output_stage_known_answers():
     assert len(b) == 44 + 6 and b[:4] == b"RIFF" and b[8:16] == b"WAVEfmt "
     assert int.from_bytes(b[4:8], "little") == 36 + 6 and int.from_bytes(b[28:32], "little") == 88200
     assert int.from_bytes(b[40:44], "little") == 6 and b[44:] == np.array([1, -2, 3], "<i2").tobytes()
+
+
+# ---------------------------------------------------------------- loader ground truth held by the reference
+def _read_dims(path):
+    import re
+    out = {}
+    for ln in open(path):
+        m = re.match(r"Name: (\S+), Shape: torch\.Size\(\[([0-9, ]*)\]\)", ln.strip())
+        if m:
+            out[m.group(1)] = tuple(int(x) for x in m.group(2).split(",") if x.strip())
+    return out
+
+
+def test_lm_weight_names_and_shapes_match_the_reference_dump():
+    """docs/llama-weight-dict.txt (Fish 1.2 checkpoint: vocab 32 000, 4 codebooks) lists exactly the tensors
+    `DualARTransformer::load` binds (dual_ar.rs:460-529); the synthetic checkpoint generator -- and with it the C loader,
+    which resolves the same names -- must reproduce every name and shape."""
+    from fish_speech_rs_b200 import synth
+    ref = _read_dims(os.path.join(GOLDEN, "llama_weight_dict_fish12.txt"))
+    assert len(ref) == 203
+    cfg = dict(synth.FISH15, vocab_size=32000, num_codebooks=4, max_seq_len=4096)
+    assert synth.lm_weight_shapes(cfg) == ref
+    # Fish 1.5 only changes the two vocabulary-sized tables and the codebook count
+    got15 = synth.lm_weight_shapes(dict(synth.FISH15))
+    diff = {k for k in got15 if got15[k] != ref.get(k)}
+    assert diff == {"embeddings.weight", "codebook_embeddings.weight", "output.weight"}
+
+
+def test_codec_weight_names_and_shapes_match_the_reference_dump():
+    """docs/weight-dims-default.txt is the Fish 1.2 generator: weight norm un-merged (`parametrizations.weight.original0/1`),
+    no `.conv.` infix, 4 FSQ groups of 128.  Fish >= 1.4 (what csrc/ loads, codec/utils/mod.rs:25-40,83-95): merged weights
+    under `<prefix>.conv.weight|bias`, 8 groups of 64 (codec/config.rs:155-168).  After that documented renaming every
+    tensor of the dump must exist with the same shape, and nothing else may be generated."""
+    import re
+    from fish_speech_rs_b200 import synth
+    ref = _read_dims(os.path.join(GOLDEN, "codec_weight_dims_fish12.txt"))
+    assert len(ref) == 509
+    wrapped = re.compile(r"^(head\.(conv_pre|conv_post|ups\.\d+|resblocks\.\d+\.blocks\.\d+\.convs[12]\.\d+)|"
+                         r"quantizer\.(down|up)sample\.\d+\.0|.*\.dwconv|backbone\.downsample_layers\.0\.0)$")
+    exp = {}
+    for name, shape in ref.items():
+        if name.endswith(".parametrizations.weight.original0"):
+            assert shape[1:] == (1, 1)  # the weight-norm gain g, folded into the merged weight
+            continue
+        if name.endswith(".parametrizations.weight.original1"):
+            base, leaf = name[: -len(".parametrizations.weight.original1")], "weight"
+        else:
+            base, leaf = name.rsplit(".", 1)
+        if "residual_fsq.rvqs." in name:
+            continue  # group count / width differ by config, checked below
+        exp[(base + ".conv." + leaf) if wrapped.match(base) else (base + "." + leaf)] = shape
+    got = synth.codec_weight_shapes(with_encoder=True)
+    got_no_fsq = {k: v for k, v in got.items() if "residual_fsq.rvqs." not in k}
+    # codec/config.rs:146-163: Fish 1.2 has ONE x2 down/up-sampling stage (downsample_factor [2]), >= 1.4 has two ([2, 2]):
+    # the second stage is the only thing the >= 1.4 generator adds, and it repeats the first stage's shapes
+    second = {k for k in got_no_fsq if re.match(r"quantizer\.(down|up)sample\.1\.", k)}
+    assert set(got_no_fsq) - set(exp) == second and len(second) == 2 * 11
+    for k in second:
+        assert got_no_fsq[k] == exp[k.replace("sample.1.", "sample.0.")]
+    assert {k: v for k, v in got_no_fsq.items() if k not in second} == exp
+    # FSQ projections: 4 x (4 <- 128) in the 1.2 dump, 8 x (4 <- 64) for >= 1.4; same tensor set per group
+    leaves = {"project_in.weight", "project_in.bias", "project_out.weight", "project_out.bias"}
+    assert {k.split("rvqs.")[1].split(".", 1)[1] for k in ref if "rvqs." in k} == leaves
+    assert {k.split("rvqs.")[1].split(".", 1)[1] for k in got if "rvqs." in k} == leaves
+    assert ref["quantizer.residual_fsq.rvqs.3.project_in.weight"] == (4, 128)
+    assert got["quantizer.residual_fsq.rvqs.7.project_in.weight"] == (4, 64)
+    assert 4 * 128 == 8 * 64 == 512
+
+
+def _sky_pcm():
+    import wave
+    with wave.open(os.path.join(GOLDEN, "sky.wav")) as w:
+        assert w.getframerate() == 44100 and w.getnchannels() == 1 and w.getsampwidth() == 2
+        raw = w.readframes(w.getnframes())
+    return np.frombuffer(raw, dtype="<i2").astype(np.float32) / 32768.0
+
+
+def test_sky_wav_through_the_oracle_front_end(codec_weights):
+    """The reference's own fixture through the restated front-end: 562 265 samples -> 1099 log-mel frames -> 274 code
+    frames, exactly the length of voices-template/default.npy (the voice the server ships for this very clip)."""
+    from oracle import mel as omel
+    pcm = _sky_pcm()
+    assert pcm.shape == (562265,)
+    m = omel.log_mel(pcm)
+    assert m.shape == (160, 1099) and np.isfinite(m).all()
+    assert m.min() >= np.log(1e-5) - 1e-6 and m.max() <= np.log(100.0) + 1e-6  # the clamp of spectrogram.rs:154-156
+    with torch.no_grad():
+        codes = ocodec.encode_mel(torch.from_numpy(m[None]), codec_weights)
+    voice = np.load(os.path.join(GOLDEN, "default_voice.npy"))
+    assert tuple(codes.shape) == (1, 8, 274) == (1,) + voice.shape
+    assert 0 <= int(codes.min()) and int(codes.max()) < 1000
