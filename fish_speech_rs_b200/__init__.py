@@ -5,6 +5,8 @@ reference's `fish_speech_core::lm` / `fish_speech_core::codec` surface on top of
 """
 from . import _ffi
 from .codec import FireflyCodec
-from .lm import DualARTransformer, SamplingArgs, generate_blocking, generate_static_batch
+from .lm import (DualARTransformer, SamplingArgs, generate_blocking, generate_blocking_with_hidden,
+                 generate_static_batch)
 
-__all__ = ["DualARTransformer", "FireflyCodec", "SamplingArgs", "generate_blocking", "generate_static_batch", "_ffi"]
+__all__ = ["DualARTransformer", "FireflyCodec", "SamplingArgs", "generate_blocking", "generate_blocking_with_hidden",
+           "generate_static_batch", "_ffi"]

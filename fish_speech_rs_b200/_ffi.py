@@ -85,6 +85,9 @@ SYMBOLS = {
     "fsb_lm_curr_kv_size": (C.c_int, [C.c_void_p, P(C.c_size_t)]),
     "fsb_lm_generate_blocking": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_size_t, P(fsb_sampling_args),
                                            C.c_uint32, C.c_int32, C.c_void_p, C.c_size_t, P(C.c_size_t)]),
+    "fsb_lm_generate_blocking_with_hidden": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_size_t, P(fsb_sampling_args),
+                                                       C.c_uint32, C.c_int32, C.c_void_p, C.c_size_t, P(C.c_size_t),
+                                                       C.c_void_p, C.c_size_t, P(C.c_size_t)]),
     "fsb_lm_generate_static_batch": (C.c_int, [C.c_void_p, P(C.c_void_p), P(C.c_int32), C.c_int32, C.c_size_t,
                                                P(fsb_sampling_args), C.c_uint32, C.c_int32, P(C.c_void_p),
                                                C.c_size_t, P(C.c_size_t)]),

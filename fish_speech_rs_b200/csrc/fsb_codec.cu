@@ -3,7 +3,12 @@
 #include <algorithm>
 #include <memory>
 
+#include <cuda.h>
+
+#include <tuple>
+
 #include "fsb_codec_kernels.cuh"
+#include "fsb_tc_gemm.cuh"
 
 namespace fsb {
 
@@ -11,6 +16,8 @@ struct ConvW {
     float *wt = nullptr;  // (Cin, K, Cout)
     float *bias = nullptr;
     int Cin = 0, Cout = 0, K = 0;
+    float *wt_tiled = nullptr;  // ResBlock convs: [C / BM][C / 16][16][K][BM] (one contiguous block per TMA bulk copy)
+    int tile_bm = 0;
 };
 
 struct ConvNeXtW {
@@ -54,7 +61,9 @@ struct fsb_codec {
     int max_frames = 0;
     uint32_t *d_codes = nullptr;
     int *d_err = nullptr;
-    float *buf[4] = {};  // 4 activation buffers of 32768 * max_frames floats
+    float *buf[6] = {};  // activation buffers of 32768 * max_frames floats (4 raw + 2 pre-activated copies for the TMA convs)
+    bool res_tma = false;  // ResBlock convs run on resconv_tma_kernel
+    std::map<std::tuple<const void *, int, int, int>, TcMap> xmaps;  // (buffer, C, L, span) -> tensor map
     float *cn_h = nullptr, *cn_g = nullptr;
     long long *d_idx = nullptr;
     double *d_tw = nullptr;   // STFT twiddles (cos | sin), encoder only
@@ -107,6 +116,17 @@ __global__ void relayout_012_to_021(const float *__restrict__ src, float *__rest
     }
 }
 
+// (Cout, Cin, K) -> [Cout / BM][Cin / 16][16][K][BM]
+__global__ void relayout_res_tiled(const float *__restrict__ src, float *__restrict__ dst, int C, int K, int BM) {
+    const size_t n = (size_t)C * C * K;
+    const int nch = C / kResCK;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int k = (int)(i % K), ci = (int)((i / K) % C), co = (int)(i / ((size_t)C * K));
+        const int ct = co / BM, col = co % BM, ch = ci / kResCK, cil = ci % kResCK;
+        dst[((((size_t)ct * nch + ch) * kResCK + cil) * K + k) * BM + col] = src[i];
+    }
+}
+
 static int load_vec(fsb_codec *c, const fsb_tensor *w, size_t n, const std::string &name, std::vector<int64_t> shape,
                     float **out) {
     DevTensor t;
@@ -117,7 +137,7 @@ static int load_vec(fsb_codec *c, const fsb_tensor *w, size_t n, const std::stri
 
 // Conv1d weight (Cout, Cin, K) / ConvTranspose1d weight (Cin, Cout, K) -> ConvW
 static int load_conv(fsb_codec *c, const fsb_tensor *w, size_t n, const std::string &prefix, int Cin, int Cout, int K,
-                     bool transposed, ConvW *out) {
+                     bool transposed, ConvW *out, bool res_tiled = false) {
     DevTensor raw;
     std::vector<void *> tmp_owned;
     std::vector<int64_t> shape = transposed ? std::vector<int64_t>{Cin, Cout, K} : std::vector<int64_t>{Cout, Cin, K};
@@ -128,6 +148,16 @@ static int load_conv(fsb_codec *c, const fsb_tensor *w, size_t n, const std::str
     if (st == FSB_OK) {
         if (transposed) relayout_012_to_021<<<256, 256, 0, c->stream>>>((const float *)raw.ptr, dst, Cin, Cout, K);
         else relayout_021_to_120<<<256, 256, 0, c->stream>>>((const float *)raw.ptr, dst, Cout, Cin, K);
+        if (res_tiled && !transposed && Cin == Cout && Cin % kResCK == 0) {
+            // second copy for resconv_tma_kernel: [C / BM][C / 16][16][K][BM], BM = min(64, C)
+            float *tl = nullptr;
+            st = calloc_dev(c, &tl, (size_t)Cin * Cout * K);
+            if (st == FSB_OK) {
+                out->tile_bm = std::min(64, Cout);
+                relayout_res_tiled<<<256, 256, 0, c->stream>>>((const float *)raw.ptr, tl, Cin, K, out->tile_bm);
+                out->wt_tiled = tl;
+            }
+        }
         cudaError_t e = cudaGetLastError();
         if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
         if (e != cudaSuccess) {
@@ -220,6 +250,54 @@ static int log_mel_to_device(fsb_codec *c, const float *pcm, long long n, int *L
     return FSB_OK;
 }
 
+// one ResBlock conv (C -> C, causal, dilation d) on pre-activated input `xact`
+static int res_conv_tma(fsb_codec *c, const ConvW &w, const float *xact, int L, int dil, const float *res, float *y,
+                        float *y_act, int acc_mode, float scale) {
+    const int C = w.Cin, K = w.K, BM = w.tile_bm;
+    const int span = res_span(K, dil);
+    auto key = std::make_tuple((const void *)xact, C, L, span);
+    auto it = c->xmaps.find(key);
+    if (it == c->xmaps.end()) {
+        TcMap m;
+        FSB_TRY(tc_make_map_f32_2d(&m, xact, (uint64_t)C, (uint64_t)L, (uint32_t)span, (uint32_t)kResCK));
+        it = c->xmaps.emplace(key, m).first;
+    }
+    ResConvArgs a;
+    a.wt = w.wt_tiled; a.bias = w.bias; a.res = res; a.y = y; a.y_act = y_act;
+    a.C = C; a.L = L; a.acc_mode = acc_mode; a.scale = scale;
+    const dim3 grid((L + kResBN - 1) / kResBN, C / BM);
+#define RES_LAUNCH(BMv, KTv, DILv)                                                                                   \
+    {                                                                                                                \
+        const size_t smem = (size_t)2 * res_stage_floats(BMv, KTv, DILv) * sizeof(float) + 128;                      \
+        static bool attr_done = false;                                                                               \
+        if (!attr_done && smem > 48 * 1024) {                                                                        \
+            FSB_CUDA_OK(cudaFuncSetAttribute(resconv_tma_kernel<BMv, KTv, DILv>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            attr_done = true;                                                                                        \
+        }                                                                                                            \
+        resconv_tma_kernel<BMv, KTv, DILv><<<grid, 256, smem, c->stream>>>(*reinterpret_cast<const CUtensorMap *>(&it->second), a); \
+    }
+#define RES_DIL(BMv, KTv)                                        \
+    switch (dil) {                                               \
+        case 1: RES_LAUNCH(BMv, KTv, 1) break;                   \
+        case 3: RES_LAUNCH(BMv, KTv, 3) break;                   \
+        default: RES_LAUNCH(BMv, KTv, 5) break;                  \
+    }
+#define RES_K(BMv)                                               \
+    switch (K) {                                                 \
+        case 3: RES_DIL(BMv, 3) break;                           \
+        case 7: RES_DIL(BMv, 7) break;                           \
+        default: RES_DIL(BMv, 11) break;                         \
+    }
+    if (BM == 64) RES_K(64)
+    else if (BM == 32) RES_K(32)
+    else RES_K(16)
+#undef RES_K
+#undef RES_DIL
+#undef RES_LAUNCH
+    CLAUNCH_CHECK(c);
+    return FSB_OK;
+}
+
 // ---------------------------------------------------------------- launches
 static int launch_conv(fsb_codec *c, ConvArgs a, int nz = 1) {
     const int off_lo = std::min(0, (a.K - 1) * a.dil) - a.pad, off_hi = std::max(0, (a.K - 1) * a.dil) - a.pad;
@@ -261,7 +339,8 @@ static int launch_conv(fsb_codec *c, ConvArgs a, int nz = 1) {
 
 // FishConvNet::forward: y (Cout, Lout) = conv(x (Cin, Lin)), Lout = (Lin + pad - (K-1)*dil - 1)/stride + 1 == Lin/stride
 static int conv_fwd(fsb_codec *c, const ConvW &w, const float *x, int Lin, float *y, int dil, int stride,
-                    bool pre_silu, const float *res, int acc_mode, float scale, bool post_tanh, int *Lout_out) {
+                    bool pre_silu, const float *res, int acc_mode, float scale, bool post_tanh, int *Lout_out,
+                    float *y_act = nullptr) {
     ConvArgs a;
     memset(&a, 0, sizeof(a));
     const int pad = (w.K - 1) * dil + 1 - stride;  // utils/mod.rs:43,55
@@ -271,12 +350,14 @@ static int conv_fwd(fsb_codec *c, const ConvW &w, const float *x, int Lin, float
     a.K = w.K; a.Kw = w.K; a.k0 = 0; a.kstep = 1;
     a.dil = dil; a.pad = pad; a.stride = stride; a.ostride = 1; a.ooff = 0;
     a.pre_silu = pre_silu; a.acc_mode = acc_mode; a.scale = scale; a.post_tanh = post_tanh;
+    a.y_act = y_act;
     if (Lout_out) *Lout_out = Lout;
     return launch_conv(c, a);
 }
 
 // FishTransConvNet::forward: y (Cout, Lin*stride); kernel K in {stride, 2*stride}
-static int convT_fwd(fsb_codec *c, const ConvW &w, const float *x, int Lin, float *y, int stride, bool pre_silu) {
+static int convT_fwd(fsb_codec *c, const ConvW &w, const float *x, int Lin, float *y, int stride, bool pre_silu,
+                     float *y_act = nullptr) {
     FSB_REQUIRE(w.K == stride || w.K == 2 * stride, FSB_ERR_UNSUPPORTED, "ConvTranspose1d k=%d s=%d unsupported", w.K,
                 stride);
     // one launch, one grid.z slice per output phase r (= t mod stride): taps {r, r + stride}
@@ -288,6 +369,7 @@ static int convT_fwd(fsb_codec *c, const ConvW &w, const float *x, int Lin, floa
     a.dil = -1; a.pad = 0; a.stride = 1; a.ostride = stride; a.ooff = 0;
     a.z_k0 = 1; a.z_ooff = 1;
     a.pre_silu = pre_silu;
+    a.y_act = y_act;
     return launch_conv(c, a, stride);
 }
 
@@ -330,6 +412,28 @@ static int decode_device(fsb_codec *c, int T, float *pcm_dev_out /* device (2048
     const float third = (float)(1.0 / 3.0);
     for (int i = 0; i < 5; ++i) {
         float *M = cur, *U = nxt;
+        if (c->res_tma) {
+            // TMA-staged ResBlock convs read pre-activated inputs: every producer also writes silu(result) where its
+            // consumer applies silu (hifi_gan.rs:76-79): SU = silu(U), SR = silu(R), X1 holds silu(conv1 output) only
+            float *SU = c->buf[4], *SR = c->buf[5];
+            FSB_TRY(convT_fwd(c, c->ups[i], M, L, U, kUpRates[i], true, SU));
+            L *= kUpRates[i];
+            for (int j = 0; j < 3; ++j) {
+                const float *xin = U, *xin_act = SU;
+                for (int m = 0; m < 3; ++m) {
+                    const int d = kResDilations[m];
+                    FSB_TRY(res_conv_tma(c, c->res_c1[i][j][m], xin_act, L, d, nullptr, nullptr, X1, 0, 0.f));
+                    if (m < 2) {
+                        FSB_TRY(res_conv_tma(c, c->res_c2[i][j][m], X1, L, d, xin, R, SR, 0, 0.f));
+                        xin = R;
+                        xin_act = SR;
+                    } else {
+                        FSB_TRY(res_conv_tma(c, c->res_c2[i][j][m], X1, L, d, xin, M, nullptr, j == 0 ? 0 : (j == 1 ? 1 : 2), third));
+                    }
+                }
+            }
+            continue;
+        }
         FSB_TRY(convT_fwd(c, c->ups[i], M, L, U, kUpRates[i], true));
         L *= kUpRates[i];
         for (int j = 0; j < 3; ++j) {
@@ -396,9 +500,9 @@ static int codec_create_impl(fsb_codec *c, const fsb_tensor *w, size_t n) {
             for (int m = 0; m < 3; ++m) {
                 const std::string p = "head.resblocks." + std::to_string(i) + ".blocks." + std::to_string(j) + ".";
                 FSB_TRY(load_conv(c, w, n, p + "convs1." + std::to_string(m) + ".conv", cout, cout, kResKernels[j], false,
-                                  &c->res_c1[i][j][m]));
+                                  &c->res_c1[i][j][m], true));
                 FSB_TRY(load_conv(c, w, n, p + "convs2." + std::to_string(m) + ".conv", cout, cout, kResKernels[j], false,
-                                  &c->res_c2[i][j][m]));
+                                  &c->res_c2[i][j][m], true));
             }
     }
     FSB_TRY(load_conv(c, w, n, "head.conv_post.conv", 16, 1, 13, false, &c->conv_post));
@@ -442,7 +546,8 @@ static int codec_create_impl(fsb_codec *c, const fsb_tensor *w, size_t n) {
     const size_t T = (size_t)c->max_frames;
     FSB_TRY(calloc_dev(c, &c->d_codes, (size_t)kGroups * T));
     FSB_TRY(calloc_dev(c, &c->d_err, 1));
-    for (int i = 0; i < 4; ++i) FSB_TRY(calloc_dev(c, &c->buf[i], 32768 * T));
+    c->res_tma = getenv("FSB_CODEC_NO_TMA") == nullptr;
+    for (int i = 0; i < (c->res_tma ? 6 : 4); ++i) FSB_TRY(calloc_dev(c, &c->buf[i], 32768 * T));
     FSB_TRY(calloc_dev(c, &c->cn_h, 4 * T * kDim));
     FSB_TRY(calloc_dev(c, &c->cn_g, 4 * T * kDim * 4));
     FSB_TRY(calloc_dev(c, &c->d_idx, (size_t)kGroups * T));

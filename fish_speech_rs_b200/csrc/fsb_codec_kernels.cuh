@@ -75,6 +75,7 @@ struct ConvArgs {
     int acc_mode;              // 0: y = v;  1: y = y + v;  2: y = (y + v) * scale   (stack + mean, hifi_gan.rs:113-118)
     float scale;
     int post_tanh;             // hifi_gan.rs:215
+    float *y_act;              // optional second output: silu(result), same layout as y (input of a TMA-staged ResBlock conv)
 };
 
 constexpr int kConvCK = 16;  // input channels staged per step (fewer load-sync-compute rounds: the global loads of a round are exposed)
@@ -182,6 +183,144 @@ __global__ void __launch_bounds__(256) conv1d_kernel(ConvArgs a) {
             else if (a.acc_mode == 2) v = (a.y[o] + v) * a.scale;
             if (a.post_tanh) v = tanhf(v);
             a.y[o] = v;
+            if (a.y_act) a.y_act[o] = silu_f(v);
+        }
+    }
+}
+
+// ------------------------------------------------------------------ ResBlock1 convs with TMA-staged tiles
+// ResBlock1::forward (hifi_gan.rs:73-86): x += conv2_d(silu(conv1_d(silu(x)))), both convs causal with dilation d, C -> C
+// channels.  These 90 convs are 95 % of the vocoder's MACs.  Same FP32 FMA implicit GEMM as conv1d_kernel (BM x 128
+// output tile, TM x 4 per thread), but the tiles are moved by the TMA engine into a two-stage shared-memory ring while the
+// previous chunk is multiplied:
+//   * weights are re-laid out at load time as [co tile][ci chunk][ci][k][BM]: the (CK ci x K taps x BM co) block of a
+//     chunk is ONE contiguous cp.async.bulk;
+//   * the input tile (CK ci x span t) is ONE cp.async.bulk.tensor.2d on a (C, L) tensor map; columns left of t = 0 are
+//     out of bounds and arrive as zeros -- the causal left padding of FishConvNet (utils/mod.rs:53-63) for free;
+//   * the input is stored pre-activated by its producer (y_act of the previous conv), so nothing is computed at staging
+//     time; the epilogue writes the raw result (residual stream / mean accumulator) and/or silu(result) for its consumer.
+struct ResConvArgs {
+    const float *wt;    // tiled weights [C / BM][C / CK][CK][K][BM]
+    const float *bias;  // (C)
+    const float *res;   // (C, L) residual (raw x), or null
+    float *y;           // (C, L) raw result, or null (conv1: only silu(result) is ever read)
+    float *y_act;       // (C, L) silu(result), or null
+    int C, L;
+    int acc_mode;       // 0: y = v;  1: y = y + v;  2: y = (y + v) * scale   (stack + mean, hifi_gan.rs:113-118)
+    float scale;
+};
+constexpr int kResCK = 16;    // input channels per chunk
+constexpr int kResBN = 128;   // time positions per tile
+
+__device__ __forceinline__ uint32_t rc_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// The TMA box must START on a 16-byte boundary (measured with tools/tma_probe.cu: a start column of -2 traps with
+// "illegal instruction", -4 works), so the left halo (K - 1) * d is rounded up to a multiple of 4 columns.
+__host__ __device__ constexpr int res_halo(int KT, int DIL) { return ((KT - 1) * DIL + 3) & ~3; }
+__host__ __device__ constexpr int res_span(int KT, int DIL) { return kResBN + res_halo(KT, DIL); }
+__host__ __device__ constexpr int res_stage_floats(int BM, int KT, int DIL) {
+    return (kResCK * KT * BM + kResCK * res_span(KT, DIL) + 31) & ~31;  // 128-byte aligned stages
+}
+
+template <int BM, int KT, int DIL>
+__global__ void __launch_bounds__(256) resconv_tma_kernel(const __grid_constant__ CUtensorMap tmx, ResConvArgs a) {
+    constexpr int TM = BM / 8, TN = 4, NTX = 32;
+    constexpr int SPAN = res_span(KT, DIL);
+    constexpr int W_FLOATS = kResCK * KT * BM, X_FLOATS = kResCK * SPAN, STAGE = res_stage_floats(BM, KT, DIL);
+    extern __shared__ float rc_smem_raw[];
+    // TMA destinations need 128-byte alignment (dynamic shared memory only guarantees 16)
+    float *rc_smem = rc_smem_raw + (((128u - (rc_smem_u32(rc_smem_raw) & 127u)) & 127u) >> 2);
+    __shared__ __align__(8) unsigned long long full[2];
+    const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+    const int t0 = blockIdx.x * kResBN, co0 = blockIdx.y * BM;
+    const int nchunk = a.C / kResCK;
+    const float *wsrc = a.wt + (size_t)blockIdx.y * nchunk * W_FLOATS;
+    const CUtensorMap *pmap = &tmx;  // address of the __grid_constant__ parameter itself (never a local copy)
+    const uint32_t bar0 = rc_smem_u32(&full[0]);
+    const int xcol0 = t0 - res_halo(KT, DIL);
+    auto issue = [=](int c) {  // chunk c -> stage c & 1 (one thread)
+        float *st = rc_smem + (c & 1) * STAGE;
+        const uint32_t bar = bar0 + (c & 1) * 8;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((W_FLOATS + X_FLOATS) * 4) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(rc_smem_u32(st)),
+                     "l"(wsrc + (size_t)c * W_FLOATS), "r"(W_FLOATS * 4), "r"(bar)
+                     : "memory");
+        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+                         rc_smem_u32(st + W_FLOATS)),
+                     "l"(pmap), "r"(bar), "r"(xcol0), "r"(c * kResCK)
+                     : "memory");
+    };
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(rc_smem_u32(&full[0])));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(rc_smem_u32(&full[1])));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        issue(0);
+    }
+    __syncthreads();
+    float acc[TM][TN];
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+    for (int c = 0; c < nchunk; ++c) {
+        if (tid == 0 && c + 1 < nchunk) issue(c + 1);  // stage (c + 1) & 1 was released by the barrier below
+        {
+            const uint32_t bar = rc_smem_u32(&full[c & 1]), parity = (uint32_t)(c >> 1) & 1u;
+            asm volatile(
+                "{\n\t"
+                ".reg .pred p;\n\t"
+                "WAIT_%=:\n\t"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+                "@p bra DONE_%=;\n\t"
+                "bra WAIT_%=;\n\t"
+                "DONE_%=:\n\t"
+                "}\n" ::"r"(bar),
+                "r"(parity)
+                : "memory");
+        }
+        const float *ws = rc_smem + (c & 1) * STAGE, *xs = ws + W_FLOATS;
+#pragma unroll 2
+        for (int ci = 0; ci < kResCK; ++ci) {
+            const float *wrow = ws + ci * KT * BM + ty * TM;
+            // xrow[j * 32 + k * DIL]: tile column 0 == t0 - halo (rounded up), tap 0 of output t reads column t - (KT - 1) * DIL
+            const float *xrow = xs + ci * SPAN + tx + (res_halo(KT, DIL) - (KT - 1) * DIL);
+#pragma unroll
+            for (int k = 0; k < KT; ++k) {
+                float w[TM], xv[TN];
+                if (TM % 4 == 0) {
+#pragma unroll
+                    for (int i = 0; i < TM; i += 4) {
+                        const float4 w4 = *reinterpret_cast<const float4 *>(wrow + k * BM + i);
+                        w[i] = w4.x; w[i + 1] = w4.y; w[i + 2] = w4.z; w[i + 3] = w4.w;
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < TM; ++i) w[i] = wrow[k * BM + i];
+                }
+#pragma unroll
+                for (int j = 0; j < TN; ++j) xv[j] = xrow[j * NTX + k * DIL];
+#pragma unroll
+                for (int i = 0; i < TM; ++i)
+#pragma unroll
+                    for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(w[i], xv[j], acc[i][j]);
+            }
+        }
+        __syncthreads();  // everybody is done with stage c & 1: it may be refilled with chunk c + 2
+    }
+#pragma unroll
+    for (int i = 0; i < TM; ++i) {
+        const int co = co0 + ty * TM + i;
+        const float bv = a.bias[co];
+#pragma unroll
+        for (int j = 0; j < TN; ++j) {
+            const int t = t0 + tx + j * NTX;
+            if (t >= a.L) continue;
+            const size_t o = (size_t)co * a.L + t;
+            float v = acc[i][j] + bv;
+            if (a.res) v = a.res[o] + v;
+            if (a.acc_mode == 1) v = a.y[o] + v;
+            else if (a.acc_mode == 2) v = (a.y[o] + v) * a.scale;
+            if (a.y) a.y[o] = v;
+            if (a.y_act) a.y_act[o] = silu_f(v);
         }
     }
 }

@@ -58,8 +58,10 @@ struct fsb_lm {
     GenState *d_st = nullptr;
     std::vector<int> kv_len;  // host mirror of pos[] between calls
     int *h_pin = nullptr;     // pinned staging (ints)
-    std::map<int, cudaGraphExec_t> frame_graphs;  // keyed by bsz
+    std::map<int, cudaGraphExec_t> frame_graphs;  // keyed by bsz (+ 4096 when hidden states are collected)
     std::map<int, cudaGraphExec_t> tail_graphs;
+    bool collect_hidden = false;  // generate_blocking_with_hidden: per-op path + store_hidden_kernel per frame
+    float *hid = nullptr;         // (max_batch, out_cap, D), allocated on first use
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
     fsb_lm_stats stats;
     uint64_t launches = 0;
@@ -168,6 +170,9 @@ static cudaError_t init_gemv_attrs_epi(int bytes) {
     return e;
 }
 static cudaError_t init_gemv_attrs(int max_k) {
+    static int max_k_set = 0;  // process-wide, monotonic (see the sampler attributes in lm_create_impl)
+    if (max_k <= max_k_set) return cudaSuccess;
+    max_k_set = max_k;
     const int bytes = 8 * max_k * (int)sizeof(float);
     cudaError_t e = init_gemv_attrs_epi<float, EPI_STORE>(bytes);
     if (e == cudaSuccess) e = init_gemv_attrs_epi<float, EPI_RESID>(bytes);
@@ -404,6 +409,10 @@ static size_t sample_smem(int n) {
 static int frame_tail(fsb_lm *lm, int nb) {
     Scratch &s = lm->s;
     const int *na = lm->h_st.n_active;
+    if (lm->collect_hidden) {
+        store_hidden_kernel<<<nb, 256, 0, lm->stream>>>(s.hidden, lm->d_st, lm->hid, lm->D);
+        LAUNCH_CHECK(lm);
+    }
     FSB_TRY(slow_head(lm, nb, na));
     sample_slow_kernel<<<nb, kSampleThreads, sample_smem(lm->n_slow_logits), lm->stream>>>(
         s.slow_logits, lm->n_slow_logits, lm->n_slow_logits, lm->d_st, lm->tok.semantic_start_id, s.hidden, s.fast_x,
@@ -439,7 +448,8 @@ static int decode_frame(fsb_lm *lm, int nb) {
 
 static int get_graph(fsb_lm *lm, std::map<int, cudaGraphExec_t> &cache, int nb, bool with_slow,
                      cudaGraphExec_t *out) {
-    auto it = cache.find(nb);
+    const int key = nb + (lm->collect_hidden ? 4096 : 0);
+    auto it = cache.find(key);
     if (it != cache.end()) {
         *out = it->second;
         return FSB_OK;
@@ -459,14 +469,14 @@ static int get_graph(fsb_lm *lm, std::map<int, cudaGraphExec_t> &cache, int nb, 
     cudaGraphExec_t ge = nullptr;
     FSB_CUDA_OK(cudaGraphInstantiate(&ge, g, 0));
     cudaGraphDestroy(g);
-    cache[nb] = ge;
+    cache[key] = ge;
     // remember how many kernels one replay launches
-    cache[-nb - 1] = reinterpret_cast<cudaGraphExec_t>((uintptr_t)per_graph);
+    cache[-key - 1] = reinterpret_cast<cudaGraphExec_t>((uintptr_t)per_graph);
     *out = ge;
     return FSB_OK;
 }
-static uint64_t graph_launches(std::map<int, cudaGraphExec_t> &cache, int nb) {
-    return (uint64_t)(uintptr_t)cache[-nb - 1];
+static uint64_t graph_launches(fsb_lm *lm, std::map<int, cudaGraphExec_t> &cache, int nb) {
+    return (uint64_t)(uintptr_t)cache[-(nb + (lm->collect_hidden ? 4096 : 0)) - 1];
 }
 
 // ---------------------------------------------------------------- megakernel host side
@@ -866,10 +876,16 @@ static int lm_create_impl(fsb_lm *lm, const fsb_tensor *w, size_t n) {
         const int sm = (int)sample_smem(std::max(lm->n_slow_logits, CS));
         FSB_REQUIRE(std::max(lm->n_slow_logits, CS) <= kSampleMaxN, FSB_ERR_UNSUPPORTED,
                     "constrained head of %d rows exceeds the block sampler", lm->n_slow_logits);
-        FSB_CUDA_OK(cudaFuncSetAttribute(sample_slow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
-        FSB_CUDA_OK(cudaFuncSetAttribute(sample_fast_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
-        FSB_CUDA_OK(
-            cudaFuncSetAttribute(sample_fast_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+        // the attribute is per kernel and per process, shared by every live handle: only ever raise it (a handle with a
+        // smaller head must not lower the limit under another handle's launches)
+        static int sm_max = 0;
+        if (sm > sm_max) {
+            FSB_CUDA_OK(cudaFuncSetAttribute(sample_slow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+            FSB_CUDA_OK(cudaFuncSetAttribute(sample_fast_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+            FSB_CUDA_OK(
+                cudaFuncSetAttribute(sample_fast_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+            sm_max = sm;
+        }
     }
     FSB_REQUIRE(std::max(lm->D, lm->I) * 32 <= 227 * 1024, FSB_ERR_UNSUPPORTED, "dim/intermediate_size too large");
     FSB_CUDA_OK(init_gemv_attrs(std::max(lm->D, lm->I)));
@@ -1012,7 +1028,7 @@ static int generate_impl(fsb_lm *lm, const uint32_t *const *prompts, const int32
     }
     int total_max = 0;
     for (int b = 0; b < bsz; ++b) total_max = std::max(total_max, max_frames[b]);
-    bool use_mega = lm->mega_ok && lm->opt.decode_mode != 1 && !lm->profile;
+    bool use_mega = lm->mega_ok && lm->opt.decode_mode != 1 && !lm->profile && !lm->collect_hidden;
     int group = 8;  // rows per megakernel launch: the largest batch template whose shared memory fits
     // wide batches (cfg3 / cfg5): ONE tcgen05 megakernel launch for all rows (fsb_lm_megab.cuh)
     int megab_min = 9;
@@ -1030,7 +1046,7 @@ static int generate_impl(fsb_lm *lm, const uint32_t *const *prompts, const int32
         // auto mode: one launch only (rows beyond a group are better served by the per-op GEMV path)
         if (lm->opt.decode_mode == 0 && bsz > group) use_mega = false;
     }
-    FSB_REQUIRE(use_mega || lm->opt.decode_mode != 2 || lm->profile, FSB_ERR_UNSUPPORTED,
+    FSB_REQUIRE(use_mega || lm->opt.decode_mode != 2 || lm->profile || lm->collect_hidden, FSB_ERR_UNSUPPORTED,
                 "decode_mode 2 (megakernel) needs bsz <= 8 (<= 32 with bf16 Fish shapes) and cooperative launch support");
     if (use_megab) {
         // launched above
@@ -1055,13 +1071,13 @@ static int generate_impl(fsb_lm *lm, const uint32_t *const *prompts, const int32
             cudaGraphExec_t tg;
             FSB_TRY(get_graph(lm, lm->tail_graphs, bsz, false, &tg));
             FSB_CUDA_OK(cudaGraphLaunch(tg, st));
-            graph_l += graph_launches(lm->tail_graphs, bsz);
+            graph_l += graph_launches(lm, lm->tail_graphs, bsz);
         }
         FSB_CUDA_OK(cudaEventRecord(lm->ev1, st));
         // ---- frame loop ----
         cudaGraphExec_t fg;
         FSB_TRY(get_graph(lm, lm->frame_graphs, bsz, true, &fg));
-        const uint64_t per_frame = graph_launches(lm->frame_graphs, bsz);
+        const uint64_t per_frame = graph_launches(lm, lm->frame_graphs, bsz);
         const int kPoll = 16;
         int launched = 1;
         if (lm->profile) {
@@ -1412,6 +1428,33 @@ int fsb_lm_generate_blocking(fsb_lm *lm, const uint32_t *prompt, int32_t prompt_
     uint32_t *outs[1] = {out_codes};
     return finish(lm, generate_impl(lm, prompts, &prompt_len, 1, max_new_tokens, sampling, flags, fixed_len, outs, cap,
                                     out_len));
+}
+
+int fsb_lm_generate_blocking_with_hidden(fsb_lm *lm, const uint32_t *prompt, int32_t prompt_len, size_t max_new_tokens,
+                                         const fsb_sampling_args *sampling, uint32_t flags, int32_t fixed_len,
+                                         uint32_t *out_codes, size_t cap, size_t *out_len, float *hidden,
+                                         size_t hidden_cap, size_t *n_hidden) {
+    FSB_TRY(check_handle(lm));
+    FSB_REQUIRE(hidden && n_hidden, FSB_ERR_INVALID, "generate_blocking_with_hidden: null hidden buffer");
+    if (!lm->hid) FSB_TRY(dev_alloc(lm, &lm->hid, (size_t)lm->max_batch * lm->h_st.out_cap * lm->D));
+    const uint32_t *prompts[1] = {prompt};
+    uint32_t *outs[1] = {out_codes};
+    lm->collect_hidden = true;
+    int st = generate_impl(lm, prompts, &prompt_len, 1, max_new_tokens, sampling, flags, fixed_len, outs, cap, out_len);
+    lm->collect_hidden = false;
+    if (st == FSB_OK) {
+        int nf = 0;
+        FSB_CUDA_OK(cudaMemcpy(&nf, lm->h_st.frame, sizeof(int), cudaMemcpyDeviceToHost));
+        if ((size_t)nf > hidden_cap) {
+            set_error("generate_blocking_with_hidden: %d frames exceed the hidden capacity %zu", nf, hidden_cap);
+            st = FSB_ERR_INVALID;
+        } else {
+            // every yielded frame, <|im_end|> frames included (single_batch.rs:268-270): (T, 1, D)
+            FSB_CUDA_OK(cudaMemcpy(hidden, lm->hid, (size_t)nf * lm->D * sizeof(float), cudaMemcpyDeviceToHost));
+            *n_hidden = (size_t)nf;
+        }
+    }
+    return finish(lm, st);
 }
 
 int fsb_lm_generate_static_batch(fsb_lm *lm, const uint32_t *const *prompts, const int32_t *prompt_lens,

@@ -30,6 +30,19 @@ __global__ void embed_sum_kernel(const uint32_t *__restrict__ toks, int S, int C
     }
 }
 
+// ------------------------------------------------------------------ hidden-state collection
+// generate_blocking_with_hidden, single_batch.rs:251,268-270: the pre-norm slow hidden state of every yielded frame
+// (the one handed to the fast stack, Q1).  hid: (B, out_cap, D); frame index = frames emitted so far.
+__global__ void store_hidden_kernel(const float *__restrict__ hidden, const GenState *st, float *__restrict__ hid, int D) {
+    if (*st->n_active == 0) return;
+    const int b = blockIdx.x;
+    if (!st->active[b]) return;
+    const int f = st->frame[b];
+    if (f >= st->out_cap) return;
+    for (int d = threadIdx.x; d < D; d += blockDim.x)
+        hid[((size_t)b * st->out_cap + f) * D + d] = hidden[(size_t)b * D + d];
+}
+
 // ------------------------------------------------------------------ GEMV
 // y[b, r] = epilogue( W[r, :] . xn[b, :] ),  xn = rms_norm(x[b]) * g  (optional)
 // replaces RmsNorm + Linear (+ residual / silu*mul), :160-165,289,383,429-440.

@@ -295,6 +295,22 @@ int tc_make_map_bf16(TcMap *out, const void *base, int rows, int K, int box_rows
     return FSB_OK;
 }
 
+int tc_make_map_f32_2d(TcMap *out, const void *base, uint64_t rows, uint64_t cols, uint32_t box_cols, uint32_t box_rows) {
+    PFN_encodeTiled enc = get_encode();
+    FSB_REQUIRE(enc != nullptr, FSB_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+    FSB_REQUIRE(cols % 4 == 0 && box_cols % 4 == 0 && box_cols <= 256 && box_rows <= 256, FSB_ERR_UNSUPPORTED,
+                "f32 tensor map: cols %llu / box %u x %u unsupported", (unsigned long long)cols, box_cols, box_rows);
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)cols * 4};
+    cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(reinterpret_cast<CUtensorMap *>(out), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void *>(base), dims,
+                     strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    FSB_REQUIRE(r == CUDA_SUCCESS, FSB_ERR_CUDA, "cuTensorMapEncodeTiled (f32) failed (%d)", (int)r);
+    return FSB_OK;
+}
+
 int tc_pick_bn(int P) { return P <= 32 ? 32 : (P <= 256 ? 64 : 128); }
 
 int tc_split3(const float *x, __nv_bfloat16 *out, size_t n, size_t seg_elems, cudaStream_t st) {

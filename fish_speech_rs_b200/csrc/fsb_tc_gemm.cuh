@@ -11,6 +11,9 @@ struct alignas(64) TcMap {
 
 // tensor map of a row-major (rows, K) bf16 matrix, box = (64 k, box_rows), 128-byte swizzle
 int tc_make_map_bf16(TcMap *out, const void *base, int rows, int K, int box_rows);
+// tensor map of a row-major (rows, cols) f32 matrix, box = (box_cols, box_rows), no swizzle, out-of-bounds elements
+// read as zero (the vocoder's causal left padding)
+int tc_make_map_f32_2d(TcMap *out, const void *base, uint64_t rows, uint64_t cols, uint32_t box_cols, uint32_t box_rows);
 // N tile (prompt positions per CTA) for a prompt chunk of P rows
 int tc_pick_bn(int P);
 // x (n elements, f32) -> hi | mid | lo bf16 copies at element offsets 0, seg_elems, 2 * seg_elems

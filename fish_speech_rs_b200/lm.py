@@ -149,6 +149,26 @@ def generate_blocking(model: DualARTransformer, prompt: np.ndarray, max_new_toke
     return out[:, : n.value].copy()
 
 
+def generate_blocking_with_hidden(model: DualARTransformer, prompt: np.ndarray, max_new_tokens: int,
+                                  sampling_args: SamplingArgs, fixed_len: Optional[int] = None
+                                  ) -> Tuple[np.ndarray, np.ndarray]:
+    """`generate_blocking_with_hidden(..., collect_hidden_states=true)` (single_batch.rs:217-306): codes u32 (C, T) and
+    the pre-norm slow hidden state of every yielded frame, f32 (T_all, 1, dim)."""
+    prompt = np.ascontiguousarray(prompt, dtype=np.uint32)
+    Cb, D = model.cfg["num_codebooks"], model.cfg["dim"]
+    P = prompt.shape[1]
+    cap = max(int(max_new_tokens) - P + 2, 1) if fixed_len is None else int(fixed_len)
+    out = np.zeros((Cb, cap), np.uint32)
+    hid = np.zeros((cap + 1, D), np.float32)
+    n, nh = C.c_size_t(), C.c_size_t()
+    flags = F.FSB_GEN_FIXED_LEN if fixed_len is not None else 0
+    sa = sampling_args._c()
+    F.check(F.lib().fsb_lm_generate_blocking_with_hidden(model._h, prompt.ctypes.data, P, int(max_new_tokens), C.byref(sa),
+                                                         flags, int(fixed_len or 0), out.ctypes.data, cap, C.byref(n),
+                                                         hid.ctypes.data, cap + 1, C.byref(nh)))
+    return out[:, : n.value].copy(), hid[: nh.value].reshape(nh.value, 1, D).copy()
+
+
 def generate_static_batch(model: DualARTransformer, prompts: List[np.ndarray], max_new_tokens: int,
                           sampling_args: SamplingArgs, fixed_len: Optional[int] = None) -> List[np.ndarray]:
     """Row i == generate_blocking(prompts[i]) with Philox row index i (independent utterances)."""

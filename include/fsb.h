@@ -168,6 +168,15 @@ int fsb_lm_generate_blocking(fsb_lm *lm, const uint32_t *prompt, int32_t prompt_
                              const fsb_sampling_args *sampling, uint32_t flags, int32_t fixed_len,
                              uint32_t *out_codes, size_t cap, size_t *out_len);
 
+/* generate_blocking_with_hidden(collect_hidden_states = true), single_batch.rs:217-306 (the server's hidden-state
+ * export, server/lib/handlers/speech.rs:24-48): same generation, plus the PRE-norm slow hidden state handed to the fast
+ * stack (Q1) of EVERY yielded frame, <|im_end|> frames included (single_batch.rs:251,268-270).
+ * hidden: f32 (hidden_cap, dim) row-major; *n_hidden = frames written (== fsb_lm_last_frames count). */
+int fsb_lm_generate_blocking_with_hidden(fsb_lm *lm, const uint32_t *prompt, int32_t prompt_len, size_t max_new_tokens,
+                                         const fsb_sampling_args *sampling, uint32_t flags, int32_t fixed_len,
+                                         uint32_t *out_codes, size_t cap, size_t *out_len, float *hidden,
+                                         size_t hidden_cap, size_t *n_hidden);
+
 /* generate_static_batch, static_batch.rs:282-390, with "independent utterances"
  * semantics: row i is exactly fsb_lm_generate_blocking on prompts[i] with Philox
  * row index i (per-row positions and KV lengths; the reference's unmasked left

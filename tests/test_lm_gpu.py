@@ -547,3 +547,28 @@ def test_full_size_fish15_against_the_oracle():
     tot, bad = replay_all(lm, ora, prompts, outs, so, 6)
     assert tot["violation"] == 0 and tot["exact"] >= tot["decisions"] - 5, (tot, bad[:5])
     lm.close()
+
+
+def test_generate_blocking_with_hidden(models):
+    """single_batch.rs:217-306 with collect_hidden_states: one pre-norm slow hidden state per yielded frame
+    (<|im_end|> frames included), equal to what the oracle's iterator saw (atol 1e-3), codes unchanged."""
+    from fish_speech_rs_b200 import generate_blocking_with_hidden
+    cfg, tok, w, gpu, ora = models
+    prompt = synth.make_prompt(cfg, tok, 26, seed=314)
+    for max_new, fixed in ((400, 9), (30, None)):
+        codes, hid = generate_blocking_with_hidden(gpu, prompt, max_new, SamplingArgs(temp=0.0), fixed_len=fixed)
+        np.testing.assert_array_equal(codes, generate_blocking(gpu, prompt, max_new, SamplingArgs(temp=0.0), fixed_len=fixed))
+        ora.clear_slow_layer_caches()
+        gen = ogen.SingleBatchGenerator(ora, t64(prompt), max_new, osamp.SamplingArgs(temp=0.0), True, 0, fixed)
+        exp = []
+        with torch.no_grad():
+            while True:
+                if fixed is not None and len(exp) >= fixed:
+                    break
+                fr = gen.next()
+                if fr is None:
+                    break
+                exp.append(gen.last_hidden.reshape(1, -1).numpy().copy())
+        ora.clear_slow_layer_caches()
+        assert hid.shape == (len(exp), 1, cfg["dim"])
+        np.testing.assert_allclose(hid[:, 0], np.concatenate(exp, 0), atol=ATOL, rtol=0)
