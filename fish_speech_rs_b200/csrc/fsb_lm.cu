@@ -726,6 +726,14 @@ static int megab_setup(fsb_lm *lm) {
     FSB_TRY(dev_alloc(lm, &x.apart, (size_t)B * lm->H * kMBMaxSplit * (lm->hd + 4)));
     FSB_TRY(dev_alloc(lm, &x.ssq_x, (size_t)B * kMBSsq));
     FSB_TRY(dev_alloc(lm, &x.ssq_fx, (size_t)B * kMBSsq));
+    {
+        // operand images (sized for the 32-row tile; rows >= the batch stay zero)
+        const size_t xop_bytes = (size_t)16 * 3 * 32 * 128;
+        for (unsigned char **q : {&x.xop_x, &x.xop_fx, &x.xop_att}) {
+            FSB_TRY(dev_alloc(lm, q, xop_bytes));
+            FSB_CUDA_OK(cudaMemset(*q, 0, xop_bytes));
+        }
+    }
     x.head_tiles = (lm->n_slow_logits + 127) / 128;
     x.head_extra = lm->slow_row0 != lm->slow_rest_base - 1 ? 1 : 0;
     if (megab_smem_bytes(32, megab_max_stages(32)) > lm->smem_optin || megab_smem_bytes(16, megab_max_stages(16)) > lm->smem_optin)

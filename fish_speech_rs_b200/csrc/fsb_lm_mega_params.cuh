@@ -108,6 +108,10 @@ struct MegaBExtra {
     float *att;               // (B, H * hd) attention output
     float *apart;             // (B, H, kMBMaxSplit, hd + 4) partial attention (o, m, l)
     float *ssq_x, *ssq_fx;    // (B, kMBSsq) partial sums of squares of the slow / fast stream
+    // operand images (K = 1024: 16 k-blocks of [3 NPAD rows][64] bf16, 128-byte swizzle) of the three activations the
+    // projections consume, written by their PRODUCERS with the consumer's norm weight folded in (x * g split into
+    // hi + mid + lo); a consumer stages a 256-column slice with one cp.async.bulk
+    unsigned char *xop_x, *xop_fx, *xop_att;
     int nstages;
     int head_tiles;           // 128-row tiles of the constrained slow head (without the extra <|im_end|> tile)
     int head_extra;           // 1: <|im_end|> is not adjacent to the semantic range -> one more tile for logit 0

@@ -458,70 +458,56 @@ struct MegaB {
     // k-block kb = [3 NPAD rows][64 k] with 128-byte rows (hi | mid | lo row groups), 16-byte chunk c of row r stored
     // at chunk c ^ (r & 7) (the 128-byte swizzle TMA would produce).  Rows >= nb are zero.  The global loads of slice
     // s + 1 are in flight while slice s is converted, and the MMAs of slice s run while slice s + 1 is staged.
-    struct XRegs {
-        float4 v[NPAD / 8][2];
-        float4 g[2];
-    };
-    __device__ __forceinline__ void load_slice(XRegs &r, const float *src, int ld, const float *gw) const {
-        const int c32 = tid & 31;  // 16-byte chunk (8 columns) of the slice
-#pragma unroll
-        for (int i = 0; i < NPAD / 8; ++i) {
-            const int b = (tid >> 5) + i * 8;
-            if (b < p.nb) {
-                r.v[i][0] = __ldcg(reinterpret_cast<const float4 *>(src + (size_t)b * ld + c32 * 8));
-                r.v[i][1] = __ldcg(reinterpret_cast<const float4 *>(src + (size_t)b * ld + c32 * 8 + 4));
-            } else {
-                r.v[i][0] = make_float4(0.f, 0.f, 0.f, 0.f);
-                r.v[i][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+    // byte offset of element (row b, column col) of term `term` in an operand image
+    static __device__ __forceinline__ uint32_t xop_off(int term, int b, int col) {
+        return (uint32_t)((col >> 6) * kXKb + (term * NPAD + b) * 128 + ((((col >> 3) & 7) ^ (b & 7)) << 4) + (col & 7) * 2);
+    }
+    static __device__ __forceinline__ void store_xop1(unsigned char *xop, int b, int col, float v) {
+        unsigned short h, m, l;
+        mb_split3(v, h, m, l);
+        *reinterpret_cast<unsigned short *>(xop + xop_off(0, b, col)) = h;
+        *reinterpret_cast<unsigned short *>(xop + xop_off(1, b, col)) = m;
+        *reinterpret_cast<unsigned short *>(xop + xop_off(2, b, col)) = l;
+    }
+    // four consecutive columns (col % 4 == 0): one 8-byte store per term
+    static __device__ __forceinline__ void store_xop4(unsigned char *xop, int b, int col, float4 v) {
+        unsigned short h[4], m[4], l[4];
+        mb_split3(v.x, h[0], m[0], l[0]);
+        mb_split3(v.y, h[1], m[1], l[1]);
+        mb_split3(v.z, h[2], m[2], l[2]);
+        mb_split3(v.w, h[3], m[3], l[3]);
+        auto pk = [](const unsigned short (&q)[4]) {
+            return make_uint2((uint32_t)q[0] | ((uint32_t)q[1] << 16), (uint32_t)q[2] | ((uint32_t)q[3] << 16));
+        };
+        *reinterpret_cast<uint2 *>(xop + xop_off(0, b, col)) = pk(h);
+        *reinterpret_cast<uint2 *>(xop + xop_off(1, b, col)) = pk(m);
+        *reinterpret_cast<uint2 *>(xop + xop_off(2, b, col)) = pk(l);
+    }
+    // the norm weight vector the CONSUMER of the activation produced by step s applies (null: none)
+    __device__ __forceinline__ const float *consumer_norm(const Step &s) const {
+        const bool slow = s.pass == 0;
+        const int li = slow ? s.l : p.NL + s.l;
+        if (s.kind == K_WO) return normtab[2 * li + 1];  // -> ffn_norm of the same block
+        // K_FRED: -> attention_norm of the next block, or the final norm in front of the head
+        if (s.l + 1 < (slow ? p.NL : p.NFL)) return normtab[2 * (li + 1)];
+        return normtab[2 * (p.NL + p.NFL) + (slow ? 0 : 1)];
+    }
+    // consumer side: the four 256-column slices of an operand image alternate between the two operand buffers; the
+    // MMAs of slice s run while slice s + 1 streams in (L2 -> shared memory, no thread touches the data)
+    __device__ __forceinline__ void stage_bulk(const unsigned char *xop) {
+        if (tid == 0) {
+            // the region was last touched through the generic proxy (K/V staging, sampler scratch, h tile) and the image
+            // was written with ordinary stores by other CTAs: order both before the async-proxy copies
+            asm volatile("fence.proxy.async;" ::: "memory");
+#pragma unroll 1
+            for (int sl = 0; sl < 4; ++sl) {
+                const int i = sl & 1;
+                // buffer i was read by the MMAs of slice sl - 2: its first completion of this phase (the barrier
+                // completes exactly twice per phase, so that one always has parity 0)
+                if (sl >= 2) mb_wait(xf + i, 0);
+                m1_mbar_expect_tx(xr + i, kXBuf);
+                m1_bulk_g2s(xs + i * kXBuf, xop + (size_t)sl * kXBuf, kXBuf, xr + i);
             }
-        }
-        if (gw) {
-            r.g[0] = __ldg(reinterpret_cast<const float4 *>(gw + c32 * 8));
-            r.g[1] = __ldg(reinterpret_cast<const float4 *>(gw + c32 * 8 + 4));
-        } else {
-            r.g[0] = r.g[1] = make_float4(1.f, 1.f, 1.f, 1.f);
-        }
-    }
-    __device__ __forceinline__ void store_slice(const XRegs &r, int buf) {
-        const int c32 = tid & 31;
-        const int kb = c32 >> 3, c = c32 & 7;
-        unsigned char *base = xs + buf * kXBuf + kb * kXKb;
-#pragma unroll
-        for (int i = 0; i < NPAD / 8; ++i) {
-            const int b = (tid >> 5) + i * 8;
-            const float v[8] = {__fmul_rn(r.v[i][0].x, r.g[0].x), __fmul_rn(r.v[i][0].y, r.g[0].y), __fmul_rn(r.v[i][0].z, r.g[0].z),
-                                __fmul_rn(r.v[i][0].w, r.g[0].w), __fmul_rn(r.v[i][1].x, r.g[1].x), __fmul_rn(r.v[i][1].y, r.g[1].y),
-                                __fmul_rn(r.v[i][1].z, r.g[1].z), __fmul_rn(r.v[i][1].w, r.g[1].w)};
-            unsigned short h[8], m[8], l[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) mb_split3(v[j], h[j], m[j], l[j]);
-            const uint32_t off = (uint32_t)(b * 128 + ((c ^ (b & 7)) << 4));
-            auto pack = [](const unsigned short (&q)[8]) {
-                return make_uint4((uint32_t)q[0] | ((uint32_t)q[1] << 16), (uint32_t)q[2] | ((uint32_t)q[3] << 16),
-                                  (uint32_t)q[4] | ((uint32_t)q[5] << 16), (uint32_t)q[6] | ((uint32_t)q[7] << 16));
-            };
-            *reinterpret_cast<uint4 *>(base + off) = pack(h);
-            *reinterpret_cast<uint4 *>(base + NPAD * 128 + off) = pack(m);
-            *reinterpret_cast<uint4 *>(base + 2 * NPAD * 128 + off) = pack(l);
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> tensor-core (async proxy) reads
-    }
-    // all four slices of a K = 1024 activation; gw: norm weights (x * g is what gets multiplied) or null
-    __device__ __forceinline__ void stage_all(const float *src, const float *gw, const float *ssq = nullptr) {
-        XRegs ra, rb;
-        load_slice(ra, src, kD, gw);
-        if (ssq) compute_invd(ssq);  // its L2 round trip overlaps the slice loads already in flight
-#pragma unroll
-        for (int s = 0; s < 4; ++s) {
-            XRegs &cur = (s & 1) ? rb : ra;
-            XRegs &nxt = (s & 1) ? ra : rb;
-            if (s + 1 < 4) load_slice(nxt, src + (s + 1) * kKs, kD, gw ? gw + (s + 1) * kKs : nullptr);
-            // buffer s & 1 was read by the MMAs of slice s - 2: its first completion of this phase (the barrier
-            // completes exactly twice per phase, so that one always has parity 0)
-            if (s >= 2) mb_wait(xf + (s & 1), 0);
-            store_slice(cur, s & 1);
-            wsync();
-            if (tid == 0) m1_mbar_arrive(xr + (s & 1));
         }
     }
     // 1 / sqrt(mean(x^2) + eps) of every row (candle_nn::RmsNorm), from the partial sums the producer of x left
@@ -570,8 +556,11 @@ struct MegaB {
         long long c0 = tm ? clock64() : 0, c1 = 0;
         const int li = slow ? s.l : p.NL + s.l;
         const float *gw = kind == K_QKV ? normtab[2 * li] : kind == K_HEAD ? normtab[2 * (p.NL + p.NFL) + (slow ? 0 : 1)] : nullptr;
-        stage_all(kind == K_WO ? e.att : stream, gw, gw ? ssq : nullptr);
+        stage_bulk(kind == K_WO ? e.xop_att : (slow ? e.xop_x : e.xop_fx));
+        if (gw) compute_invd(ssq);
+        const float gnext = kind == K_WO ? __ldg(consumer_norm(s) + 128 * t + (warp & 3) * 32 + lane) : 0.f;
         if (tm) { c1 = clock64(); td[0] += c1 - c0; c0 = c1; }
+        wsync();  // invd visible
         mb_wait(acc_full, pacc);
         pacc ^= 1;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -592,6 +581,7 @@ struct MegaB {
                 if (b < p.nb) {
                     const float nv = __fadd_rn(xo[j], r[j]);
                     stream[(size_t)b * kD + 128 * t + row] = nv;
+                    store_xop1(slow ? e.xop_x : e.xop_fx, b, 128 * t + row, __fmul_rn(nv, gnext));
                     const float q = warp_sum(nv * nv);
                     if (lane == 0) ssq[(size_t)b * kMBSsq + t * 4 + qd] = q;
                 }
@@ -668,7 +658,11 @@ struct MegaB {
         unsigned long long *td = p.dbg + 192 + K_FFN * 8;
         long long c0 = tm ? clock64() : 0, c1 = 0;
         const int li = slow ? s.l : p.NL + s.l;
-        stage_all(stream, normtab[2 * li + 1], slow ? e.ssq_x : e.ssq_fx);
+        stage_bulk(slow ? e.xop_x : e.xop_fx);
+        compute_invd(slow ? e.ssq_x : e.ssq_fx);
+        wsync();  // invd visible
+        (void)li;
+        (void)stream;
         if (tm) { c1 = clock64(); td[0] += c1 - c0; c0 = c1; }
         mb_wait(acc_full, pacc);
         pacc ^= 1;
@@ -765,6 +759,9 @@ struct MegaB {
             const float4 nv = make_float4(__fadd_rn(xo.x, a.x), __fadd_rn(xo.y, a.y), __fadd_rn(xo.z, a.z), __fadd_rn(xo.w, a.w));
             *xp = nv;
             sq = nv.x * nv.x + nv.y * nv.y + nv.z * nv.z + nv.w * nv.w;
+            const float4 g4 = __ldg(reinterpret_cast<const float4 *>(consumer_norm(s) + col));
+            store_xop4(slow ? e.xop_x : e.xop_fx, b, col,
+                       make_float4(__fmul_rn(nv.x, g4.x), __fmul_rn(nv.y, g4.y), __fmul_rn(nv.z, g4.z), __fmul_rn(nv.w, g4.w)));
         }
         sq = warp_sum(sq);
         if (lane == 0) ssq[(size_t)b * kMBSsq + (c & 3) * 8 + warp] = sq;
@@ -817,34 +814,39 @@ struct MegaB {
             }
             wsync();
             const float *ks = kvb + buf * kBuf, *vs = ks + kMBChunk * kMBKvStride;
-            for (int jb = 0; jb < n; jb += 8) {  // warp-uniform trip count (the shuffles need all lanes)
-                const int j = jb + g;
-                const bool valid = j < n;
-                const int jc = valid ? j : 0;
-                const float *kr = ks + jc * kMBKvStride + sub * 4, *vr = vs + jc * kMBKvStride + sub * 4;
-                float dot = 0.f;
+            // 16 positions per iteration (two groups of 8, one per lane group g): independent dot-product chains
+            // (4 partial sums each) and ONE rescale of the running output per 16 positions instead of per position
+            for (int jb = 0; jb < n; jb += 16) {  // warp-uniform trip count (the shuffles need all lanes)
+                const int ja = jb + g, jbb = jb + 8 + g;
+                const bool va = ja < n, vb = jbb < n;
+                const float *ka = ks + (va ? ja : 0) * kMBKvStride + sub * 4, *kb2 = ks + (vb ? jbb : 0) * kMBKvStride + sub * 4;
+                float da[4], db[4];
 #pragma unroll
                 for (int jj = 0; jj < 4; ++jj) {
-                    const float4 kk = *reinterpret_cast<const float4 *>(kr + jj * 16);
-                    dot = fmaf(qv[jj].x, kk.x, dot);
-                    dot = fmaf(qv[jj].y, kk.y, dot);
-                    dot = fmaf(qv[jj].z, kk.z, dot);
-                    dot = fmaf(qv[jj].w, kk.w, dot);
+                    const float4 x = *reinterpret_cast<const float4 *>(ka + jj * 16);
+                    const float4 y = *reinterpret_cast<const float4 *>(kb2 + jj * 16);
+                    da[jj] = fmaf(qv[jj].w, x.w, fmaf(qv[jj].z, x.z, fmaf(qv[jj].y, x.y, qv[jj].x * x.x)));
+                    db[jj] = fmaf(qv[jj].w, y.w, fmaf(qv[jj].z, y.z, fmaf(qv[jj].y, y.y, qv[jj].x * y.x)));
                 }
-                dot += __shfl_xor_sync(0xffffffffu, dot, 1);
-                dot += __shfl_xor_sync(0xffffffffu, dot, 2);
-                if (valid) {
-                    const float m_new = fmaxf(m, dot);
-                    const float corr = expf(m - m_new);
-                    const float pj = expf(dot - m_new);
-                    l = fmaf(l, corr, pj);
+                float sa = (da[0] + da[1]) + (da[2] + da[3]), sb = (db[0] + db[1]) + (db[2] + db[3]);
+                sa += __shfl_xor_sync(0xffffffffu, sa, 1);
+                sb += __shfl_xor_sync(0xffffffffu, sb, 1);
+                sa += __shfl_xor_sync(0xffffffffu, sa, 2);
+                sb += __shfl_xor_sync(0xffffffffu, sb, 2);
+                if (va) {  // (vb implies va; an empty lane group skips the update altogether)
+                    const float m_new = fmaxf(m, vb ? fmaxf(sa, sb) : sa);
+                    const float corr = expf(m - m_new);  // exp(-inf) == 0 on the first group
+                    const float pa = expf(sa - m_new), pb = vb ? expf(sb - m_new) : 0.f;
+                    l = fmaf(l, corr, pa + pb);
+                    const float *va_r = vs + ja * kMBKvStride + sub * 4, *vb_r = vs + (vb ? jbb : ja) * kMBKvStride + sub * 4;
 #pragma unroll
                     for (int jj = 0; jj < 4; ++jj) {
-                        const float4 vv = *reinterpret_cast<const float4 *>(vr + jj * 16);
-                        o[jj * 4 + 0] = fmaf(o[jj * 4 + 0], corr, pj * vv.x);
-                        o[jj * 4 + 1] = fmaf(o[jj * 4 + 1], corr, pj * vv.y);
-                        o[jj * 4 + 2] = fmaf(o[jj * 4 + 2], corr, pj * vv.z);
-                        o[jj * 4 + 3] = fmaf(o[jj * 4 + 3], corr, pj * vv.w);
+                        const float4 x = *reinterpret_cast<const float4 *>(va_r + jj * 16);
+                        const float4 y = *reinterpret_cast<const float4 *>(vb_r + jj * 16);
+                        o[jj * 4 + 0] = fmaf(pb, y.x, fmaf(pa, x.x, o[jj * 4 + 0] * corr));
+                        o[jj * 4 + 1] = fmaf(pb, y.y, fmaf(pa, x.y, o[jj * 4 + 1] * corr));
+                        o[jj * 4 + 2] = fmaf(pb, y.z, fmaf(pa, x.z, o[jj * 4 + 2] * corr));
+                        o[jj * 4 + 3] = fmaf(pb, y.w, fmaf(pa, x.w, o[jj * 4 + 3] * corr));
                     }
                     m = m_new;
                 }
@@ -928,12 +930,11 @@ struct MegaB {
             const int h = kvh * kRep + warp;
             if (ns == 1) {
                 if (g == 0) {
-                    float *out = e.att + (size_t)b * kD + h * kHd + sub * 4;
                     const float inv = 1.0f / l;
 #pragma unroll
                     for (int jj = 0; jj < 4; ++jj)
-                        *reinterpret_cast<float4 *>(out + jj * 16) =
-                            make_float4(o[jj * 4 + 0] * inv, o[jj * 4 + 1] * inv, o[jj * 4 + 2] * inv, o[jj * 4 + 3] * inv);
+                        store_xop4(e.xop_att, b, h * kHd + sub * 4 + jj * 16,
+                                   make_float4(o[jj * 4 + 0] * inv, o[jj * 4 + 1] * inv, o[jj * 4 + 2] * inv, o[jj * 4 + 3] * inv));
                 }
                 continue;
             }
@@ -969,7 +970,8 @@ struct MegaB {
                     a0 = fmaf(ov.x, w, a0);
                     a1 = fmaf(ov.y, w, a1);
                 }
-                *reinterpret_cast<float2 *>(e.att + (size_t)b * kD + h * kHd + lane * 2) = make_float2(a0 / L, a1 / L);
+                store_xop1(e.xop_att, b, h * kHd + lane * 2, a0 / L);
+                store_xop1(e.xop_att, b, h * kHd + lane * 2 + 1, a1 / L);
             }
         }
     }
@@ -1058,6 +1060,8 @@ struct MegaB {
         {
             const float4 v = __ldcg(reinterpret_cast<const float4 *>(p.x + (size_t)b * kD) + tid);
             reinterpret_cast<float4 *>(p.fx + (size_t)b * kD)[tid] = v;
+            const float4 g4 = __ldg(reinterpret_cast<const float4 *>(normtab[2 * p.NL]) + tid);  // first fast block's attention_norm
+            store_xop4(e.xop_fx, b, 4 * tid, make_float4(__fmul_rn(v.x, g4.x), __fmul_rn(v.y, g4.y), __fmul_rn(v.z, g4.z), __fmul_rn(v.w, g4.w)));
             if (tid < kMBSsq) e.ssq_fx[(size_t)b * kMBSsq + tid] = __ldcg(e.ssq_x + (size_t)b * kMBSsq + tid);
         }
         wsync();
@@ -1098,6 +1102,8 @@ struct MegaB {
                 const uint2 raw = __ldg(reinterpret_cast<const uint2 *>(fe) + tid);
                 const float4 v = make_float4(bf16lo(raw.x), bf16hi(raw.x), bf16lo(raw.y), bf16hi(raw.y));
                 reinterpret_cast<float4 *>(p.fx + (size_t)b * kD)[tid] = v;
+                const float4 g4 = __ldg(reinterpret_cast<const float4 *>(normtab[2 * p.NL]) + tid);
+                store_xop4(e.xop_fx, b, 4 * tid, make_float4(__fmul_rn(v.x, g4.x), __fmul_rn(v.y, g4.y), __fmul_rn(v.z, g4.z), __fmul_rn(v.w, g4.w)));
                 finish_row(v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w, e.ssq_fx + (size_t)b * kMBSsq);
             }
         }
@@ -1149,6 +1155,8 @@ struct MegaB {
                     acc.w = __fadd_rn(acc.w, __fmul_rn(bf16hi(rc[c].y), mf));
                 }
                 reinterpret_cast<float4 *>(p.x + (size_t)b * kD)[tid] = acc;
+                const float4 g4 = __ldg(reinterpret_cast<const float4 *>(normtab[0]) + tid);  // first slow block's attention_norm
+                store_xop4(e.xop_x, b, 4 * tid, make_float4(__fmul_rn(acc.x, g4.x), __fmul_rn(acc.y, g4.y), __fmul_rn(acc.z, g4.z), __fmul_rn(acc.w, g4.w)));
                 finish_row(acc.x * acc.x + acc.y * acc.y + acc.z * acc.z + acc.w * acc.w, e.ssq_x + (size_t)b * kMBSsq);
             }
         }
@@ -1163,6 +1171,8 @@ struct MegaB {
         // sum of squares of the prefilled hidden rows (the launch starts at the slow head of frame 0)
         if (samples) {
             const float4 v = __ldcg(reinterpret_cast<const float4 *>(p.x + (size_t)blockIdx.x * kD) + tid);
+            const float4 g4 = __ldg(reinterpret_cast<const float4 *>(p.norm) + tid);  // consumer: the slow head
+            store_xop4(e.xop_x, blockIdx.x, 4 * tid, make_float4(__fmul_rn(v.x, g4.x), __fmul_rn(v.y, g4.y), __fmul_rn(v.z, g4.z), __fmul_rn(v.w, g4.w)));
             finish_row(v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w, e.ssq_x + (size_t)blockIdx.x * kMBSsq);
         }
         frame_prep();
