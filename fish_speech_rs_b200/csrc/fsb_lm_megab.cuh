@@ -139,8 +139,7 @@ struct MegaB {
     static constexpr int kTmemCols = 512;
     static constexpr int kXsBytes = NPAD == 16 ? kMBXsBytes16 : kMBXsBytes32;
     static_assert(2 * kXBuf <= kXsBytes, "two activation slice buffers do not fit");
-    static_assert(2 * 2 * kMBChunk * kMBKvStride * 4 <= kXsBytes, "two K/V chunk buffers do not fit");
-    static_assert(kAccCols + 8 * kAcc2Cols <= kTmemCols, "TMEM columns");
+        static_assert(kAccCols + 8 * kAcc2Cols <= kTmemCols, "TMEM columns");
 
     enum { K_QKV = 0, K_ATT = 1, K_WO = 2, K_FFN = 3, K_FRED = 4, K_HEAD = 5, K_SAMPLE = 6, K_END = 7 };
     struct Step { int frame, pass, l, kind; };  // pass 0 = slow stack, pass c + 1 = fast step of codebook c
@@ -774,7 +773,12 @@ struct MegaB {
                                               int j0, int j1, float &m, float &l, float (&o)[16]) {
         const int g = lane >> 2, sub = lane & 3;
         const int h = kvh * kRep + warp;
-        constexpr int kBuf = 2 * kMBChunk * kMBKvStride;  // floats of one chunk buffer (K rows then V rows)
+        // K/V rows stream through a ring of kNB buffers of kCh positions (K rows then V rows, padded row stride):
+        // kNB - 1 chunks are in flight while one is consumed -- the cache stream is latency-bound (HBM round trip per
+        // chunk), so what matters is the number of bytes in flight per SM
+        constexpr int kCh = 32, kNB = 4;
+        constexpr int kBuf = 2 * kCh * kMBKvStride;
+        static_assert(kNB * kBuf * 4 <= kXsBytes, "K/V ring does not fit");
         float *kvb = reinterpret_cast<float *>(xs);
         float4 qv[4];
         const float *qp = p.q + (size_t)b * kD + (size_t)h * kHd + sub * 4;
@@ -790,36 +794,34 @@ struct MegaB {
         for (int i = 0; i < 16; ++i) o[i] = 0.f;
         const float *kb = kcache + ((size_t)b * kKV + kvh) * cache_len * kHd;
         const float *vb = vcache + ((size_t)b * kKV + kvh) * cache_len * kHd;
-        auto stage = [&](int c0, int buf) {  // positions [c0, min(c0 + 64, j1)) -> chunk buffer `buf`
-            const int n = min(kMBChunk, j1 - c0);
-            float *ks = kvb + buf * kBuf, *vs = ks + kMBChunk * kMBKvStride;
-            for (int i = tid; i < n * 16; i += kMBWorkers) {
-                const int j = i >> 4, sg = i & 15;
-                cp_async16(ks + j * kMBKvStride + sg * 4, kb + (size_t)(c0 + j) * kHd + sg * 4);
-                cp_async16(vs + j * kMBKvStride + sg * 4, vb + (size_t)(c0 + j) * kHd + sg * 4);
+        const int nchunks = (j1 - j0 + kCh - 1) / kCh;
+        auto stage = [&](int c) {  // chunk c -> buffer c % kNB; always commits a group (possibly empty)
+            if (c < nchunks) {
+                const int c0 = j0 + c * kCh, n = min(kCh, j1 - c0);
+                float *ks = kvb + (c % kNB) * kBuf, *vs = ks + kCh * kMBKvStride;
+                for (int i = tid; i < n * 16; i += kMBWorkers) {
+                    const int j = i >> 4, sg = i & 15;
+                    cp_async16(ks + j * kMBKvStride + sg * 4, kb + (size_t)(c0 + j) * kHd + sg * 4);
+                    cp_async16(vs + j * kMBKvStride + sg * 4, vb + (size_t)(c0 + j) * kHd + sg * 4);
+                }
             }
             cp_async_commit();
         };
-        wsync();  // both buffers are free (previous item / previous user of the region)
-        stage(j0, 0);
-        int buf = 0;
-        for (int c0 = j0; c0 < j1; c0 += kMBChunk, buf ^= 1) {
-            const int n = min(kMBChunk, j1 - c0);
-            // the next chunk streams in while this one is consumed
-            if (c0 + kMBChunk < j1) {
-                stage(c0 + kMBChunk, buf ^ 1);
-                asm volatile("cp.async.wait_group 1;" ::: "memory");
-            } else {
-                cp_async_wait_all();
-            }
+        wsync();  // the ring is free (previous item / previous user of the region)
+#pragma unroll
+        for (int c = 0; c < kNB - 1; ++c) stage(c);
+        for (int c = 0; c < nchunks; ++c) {
+            stage(c + kNB - 1);  // into the buffer consumed in iteration c - 1 (released by the barrier below)
+            asm volatile("cp.async.wait_group %0;" ::"n"(kNB - 1) : "memory");  // chunk c has landed
             wsync();
-            const float *ks = kvb + buf * kBuf, *vs = ks + kMBChunk * kMBKvStride;
+            const int n = min(kCh, j1 - (j0 + c * kCh));
+            const float *ks = kvb + (c % kNB) * kBuf, *vs = ks + kCh * kMBKvStride;
             // 16 positions per iteration (two groups of 8, one per lane group g): independent dot-product chains
             // (4 partial sums each) and ONE rescale of the running output per 16 positions instead of per position
             for (int jb = 0; jb < n; jb += 16) {  // warp-uniform trip count (the shuffles need all lanes)
                 const int ja = jb + g, jbb = jb + 8 + g;
-                const bool va = ja < n, vb = jbb < n;
-                const float *ka = ks + (va ? ja : 0) * kMBKvStride + sub * 4, *kb2 = ks + (vb ? jbb : 0) * kMBKvStride + sub * 4;
+                const bool va = ja < n, vb2 = jbb < n;
+                const float *ka = ks + (va ? ja : 0) * kMBKvStride + sub * 4, *kb2 = ks + (vb2 ? jbb : 0) * kMBKvStride + sub * 4;
                 float da[4], db[4];
 #pragma unroll
                 for (int jj = 0; jj < 4; ++jj) {
@@ -833,12 +835,12 @@ struct MegaB {
                 sb += __shfl_xor_sync(0xffffffffu, sb, 1);
                 sa += __shfl_xor_sync(0xffffffffu, sa, 2);
                 sb += __shfl_xor_sync(0xffffffffu, sb, 2);
-                if (va) {  // (vb implies va; an empty lane group skips the update altogether)
-                    const float m_new = fmaxf(m, vb ? fmaxf(sa, sb) : sa);
+                if (va) {  // (vb2 implies va; an empty lane group skips the update altogether)
+                    const float m_new = fmaxf(m, vb2 ? fmaxf(sa, sb) : sa);
                     const float corr = expf(m - m_new);  // exp(-inf) == 0 on the first group
-                    const float pa = expf(sa - m_new), pb = vb ? expf(sb - m_new) : 0.f;
+                    const float pa = expf(sa - m_new), pb = vb2 ? expf(sb - m_new) : 0.f;
                     l = fmaf(l, corr, pa + pb);
-                    const float *va_r = vs + ja * kMBKvStride + sub * 4, *vb_r = vs + (vb ? jbb : ja) * kMBKvStride + sub * 4;
+                    const float *va_r = vs + ja * kMBKvStride + sub * 4, *vb_r = vs + (vb2 ? jbb : ja) * kMBKvStride + sub * 4;
 #pragma unroll
                     for (int jj = 0; jj < 4; ++jj) {
                         const float4 x = *reinterpret_cast<const float4 *>(va_r + jj * 16);
@@ -851,8 +853,9 @@ struct MegaB {
                     m = m_new;
                 }
             }
-            wsync();  // this buffer is overwritten by the chunk after next
+            wsync();  // buffer c % kNB may be refilled (with chunk c + kNB) by the next iteration
         }
+        cp_async_wait_all();
         // merge the 8 position groups (lanes with equal `sub`)
 #pragma unroll
         for (int off = 4; off < 32; off <<= 1) {
@@ -878,15 +881,18 @@ struct MegaB {
         }
         wsync();
         if (tid == 0) {
-            int total = 0;
-            for (int b = 0; b < p.nb; ++b) total += act_s[b] ? pos_s[b] + 1 : 0;
+            // split every live (row, kv head) into ns position ranges, ns proportional to the row's length, such that
+            // the items never outnumber the CTAs (an item is sequential; a second round would double the phase)
+            int total = 0, live = 0;
+            for (int b = 0; b < p.nb; ++b)
+                if (act_s[b]) { total += pos_s[b] + 1; ++live; }
             const int G = (int)gridDim.x;
-            int pit = (total * kKV * 10 + G * 9 - 1) / (G * 9);
-            pit = max(kMBChunk, (pit + kMBChunk - 1) / kMBChunk * kMBChunk);
+            const int slots = max(G / kKV, live);  // ranges to hand out over all rows (per kv head)
             int base = 0;
             for (int b = 0; b < p.nb; ++b) {
                 const int len = pos_s[b] + 1;
-                int ns = min(kMBMaxSplit, (len + pit - 1) / pit);
+                int ns = (int)(((long long)len * slots) / max(total, 1));  // floor: sum over live rows <= slots
+                ns = max(1, min(min(ns, kMBMaxSplit), (len + kMBChunk - 1) / kMBChunk));
                 int pr = ((len + ns - 1) / ns + kMBChunk - 1) / kMBChunk * kMBChunk;
                 ns = (len + pr - 1) / pr;
                 nsplit_s[b] = ns;
