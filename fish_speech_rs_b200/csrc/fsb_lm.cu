@@ -41,6 +41,7 @@ struct fsb_lm {
     int max_batch, max_len, fast_len;
     int wdt;  // weight dtype
     int prefill_rows;
+    size_t toks_cap = 0;  // u32 words of the prompt staging arena
     int nsplit;
     int n_slow_logits, slow_row0, slow_rest_base;
     cudaStream_t stream = nullptr;
@@ -307,31 +308,43 @@ static int gemm(fsb_lm *lm, const float *A, const DevTensor &W, const float *res
     return FSB_OK;
 }
 
-// toks_dev: (C+1, S_total) device, columns [c0, c0+S) are processed; KV rows land at pos0.. of row b.
-static int prefill_chunk(fsb_lm *lm, const uint32_t *toks_dev, int S_total, int c0, int S, int b, int pos0,
-                         int rope_delta) {
+// One prefill pass over up to `prefill_rows` prompt positions that may belong to SEVERAL batch rows: the dense
+// projections (QKV / O / FFN) see all positions as one GEMM (the tcgen05 kernel needs hundreds of tiles to fill 148 SMs;
+// one 384-token prompt yields 30-96), while embedding, RoPE + KV append and causal attention run per row segment.
+struct PrefillSeg {
+    const uint32_t *toks;  // device (C+1, S_total) of the row
+    int S_total;           // leading dimension of toks
+    int c0, n;             // prompt columns [c0, c0 + n) of the row
+    int b, pos0;           // batch row, cache position of column c0
+    int rope_delta;        // RoPE row = cache position + rope_delta
+    int off;               // first position of the segment inside the pass
+    bool last;             // the segment ends the row's prompt: its last position is the row's hidden state
+};
+
+static int prefill_pass(fsb_lm *lm, const std::vector<PrefillSeg> &segs) {
     const int D = lm->D, H = lm->H, KV = lm->KV, hd = lm->hd, I = lm->I, QKV = lm->QKV;
     Scratch &s = lm->s;
-    // embed: token (c, s) at toks_dev[c * S_total + c0 + s]; reuse the kernel with S = S_total, rows offset
-    {
-        // the embed kernel indexes toks[(b*(C+1) + c)*S + s]; feed it a shifted base so that s in [0, S)
+    cudaStream_t st = lm->stream;
+    int S = 0;
+    for (const PrefillSeg &g : segs) S = std::max(S, g.off + g.n);
+    for (const PrefillSeg &g : segs) {
+        // the embed kernel indexes toks[c * S_total + s]; a shifted base selects the segment's columns
         if (lm->wdt == FSB_F32)
-            embed_sum_kernel<float><<<S, 256, 0, lm->stream>>>(toks_dev + c0, S_total, lm->C, D, lm->CS,
-                                                              (const float *)lm->emb.ptr, (const float *)lm->cb_emb.ptr,
-                                                              lm->tok.semantic_start_id, lm->tok.semantic_end_id,
-                                                              lm->tok.has_semantic_end, s.x, nullptr);
+            embed_sum_kernel<float><<<g.n, 256, 0, st>>>(g.toks + g.c0, g.S_total, lm->C, D, lm->CS, (const float *)lm->emb.ptr,
+                                                        (const float *)lm->cb_emb.ptr, lm->tok.semantic_start_id,
+                                                        lm->tok.semantic_end_id, lm->tok.has_semantic_end,
+                                                        s.x + (size_t)g.off * D, nullptr);
         else
-            embed_sum_kernel<__nv_bfloat16><<<S, 256, 0, lm->stream>>>(
-                toks_dev + c0, S_total, lm->C, D, lm->CS, (const __nv_bfloat16 *)lm->emb.ptr,
+            embed_sum_kernel<__nv_bfloat16><<<g.n, 256, 0, st>>>(
+                g.toks + g.c0, g.S_total, lm->C, D, lm->CS, (const __nv_bfloat16 *)lm->emb.ptr,
                 (const __nv_bfloat16 *)lm->cb_emb.ptr, lm->tok.semantic_start_id, lm->tok.semantic_end_id,
-                lm->tok.has_semantic_end, s.x, nullptr);
+                lm->tok.has_semantic_end, s.x + (size_t)g.off * D, nullptr);
         LAUNCH_CHECK(lm);
     }
     const float scale = 1.0f / sqrtf((float)hd);
     const bool tc = lm->tc_ok;
     const int bn = tc_pick_bn(S), bi = bn == 32 ? 0 : (bn == 64 ? 1 : 2);
     const int seg = lm->prefill_rows;
-    cudaStream_t st = lm->stream;
     for (int l = 0; l < lm->NL; ++l) {
         const LayerW &L = lm->layers[l];
         if (tc) {
@@ -339,17 +352,20 @@ static int prefill_chunk(fsb_lm *lm, const uint32_t *toks_dev, int S_total, int 
             FSB_TRY(tc_gemm(L.m_wqkv, lm->mx_xn[bi], bn, s.qkv, nullptr, S, QKV, D, seg, QKV, st));
             lm->launches += 2;
         } else {
-            rmsnorm_rows_kernel<<<(S + 3) / 4, 128, 0, lm->stream>>>(s.x, (const float *)L.attn_norm.ptr,
-                                                                     lm->cfg.norm_eps, S, D, s.xn);
+            rmsnorm_rows_kernel<<<(S + 3) / 4, 128, 0, st>>>(s.x, (const float *)L.attn_norm.ptr, lm->cfg.norm_eps, S, D, s.xn);
             LAUNCH_CHECK(lm);
             FSB_TRY(gemm<EPI_STORE>(lm, s.xn, L.wqkv, nullptr, s.qkv, S, QKV, D));
         }
-        rope_append_rows_kernel<<<S, 256, 0, lm->stream>>>(s.qkv, s.q, slow_k(lm, l), slow_v(lm, l), lm->cosT,
-                                                           lm->sinT, b, pos0, rope_delta, H, KV, hd, lm->max_len);
-        LAUNCH_CHECK(lm);
-        attn_prefill_kernel<<<dim3((S + kPrefQ - 1) / kPrefQ, KV), 512, 0, lm->stream>>>(s.q, slow_k(lm, l), slow_v(lm, l), b, pos0,
-                                                                          S, H, KV, hd, lm->max_len, scale, s.att);
-        LAUNCH_CHECK(lm);
+        for (const PrefillSeg &g : segs) {
+            rope_append_rows_kernel<<<g.n, 256, 0, st>>>(s.qkv + (size_t)g.off * QKV, s.q + (size_t)g.off * H * hd, slow_k(lm, l),
+                                                         slow_v(lm, l), lm->cosT, lm->sinT, g.b, g.pos0, g.rope_delta, H, KV, hd,
+                                                         lm->max_len);
+            LAUNCH_CHECK(lm);
+            attn_prefill_kernel<<<dim3((g.n + kPrefQ - 1) / kPrefQ, KV), 512, 0, st>>>(
+                s.q + (size_t)g.off * H * hd, slow_k(lm, l), slow_v(lm, l), g.b, g.pos0, g.n, H, KV, hd, lm->max_len, scale,
+                s.att + (size_t)g.off * H * hd);
+            LAUNCH_CHECK(lm);
+        }
         if (tc) {
             FSB_TRY(tc_split3(s.att, lm->sp_att, (size_t)S * H * hd, (size_t)seg * H * hd, st));
             FSB_TRY(tc_gemm(L.m_wo, lm->mx_att[bi], bn, s.x, s.x, S, D, H * hd, seg, D, st));
@@ -366,16 +382,19 @@ static int prefill_chunk(fsb_lm *lm, const uint32_t *toks_dev, int S_total, int 
             FSB_TRY(tc_gemm(L.m_w2, lm->mx_h[bi], bn, s.x, s.x, S, D, I, seg, D, st));
             lm->launches += 5;
         } else {
-            rmsnorm_rows_kernel<<<(S + 3) / 4, 128, 0, lm->stream>>>(s.x, (const float *)L.ffn_norm.ptr, lm->cfg.norm_eps,
-                                                                     S, D, s.xn);
+            rmsnorm_rows_kernel<<<(S + 3) / 4, 128, 0, st>>>(s.x, (const float *)L.ffn_norm.ptr, lm->cfg.norm_eps, S, D, s.xn);
             LAUNCH_CHECK(lm);
             FSB_TRY(gemm<EPI_STORE>(lm, s.xn, L.w1, nullptr, s.g1, S, I, D));
             FSB_TRY(gemm<EPI_STORE>(lm, s.xn, L.w3, nullptr, s.g3, S, I, D));
-            swiglu_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, lm->stream>>>(s.g1, s.g3, n, s.g1);
+            swiglu_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(s.g1, s.g3, n, s.g1);
             LAUNCH_CHECK(lm);
             FSB_TRY(gemm<EPI_RESID>(lm, s.g1, L.w2, s.x, s.x, S, D, I));
         }
     }
+    for (const PrefillSeg &g : segs)
+        if (g.last)
+            FSB_CUDA_OK(cudaMemcpyAsync(s.hidden + (size_t)g.b * D, s.x + (size_t)(g.off + g.n - 1) * D, D * sizeof(float),
+                                        cudaMemcpyDeviceToDevice, st));
     return FSB_OK;
 }
 
@@ -384,11 +403,35 @@ static int prefill_chunk(fsb_lm *lm, const uint32_t *toks_dev, int S_total, int 
 static int prefill_row(fsb_lm *lm, const uint32_t *toks_dev, int S, int b, int pos0, int rope_delta) {
     for (int c0 = 0; c0 < S; c0 += lm->prefill_rows) {
         const int n = std::min(lm->prefill_rows, S - c0);
-        FSB_TRY(prefill_chunk(lm, toks_dev, S, c0, n, b, pos0 + c0, rope_delta));
-        if (c0 + n == S)
-            FSB_CUDA_OK(cudaMemcpyAsync(lm->s.hidden + (size_t)b * lm->D, lm->s.x + (size_t)(n - 1) * lm->D,
-                                        lm->D * sizeof(float), cudaMemcpyDeviceToDevice, lm->stream));
+        std::vector<PrefillSeg> segs(1);
+        segs[0] = PrefillSeg{toks_dev, S, c0, n, b, pos0 + c0, rope_delta, 0, c0 + n == S};
+        FSB_TRY(prefill_pass(lm, segs));
     }
+    return FSB_OK;
+}
+
+// Prefill of a whole batch: the rows' prompts are packed back to back into passes of up to `prefill_rows` positions.
+// toks_dev: the rows' (C+1, P_b) arrays back to back.
+static int prefill_batch(fsb_lm *lm, const uint32_t *toks_dev, const int32_t *prompt_lens, int bsz) {
+    std::vector<PrefillSeg> segs;
+    int used = 0;
+    size_t tok_off = 0;
+    for (int b = 0; b < bsz; ++b) {
+        const int P = prompt_lens[b];
+        for (int c0 = 0; c0 < P;) {
+            if (used == lm->prefill_rows) {
+                FSB_TRY(prefill_pass(lm, segs));
+                segs.clear();
+                used = 0;
+            }
+            const int n = std::min(lm->prefill_rows - used, P - c0);
+            segs.push_back(PrefillSeg{toks_dev + tok_off, P, c0, n, b, lm->kv_len[b] + c0, 0, used, c0 + n == P});
+            used += n;
+            c0 += n;
+        }
+        tok_off += (size_t)(lm->C + 1) * P;
+    }
+    if (!segs.empty()) FSB_TRY(prefill_pass(lm, segs));
     return FSB_OK;
 }
 
@@ -857,7 +900,8 @@ static int lm_create_impl(fsb_lm *lm, const fsb_tensor *w, size_t n) {
     FSB_TRY(dev_alloc(lm, &s.hidden, (size_t)B * D));
     FSB_TRY(dev_alloc(lm, &s.fast_x, (size_t)B * D));
     FSB_TRY(dev_alloc(lm, &s.fast_logits, (size_t)B * CS));
-    FSB_TRY(dev_alloc(lm, &s.toks, (size_t)(C + 1) * std::max(lm->max_len, 1)));
+    lm->toks_cap = (size_t)(C + 1) * std::max(lm->max_len, 1) * B;  // every row's prompt at once (batched prefill)
+    FSB_TRY(dev_alloc(lm, &s.toks, lm->toks_cap));
 
     GenState &g = lm->h_st;
     memset(&g, 0, sizeof(g));
@@ -1026,13 +1070,15 @@ static int generate_impl(fsb_lm *lm, const uint32_t *const *prompts, const int32
     uint64_t graph_l = 0;
     // ---- prefill, row by row (independent utterances) ----
     FSB_CUDA_OK(cudaEventRecord(lm->ev0, st));
-    for (int b = 0; b < bsz; ++b) {
-        const int P = prompt_lens[b];
-        FSB_CUDA_OK(cudaMemcpyAsync(lm->s.toks, prompts[b], (size_t)(C + 1) * P * sizeof(uint32_t),
-                                    cudaMemcpyHostToDevice, st));
-        FSB_TRY(prefill_row(lm, lm->s.toks, P, b, lm->kv_len[b], 0));
-        // prompts[b] may be pageable: the copy above is synchronous w.r.t. the host for pageable
-        // memory, and s.toks is only reused after the row's kernels are queued on the same stream.
+    {
+        size_t tok_off = 0;
+        for (int b = 0; b < bsz; ++b) {
+            const size_t n = (size_t)(C + 1) * prompt_lens[b];
+            FSB_REQUIRE(tok_off + n <= lm->toks_cap, FSB_ERR_STATE, "prompts exceed the token staging arena");
+            FSB_CUDA_OK(cudaMemcpyAsync(lm->s.toks + tok_off, prompts[b], n * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+            tok_off += n;
+        }
+        FSB_TRY(prefill_batch(lm, lm->s.toks, prompt_lens, bsz));
     }
     int total_max = 0;
     for (int b = 0; b < bsz; ++b) total_max = std::max(total_max, max_frames[b]);
@@ -1271,7 +1317,8 @@ int fsb_lm_create(const fsb_model_args *args, const fsb_token_config *tok, const
     lm->max_batch = opts->max_batch;
     lm->max_len = opts->max_seq_len > 0 ? std::min(opts->max_seq_len, args->max_seq_len) : args->max_seq_len;
     lm->fast_len = lm->C;
-    lm->prefill_rows = 1024;
+    // positions per prefill pass: one prompt for a single-row handle, several rows' prompts packed together otherwise
+    lm->prefill_rows = lm->max_batch > 1 ? 4096 : 1024;
     lm->nsplit = 16;
     FSB_REQUIRE(tok->im_end_id < (uint32_t)lm->V && tok->semantic_start_id < (uint32_t)lm->V, FSB_ERR_INVALID,
                 "token ids outside the vocabulary");
