@@ -42,6 +42,7 @@ struct fsb_lm {
     int wdt;  // weight dtype
     int prefill_rows;
     size_t toks_cap = 0;  // u32 words of the prompt staging arena
+    int4 *d_segs = nullptr;  // segment table of the current prefill pass (<= 256 entries)
     int nsplit;
     int n_slow_logits, slow_row0, slow_rest_base;
     cudaStream_t stream = nullptr;
@@ -345,6 +346,19 @@ static int prefill_pass(fsb_lm *lm, const std::vector<PrefillSeg> &segs) {
     const bool tc = lm->tc_ok;
     const int bn = tc_pick_bn(S), bi = bn == 32 ? 0 : (bn == 64 ? 1 : 2);
     const int seg = lm->prefill_rows;
+    // segment table for the batched RoPE / attention launches (rope_delta != 0 only occurs on the single-row step API)
+    bool batched = segs.size() > 1 && segs.size() <= 256;
+    int max_n = 0;
+    for (const PrefillSeg &g : segs) {
+        max_n = std::max(max_n, g.n);
+        if (g.rope_delta != 0) batched = false;
+    }
+    if (batched) {
+        std::vector<int4> h(segs.size());
+        for (size_t i = 0; i < segs.size(); ++i) h[i] = make_int4(segs[i].b, segs[i].pos0, segs[i].n, segs[i].off);
+        // (pageable source: the copy is staged by the runtime before the call returns)
+        FSB_CUDA_OK(cudaMemcpyAsync(lm->d_segs, h.data(), h.size() * sizeof(int4), cudaMemcpyHostToDevice, st));
+    }
     for (int l = 0; l < lm->NL; ++l) {
         const LayerW &L = lm->layers[l];
         if (tc) {
@@ -356,15 +370,25 @@ static int prefill_pass(fsb_lm *lm, const std::vector<PrefillSeg> &segs) {
             LAUNCH_CHECK(lm);
             FSB_TRY(gemm<EPI_STORE>(lm, s.xn, L.wqkv, nullptr, s.qkv, S, QKV, D));
         }
-        for (const PrefillSeg &g : segs) {
-            rope_append_rows_kernel<<<g.n, 256, 0, st>>>(s.qkv + (size_t)g.off * QKV, s.q + (size_t)g.off * H * hd, slow_k(lm, l),
-                                                         slow_v(lm, l), lm->cosT, lm->sinT, g.b, g.pos0, g.rope_delta, H, KV, hd,
-                                                         lm->max_len);
+        if (batched) {
+            // one launch for every row segment of the pass (a 384-token prompt alone yields 96 CTAs of 105 us each)
+            rope_append_rows_kernel<<<dim3(max_n, (unsigned)segs.size()), 256, 0, st>>>(
+                s.qkv, s.q, slow_k(lm, l), slow_v(lm, l), lm->cosT, lm->sinT, 0, 0, 0, H, KV, hd, lm->max_len, lm->d_segs);
             LAUNCH_CHECK(lm);
-            attn_prefill_kernel<<<dim3((g.n + kPrefQ - 1) / kPrefQ, KV), 512, 0, st>>>(
-                s.q + (size_t)g.off * H * hd, slow_k(lm, l), slow_v(lm, l), g.b, g.pos0, g.n, H, KV, hd, lm->max_len, scale,
-                s.att + (size_t)g.off * H * hd);
+            attn_prefill_kernel<<<dim3((max_n + kPrefQ - 1) / kPrefQ, KV, (unsigned)segs.size()), 512, 0, st>>>(
+                s.q, slow_k(lm, l), slow_v(lm, l), 0, 0, 0, H, KV, hd, lm->max_len, scale, s.att, lm->d_segs);
             LAUNCH_CHECK(lm);
+        } else {
+            for (const PrefillSeg &g : segs) {
+                rope_append_rows_kernel<<<g.n, 256, 0, st>>>(s.qkv + (size_t)g.off * QKV, s.q + (size_t)g.off * H * hd,
+                                                             slow_k(lm, l), slow_v(lm, l), lm->cosT, lm->sinT, g.b, g.pos0,
+                                                             g.rope_delta, H, KV, hd, lm->max_len);
+                LAUNCH_CHECK(lm);
+                attn_prefill_kernel<<<dim3((g.n + kPrefQ - 1) / kPrefQ, KV), 512, 0, st>>>(
+                    s.q + (size_t)g.off * H * hd, slow_k(lm, l), slow_v(lm, l), g.b, g.pos0, g.n, H, KV, hd, lm->max_len, scale,
+                    s.att + (size_t)g.off * H * hd);
+                LAUNCH_CHECK(lm);
+            }
         }
         if (tc) {
             FSB_TRY(tc_split3(s.att, lm->sp_att, (size_t)S * H * hd, (size_t)seg * H * hd, st));
@@ -902,6 +926,7 @@ static int lm_create_impl(fsb_lm *lm, const fsb_tensor *w, size_t n) {
     FSB_TRY(dev_alloc(lm, &s.fast_logits, (size_t)B * CS));
     lm->toks_cap = (size_t)(C + 1) * std::max(lm->max_len, 1) * B;  // every row's prompt at once (batched prefill)
     FSB_TRY(dev_alloc(lm, &s.toks, lm->toks_cap));
+    FSB_TRY(dev_alloc(lm, &lm->d_segs, 256));
 
     GenState &g = lm->h_st;
     memset(&g, 0, sizeof(g));

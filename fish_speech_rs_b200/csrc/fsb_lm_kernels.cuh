@@ -399,7 +399,17 @@ __global__ void swiglu_rows_kernel(const float *g1, const float *__restrict__ g3
 __global__ void rope_append_rows_kernel(const float *__restrict__ qkv, float *__restrict__ q, float *__restrict__ kc,
                                         float *__restrict__ vc, const float *__restrict__ cosT,
                                         const float *__restrict__ sinT, int b, int pos0, int rope_delta, int H,
-                                        int KV, int hd, int max_len) {
+                                        int KV, int hd, int max_len, const int4 *segs = nullptr) {
+    // batched form (prefill of several rows in one pass): blockIdx.y = segment {row b, cache pos0, positions n, first
+    // position of the segment inside the pass}
+    if (segs) {
+        const int4 sg = segs[blockIdx.y];
+        if ((int)blockIdx.x >= sg.z) return;
+        b = sg.x;
+        pos0 = sg.y;
+        qkv += (size_t)sg.w * (H + 2 * KV) * hd;
+        q += (size_t)sg.w * H * hd;
+    }
     const int s = blockIdx.x;
     const int pos = pos0 + s;
     const int rpos = pos + rope_delta;
@@ -437,7 +447,18 @@ constexpr int kPrefStride = 65;    // floats per staged K row (conflict-free col
 constexpr int kPrefIPW = 4;        // (query, head) items per warp kept in registers while the K / V tiles stream by
 __global__ void __launch_bounds__(512) attn_prefill_kernel(const float *__restrict__ q, const float *__restrict__ kc,
                                                            const float *__restrict__ vc, int b, int pos0, int S, int H, int KV,
-                                                           int hd, int max_len, float scale, float *__restrict__ y) {
+                                                           int hd, int max_len, float scale, float *__restrict__ y,
+                                                           const int4 *segs = nullptr) {
+    // batched form: blockIdx.z = segment (see rope_append_rows_kernel); one launch covers every row of a prefill pass
+    if (segs) {
+        const int4 sg = segs[blockIdx.z];
+        if ((int)blockIdx.x * kPrefQ >= sg.z) return;
+        b = sg.x;
+        pos0 = sg.y;
+        S = sg.z;
+        q += (size_t)sg.w * H * hd;
+        y += (size_t)sg.w * H * hd;
+    }
     // hd == 64 (host-checked).  Work items = kPrefQ queries x n_rep heads; 16 warps x kPrefIPW items per round.
     __shared__ float ks[32 * kPrefStride];
     __shared__ float vs[32 * 64];
