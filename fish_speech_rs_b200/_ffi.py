@@ -92,6 +92,13 @@ SYMBOLS = {
                                                P(fsb_sampling_args), C.c_uint32, C.c_int32, P(C.c_void_p),
                                                C.c_size_t, P(C.c_size_t)]),
     "fsb_lm_last_frames": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_size_t, P(C.c_size_t)]),
+    "fsb_lm_kv_snapshot_save": (C.c_int, [C.c_void_p, C.c_int32, C.c_size_t, P(C.c_void_p)]),
+    "fsb_lm_kv_snapshot_restore": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32]),
+    "fsb_lm_kv_snapshot_free": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "fsb_lm_session_begin": (C.c_int, [C.c_void_p, P(fsb_sampling_args), C.c_uint32]),
+    "fsb_lm_session_admit": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_size_t, C.c_int32]),
+    "fsb_lm_session_run": (C.c_int, [C.c_void_p, C.c_int32, P(C.c_int32), P(C.c_int32)]),
+    "fsb_lm_session_collect": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_size_t, P(C.c_size_t)]),
     "fsb_lm_get_stats": (C.c_int, [C.c_void_p, P(fsb_lm_stats)]),
     "fsb_lm_set_profile": (C.c_int, [C.c_void_p, C.c_int]),
     "fsb_codec_create": (C.c_int, [P(fsb_tensor), C.c_size_t, P(fsb_codec_options), P(C.c_void_p)]),

@@ -33,6 +33,11 @@ struct Scratch {
 
 using namespace fsb;
 
+struct fsb_kv_snapshot {
+    float *k = nullptr, *v = nullptr;  // (NL, KV, n, hd) each
+    size_t n = 0;
+};
+
 struct fsb_lm {
     fsb_model_args cfg;
     fsb_token_config tok;
@@ -62,6 +67,8 @@ struct fsb_lm {
     int *h_pin = nullptr;     // pinned staging (ints)
     std::map<int, cudaGraphExec_t> frame_graphs;  // keyed by bsz (+ 4096 when hidden states are collected)
     std::map<int, cudaGraphExec_t> tail_graphs;
+    bool session = false;              // fsb_lm_session_*: rows are slots
+    std::vector<int> slot_state;       // 0 free, 1 generating, 2 finished (awaiting collect)
     bool collect_hidden = false;  // generate_blocking_with_hidden: per-op path + store_hidden_kernel per frame
     float *hid = nullptr;         // (max_batch, out_cap, D), allocated on first use
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
@@ -811,11 +818,11 @@ static int megab_setup(fsb_lm *lm) {
 }
 
 // all rows of the batch in one launch (bsz <= 32)
-static int megab_launch_rows(fsb_lm *lm, int nb, int nframes) {
+static int megab_launch_rows(fsb_lm *lm, int nb, int nframes, bool first_is_tail = true) {
     MegaParams mp = lm->mp;
     mp.nb = nb;
     mp.nframes = nframes;
-    mp.first_is_tail = 1;
+    mp.first_is_tail = first_is_tail ? 1 : 0;
     mp.row0 = 0;
     mp.st = lm->h_st;
     const size_t cnt_words = (size_t)2 * 32 + 4;
@@ -1561,6 +1568,201 @@ int fsb_lm_last_frames(fsb_lm *lm, int32_t row, uint32_t *out, size_t cap, size_
     for (int f = 0; f < nf; ++f)
         for (int c = 0; c < C1; ++c) out[(size_t)c * cap + f] = h[(size_t)f * C1 + c];
     *out_len = (size_t)nf;
+    return FSB_OK;
+}
+
+// ---------------------------------------------------------------- per-voice KV snapshots
+int fsb_lm_kv_snapshot_save(fsb_lm *lm, int32_t row, size_t n_positions, fsb_kv_snapshot **out) {
+    FSB_TRY(check_handle(lm));
+    FSB_REQUIRE(out && row >= 0 && row < lm->max_batch, FSB_ERR_INVALID, "kv_snapshot_save: bad arguments");
+    FSB_REQUIRE(n_positions >= 1 && n_positions <= (size_t)lm->kv_len[row], FSB_ERR_STATE,
+                "kv_snapshot_save: row %d caches %d positions, %zu requested", row, lm->kv_len[row], n_positions);
+    std::unique_ptr<fsb_kv_snapshot> sn(new fsb_kv_snapshot());
+    sn->n = n_positions;
+    const size_t per_layer = (size_t)lm->KV * n_positions * lm->hd;
+    FSB_CUDA_OK(cudaMalloc((void **)&sn->k, per_layer * lm->NL * sizeof(float)));
+    if (cudaMalloc((void **)&sn->v, per_layer * lm->NL * sizeof(float)) != cudaSuccess) {
+        cudaFree(sn->k);
+        set_error("kv_snapshot_save: out of memory");
+        return FSB_ERR_OOM;
+    }
+    const size_t width = n_positions * lm->hd * sizeof(float), pitch = (size_t)lm->max_len * lm->hd * sizeof(float);
+    for (int l = 0; l < lm->NL; ++l) {
+        const size_t src = ((size_t)row * lm->KV) * lm->max_len * lm->hd;
+        FSB_CUDA_OK(cudaMemcpy2DAsync(sn->k + l * per_layer, width, slow_k(lm, l) + src, pitch, width, lm->KV, cudaMemcpyDeviceToDevice, lm->stream));
+        FSB_CUDA_OK(cudaMemcpy2DAsync(sn->v + l * per_layer, width, slow_v(lm, l) + src, pitch, width, lm->KV, cudaMemcpyDeviceToDevice, lm->stream));
+    }
+    FSB_CUDA_OK(cudaStreamSynchronize(lm->stream));
+    *out = sn.release();
+    return FSB_OK;
+}
+
+int fsb_lm_kv_snapshot_restore(fsb_lm *lm, const fsb_kv_snapshot *sn, int32_t row) {
+    FSB_TRY(check_handle(lm));
+    FSB_REQUIRE(sn && row >= 0 && row < lm->max_batch, FSB_ERR_INVALID, "kv_snapshot_restore: bad arguments");
+    FSB_REQUIRE(sn->n <= (size_t)lm->max_len, FSB_ERR_STATE, "kv_snapshot_restore: %zu positions exceed the KV arena", sn->n);
+    const size_t per_layer = (size_t)lm->KV * sn->n * lm->hd;
+    const size_t width = sn->n * lm->hd * sizeof(float), pitch = (size_t)lm->max_len * lm->hd * sizeof(float);
+    for (int l = 0; l < lm->NL; ++l) {
+        const size_t dst = ((size_t)row * lm->KV) * lm->max_len * lm->hd;
+        FSB_CUDA_OK(cudaMemcpy2DAsync(slow_k(lm, l) + dst, pitch, sn->k + l * per_layer, width, width, lm->KV, cudaMemcpyDeviceToDevice, lm->stream));
+        FSB_CUDA_OK(cudaMemcpy2DAsync(slow_v(lm, l) + dst, pitch, sn->v + l * per_layer, width, width, lm->KV, cudaMemcpyDeviceToDevice, lm->stream));
+    }
+    FSB_CUDA_OK(cudaStreamSynchronize(lm->stream));
+    lm->kv_len[row] = (int)sn->n;
+    return FSB_OK;
+}
+
+int fsb_lm_kv_snapshot_free(fsb_lm *lm, fsb_kv_snapshot *sn) {
+    if (!sn) return FSB_OK;
+    if (lm) cudaSetDevice(lm->opt.device);
+    cudaFree(sn->k);
+    cudaFree(sn->v);
+    delete sn;
+    return FSB_OK;
+}
+
+// ---------------------------------------------------------------- continuous batching
+static int session_emit(fsb_lm *lm, int row, uint32_t *out_codes, size_t cap, size_t *out_len) {
+    const int C = lm->C;
+    int nf = 0;
+    FSB_CUDA_OK(cudaMemcpy(&nf, lm->h_st.frame + row, sizeof(int), cudaMemcpyDeviceToHost));
+    std::vector<uint32_t> h((size_t)nf * (C + 1));
+    if (nf > 0)
+        FSB_CUDA_OK(cudaMemcpy(h.data(), lm->h_st.out + (size_t)row * lm->h_st.out_cap * (C + 1), h.size() * sizeof(uint32_t),
+                               cudaMemcpyDeviceToHost));
+    size_t T = 0;
+    for (int f = 0; f < nf; ++f) {  // generate_blocking_with_hidden: frame 0 always kept (Q4), later <|im_end|> frames dropped
+        const uint32_t *fr = &h[(size_t)f * (C + 1)];
+        if (f > 0 && fr[0] == lm->tok.im_end_id) continue;
+        FSB_REQUIRE(T < cap, FSB_ERR_INVALID, "slot %d: output capacity %zu too small", row, cap);
+        for (int c = 0; c < C; ++c) out_codes[(size_t)c * cap + T] = fr[1 + c];
+        ++T;
+    }
+    *out_len = T;
+    return FSB_OK;
+}
+
+int fsb_lm_session_begin(fsb_lm *lm, const fsb_sampling_args *sa, uint32_t flags) {
+    FSB_TRY(check_handle(lm));
+    FSB_REQUIRE(sa, FSB_ERR_INVALID, "session_begin: null sampling args");
+    FSB_REQUIRE(lm->megab_ok && lm->max_batch >= 2 && lm->max_batch <= lm->megab_rows_cap, FSB_ERR_UNSUPPORTED,
+                "sessions need the wide-batch kernel (bf16 weights, Fish 1.4/1.5 shapes, 2 <= max_batch <= 32)");
+    FSB_REQUIRE(std::isfinite(sa->temp) && sa->temp >= 0.0 && std::isfinite(sa->top_p) && (sa->temp <= 1e-7 || sa->top_k >= 1) &&
+                    std::isfinite(sa->repetition_penalty) && sa->repetition_penalty != 0.f,
+                FSB_ERR_INVALID, "session_begin: invalid sampling arguments");
+    GenState &g = lm->h_st;
+    g.fixed_len = (flags & FSB_GEN_FIXED_LEN) ? 1 : 0;
+    g.legacy_slow = (lm->opt.fish_version != FSB_FISH_1_5) ? 1 : 0;
+    g.sp.greedy = sa->temp <= 1e-7 ? 1 : 0;
+    g.sp.inv_temp = g.sp.greedy ? 1.0f : (float)(1.0 / sa->temp);
+    g.sp.top_p = (float)sa->top_p;
+    g.sp.top_k = sa->top_k;
+    g.sp.penalty = sa->repetition_penalty;
+    g.sp.seed = sa->seed;
+    FSB_REQUIRE(g.sp.greedy || g.sp.top_k <= (uint32_t)kSelMaxK, FSB_ERR_UNSUPPORTED, "sessions need top_k <= %d", kSelMaxK);
+    const int B = lm->max_batch;
+    cudaStream_t st = lm->stream;
+    FSB_TRY(upload_state(lm));
+    FSB_CUDA_OK(cudaMemsetAsync(g.active, 0, B * sizeof(int), st));
+    FSB_CUDA_OK(cudaMemsetAsync(g.eos, 0, B * sizeof(int), st));
+    FSB_CUDA_OK(cudaMemsetAsync(g.frame, 0, B * sizeof(int), st));
+    FSB_CUDA_OK(cudaMemsetAsync(g.n_active, 0, B * sizeof(int), st));
+    FSB_CUDA_OK(cudaStreamSynchronize(st));
+    lm->slot_state.assign(B, 0);
+    std::fill(lm->kv_len.begin(), lm->kv_len.end(), 0);
+    lm->session = true;
+    return FSB_OK;
+}
+
+int fsb_lm_session_admit(fsb_lm *lm, int32_t slot, const uint32_t *prompt, int32_t P, size_t max_new_tokens,
+                         int32_t fixed_len) {
+    FSB_TRY(check_handle(lm));
+    auto body = [&]() -> int {
+        FSB_REQUIRE(lm->session, FSB_ERR_STATE, "session_admit: no session (call fsb_lm_session_begin)");
+        FSB_REQUIRE(slot >= 0 && slot < lm->max_batch && prompt && P >= 1, FSB_ERR_INVALID, "session_admit: bad arguments");
+        FSB_REQUIRE(lm->slot_state[slot] == 0, FSB_ERR_STATE, "session_admit: slot %d is not free", slot);
+        const int C = lm->C;
+        GenState &g = lm->h_st;
+        for (int i = 0; i < P; ++i)
+            FSB_REQUIRE(prompt[i] < (uint32_t)lm->V, FSB_ERR_INVALID, "session_admit: token id %u >= vocab_size", prompt[i]);
+        for (int c = 1; c <= C; ++c)
+            for (int i = 0; i < P; ++i)
+                FSB_REQUIRE(prompt[(size_t)c * P + i] < (uint32_t)lm->CS, FSB_ERR_INVALID, "session_admit: code out of range");
+        long long lim = (long long)max_new_tokens - P + 2;  // Q3
+        if (lim < 1) lim = 1;
+        if (g.fixed_len) {
+            FSB_REQUIRE(fixed_len >= 1, FSB_ERR_INVALID, "session_admit: FSB_GEN_FIXED_LEN needs fixed_len >= 1");
+            lim = std::min<long long>(lim, fixed_len);
+        }
+        FSB_REQUIRE(P + lim <= lm->max_len && lim <= g.out_cap, FSB_ERR_STATE,
+                    "session_admit: %d prompt + %lld frames exceed the KV arena (%d positions)", P, lim, lm->max_len);
+        cudaStream_t st = lm->stream;
+        FSB_CUDA_OK(cudaMemcpyAsync(lm->s.toks, prompt, (size_t)(C + 1) * P * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        lm->kv_len[slot] = 0;
+        FSB_TRY(prefill_row(lm, lm->s.toks, P, slot, 0, 0));
+        int *hp = lm->h_pin;
+        hp[0] = 1; hp[1] = (int)lim; hp[2] = P; hp[3] = 0; hp[4] = 1;
+        FSB_CUDA_OK(cudaMemcpyAsync(g.active + slot, hp, sizeof(int), cudaMemcpyHostToDevice, st));
+        FSB_CUDA_OK(cudaMemcpyAsync(g.max_frames + slot, hp + 1, sizeof(int), cudaMemcpyHostToDevice, st));
+        FSB_CUDA_OK(cudaMemcpyAsync(g.pos + slot, hp + 2, sizeof(int), cudaMemcpyHostToDevice, st));
+        FSB_CUDA_OK(cudaMemcpyAsync(g.eos + slot, hp + 3, sizeof(int), cudaMemcpyHostToDevice, st));
+        FSB_CUDA_OK(cudaMemcpyAsync(g.frame + slot, hp + 3, sizeof(int), cudaMemcpyHostToDevice, st));
+        FSB_CUDA_OK(cudaMemcpyAsync(g.n_active + 1, hp + 4, sizeof(int), cudaMemcpyHostToDevice, st));  // live-row counter of the launch below
+        FSB_CUDA_OK(cudaMemsetAsync(g.rep + (size_t)slot * C, 0, (size_t)C * sizeof(RepPenState), st));
+        FSB_CUDA_OK(cudaStreamSynchronize(st));  // hp is reused
+        // the frame produced from the prompt itself (slow head on the prefilled state + the C fast steps), by the
+        // single-row kernel on this row alone; the slot then joins the wide launches in resume mode
+        FSB_TRY(mega_launch(lm, slot, 1, 1, 1, true));
+        FSB_CUDA_OK(cudaMemcpyAsync(hp, g.active + slot, sizeof(int), cudaMemcpyDeviceToHost, st));
+        FSB_CUDA_OK(cudaStreamSynchronize(st));
+        lm->slot_state[slot] = hp[0] ? 1 : 2;
+        lm->kv_len[slot] = P;
+        return FSB_OK;
+    };
+    return finish(lm, body());
+}
+
+int fsb_lm_session_run(fsb_lm *lm, int32_t max_frames, int32_t *active, int32_t *n_active) {
+    FSB_TRY(check_handle(lm));
+    auto body = [&]() -> int {
+        FSB_REQUIRE(lm->session, FSB_ERR_STATE, "session_run: no session");
+        FSB_REQUIRE(max_frames >= 1, FSB_ERR_INVALID, "session_run: max_frames must be >= 1");
+        const int B = lm->max_batch;
+        int live = 0;
+        for (int b = 0; b < B; ++b) live += lm->slot_state[b] == 1;
+        cudaStream_t st = lm->stream;
+        int *hp = lm->h_pin;
+        if (live > 0) {
+            hp[0] = live;
+            FSB_CUDA_OK(cudaMemcpyAsync(lm->h_st.n_active, hp, sizeof(int), cudaMemcpyHostToDevice, st));
+            FSB_CUDA_OK(cudaStreamSynchronize(st));
+            FSB_TRY(megab_launch_rows(lm, B, max_frames, false));  // resume mode: every frame starts with the slow stack
+            FSB_CUDA_OK(cudaMemcpyAsync(hp, lm->h_st.active, B * sizeof(int), cudaMemcpyDeviceToHost, st));
+            FSB_CUDA_OK(cudaMemcpyAsync(hp + B, lm->h_st.pos, B * sizeof(int), cudaMemcpyDeviceToHost, st));
+            FSB_CUDA_OK(cudaStreamSynchronize(st));
+            live = 0;
+            for (int b = 0; b < B; ++b)
+                if (lm->slot_state[b] == 1) {
+                    lm->kv_len[b] = hp[B + b];
+                    if (!hp[b]) lm->slot_state[b] = 2;
+                    else ++live;
+                }
+        }
+        if (active)
+            for (int b = 0; b < B; ++b) active[b] = lm->slot_state[b] == 1 ? 1 : 0;
+        if (n_active) *n_active = live;
+        return FSB_OK;
+    };
+    return finish(lm, body());
+}
+
+int fsb_lm_session_collect(fsb_lm *lm, int32_t slot, uint32_t *out_codes, size_t cap, size_t *out_len) {
+    FSB_TRY(check_handle(lm));
+    FSB_REQUIRE(lm->session && slot >= 0 && slot < lm->max_batch && out_codes && out_len, FSB_ERR_INVALID, "session_collect: bad arguments");
+    FSB_REQUIRE(lm->slot_state[slot] == 2, FSB_ERR_STATE, "session_collect: slot %d has not finished", slot);
+    FSB_TRY(session_emit(lm, slot, out_codes, cap, out_len));
+    lm->slot_state[slot] = 0;
     return FSB_OK;
 }
 

@@ -207,7 +207,9 @@ struct MegaB {
     __device__ __forceinline__ Step first_step() const {
         Step s;
         s.frame = 0; s.pass = 0; s.l = 0;
-        s.kind = K_HEAD;  // the launch starts at the slow head of frame 0 (the hidden rows come from the prefill)
+        // first_is_tail: the launch starts at the slow head of frame 0 (the hidden rows come from the prefill).  Otherwise
+        // it RESUMES rows whose previous frame is complete: every frame of the launch runs the slow stack first
+        s.kind = p.first_is_tail ? K_HEAD : K_QKV;
         return s;
     }
     __device__ __forceinline__ Step advance(const Step &s) const {
@@ -1019,6 +1021,34 @@ struct MegaB {
         }
     }
 
+    // slow input of the row's next frame: DualARTransformer::embed (dual_ar.rs:532-567) on the codes of the frame just
+    // emitted (s_prev), plus its operand image (first block's attention_norm folded in) and sum of squares
+    __device__ __forceinline__ void embed_next_input() {
+        const int b = blockIdx.x;
+        const __nv_bfloat16 *emb = reinterpret_cast<const __nv_bfloat16 *>(p.emb);
+        const __nv_bfloat16 *cbe = reinterpret_cast<const __nv_bfloat16 *>(p.cb_emb);
+        const uint32_t tok0 = s_prev[0];
+        const bool msk = p.has_end ? (tok0 <= p.sem_end && tok0 >= p.sem_start) : (tok0 == p.sem_start);
+        const float mf = msk ? 1.f : 0.f;
+        const uint2 r0 = __ldg(reinterpret_cast<const uint2 *>(emb + (size_t)tok0 * kD) + tid);
+        float4 acc = make_float4(bf16lo(r0.x), bf16hi(r0.x), bf16lo(r0.y), bf16hi(r0.y));
+        uint2 rc[kC];
+#pragma unroll
+        for (int c = 0; c < kC; ++c)
+            rc[c] = __ldg(reinterpret_cast<const uint2 *>(cbe + ((size_t)c * kCS + s_prev[1 + c]) * kD) + tid);
+#pragma unroll
+        for (int c = 0; c < kC; ++c) {
+            acc.x = __fadd_rn(acc.x, __fmul_rn(bf16lo(rc[c].x), mf));
+            acc.y = __fadd_rn(acc.y, __fmul_rn(bf16hi(rc[c].x), mf));
+            acc.z = __fadd_rn(acc.z, __fmul_rn(bf16lo(rc[c].y), mf));
+            acc.w = __fadd_rn(acc.w, __fmul_rn(bf16hi(rc[c].y), mf));
+        }
+        reinterpret_cast<float4 *>(p.x + (size_t)b * kD)[tid] = acc;
+        const float4 g4 = __ldg(reinterpret_cast<const float4 *>(normtab[0]) + tid);  // first slow block's attention_norm
+        store_xop4(e.xop_x, b, 4 * tid, make_float4(__fmul_rn(acc.x, g4.x), __fmul_rn(acc.y, g4.y), __fmul_rn(acc.z, g4.z), __fmul_rn(acc.w, g4.w)));
+        finish_row(acc.x * acc.x + acc.y * acc.y + acc.z * acc.z + acc.w * acc.w, e.ssq_x + (size_t)b * kMBSsq);
+    }
+
     __device__ __forceinline__ void sample_slow(int kframe) {
         const GenState &st = p.st;
         const int b = blockIdx.x, C1 = kC + 1;
@@ -1140,31 +1170,7 @@ struct MegaB {
             const uint32_t *src = reinterpret_cast<const uint32_t *>(s_rep);
             uint32_t *dst = reinterpret_cast<uint32_t *>(st.rep + (size_t)b * kC);
             for (int i = tid; i < kC * words; i += kMBWorkers) dst[i] = src[i];
-            if (cont) {
-                // next frame's slow input: DualARTransformer::embed (dual_ar.rs:532-567) on this frame's codes
-                const __nv_bfloat16 *emb = reinterpret_cast<const __nv_bfloat16 *>(p.emb);
-                const __nv_bfloat16 *cbe = reinterpret_cast<const __nv_bfloat16 *>(p.cb_emb);
-                const uint32_t tok0 = s_prev[0];
-                const bool msk = p.has_end ? (tok0 <= p.sem_end && tok0 >= p.sem_start) : (tok0 == p.sem_start);
-                const float mf = msk ? 1.f : 0.f;
-                const uint2 r0 = __ldg(reinterpret_cast<const uint2 *>(emb + (size_t)tok0 * kD) + tid);
-                float4 acc = make_float4(bf16lo(r0.x), bf16hi(r0.x), bf16lo(r0.y), bf16hi(r0.y));
-                uint2 rc[kC];
-#pragma unroll
-                for (int c = 0; c < kC; ++c)
-                    rc[c] = __ldg(reinterpret_cast<const uint2 *>(cbe + ((size_t)c * kCS + s_prev[1 + c]) * kD) + tid);
-#pragma unroll
-                for (int c = 0; c < kC; ++c) {
-                    acc.x = __fadd_rn(acc.x, __fmul_rn(bf16lo(rc[c].x), mf));
-                    acc.y = __fadd_rn(acc.y, __fmul_rn(bf16hi(rc[c].x), mf));
-                    acc.z = __fadd_rn(acc.z, __fmul_rn(bf16lo(rc[c].y), mf));
-                    acc.w = __fadd_rn(acc.w, __fmul_rn(bf16hi(rc[c].y), mf));
-                }
-                reinterpret_cast<float4 *>(p.x + (size_t)b * kD)[tid] = acc;
-                const float4 g4 = __ldg(reinterpret_cast<const float4 *>(normtab[0]) + tid);  // first slow block's attention_norm
-                store_xop4(e.xop_x, b, 4 * tid, make_float4(__fmul_rn(acc.x, g4.x), __fmul_rn(acc.y, g4.y), __fmul_rn(acc.z, g4.z), __fmul_rn(acc.w, g4.w)));
-                finish_row(acc.x * acc.x + acc.y * acc.y + acc.z * acc.z + acc.w * acc.w, e.ssq_x + (size_t)b * kMBSsq);
-            }
+            if (cont) embed_next_input();
         }
         wsync();
     }
@@ -1174,8 +1180,11 @@ struct MegaB {
         Step cur = first_step();
         const bool samples = (int)blockIdx.x < p.nb;
         if (samples) load_sampler_state();
+        if (samples && !p.first_is_tail) {
+            if (s_active[0]) embed_next_input();  // resume: the row's input is rebuilt from the codes of its last frame
+        }
         // sum of squares of the prefilled hidden rows (the launch starts at the slow head of frame 0)
-        if (samples) {
+        if (samples && p.first_is_tail) {
             const float4 v = __ldcg(reinterpret_cast<const float4 *>(p.x + (size_t)blockIdx.x * kD) + tid);
             const float4 g4 = __ldg(reinterpret_cast<const float4 *>(p.norm) + tid);  // consumer: the slow head
             store_xop4(e.xop_x, blockIdx.x, 4 * tid, make_float4(__fmul_rn(v.x, g4.x), __fmul_rn(v.y, g4.y), __fmul_rn(v.z, g4.z), __fmul_rn(v.w, g4.w)));

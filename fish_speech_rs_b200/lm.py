@@ -122,6 +122,42 @@ class DualARTransformer:
         F.check(F.lib().fsb_lm_last_frames(self._h, int(row), out.ctypes.data, cap, C.byref(n)))
         return out[:, : n.value].copy()
 
+    # ---- per-voice conditioning KV (speech.rs:40)
+    def kv_snapshot_save(self, row: int, n_positions: int):
+        h = C.c_void_p()
+        F.check(F.lib().fsb_lm_kv_snapshot_save(self._h, int(row), int(n_positions), C.byref(h)))
+        return h
+
+    def kv_snapshot_restore(self, snap, row: int):
+        F.check(F.lib().fsb_lm_kv_snapshot_restore(self._h, snap, int(row)))
+
+    def kv_snapshot_free(self, snap):
+        F.check(F.lib().fsb_lm_kv_snapshot_free(self._h, snap))
+
+    # ---- continuous batching (state.rs:13, static_batch.rs:160-173)
+    def session_begin(self, sampling_args: "SamplingArgs", fixed_len: bool = False):
+        sa = sampling_args._c()
+        F.check(F.lib().fsb_lm_session_begin(self._h, C.byref(sa), F.FSB_GEN_FIXED_LEN if fixed_len else 0))
+
+    def session_admit(self, slot: int, prompt: np.ndarray, max_new_tokens: int, fixed_len: int = 0):
+        prompt = np.ascontiguousarray(prompt, dtype=np.uint32)
+        F.check(F.lib().fsb_lm_session_admit(self._h, int(slot), prompt.ctypes.data, prompt.shape[1], int(max_new_tokens),
+                                             int(fixed_len)))
+
+    def session_run(self, max_frames: int) -> np.ndarray:
+        """up to `max_frames` more frames for every live slot; returns the per-slot "still generating" mask"""
+        act = (C.c_int32 * self.max_batch)()
+        n = C.c_int32()
+        F.check(F.lib().fsb_lm_session_run(self._h, int(max_frames), act, C.byref(n)))
+        return np.array(list(act), dtype=bool)
+
+    def session_collect(self, slot: int, cap: int) -> np.ndarray:
+        Cb = self.cfg["num_codebooks"]
+        out = np.zeros((Cb, cap), np.uint32)
+        n = C.c_size_t()
+        F.check(F.lib().fsb_lm_session_collect(self._h, int(slot), out.ctypes.data, cap, C.byref(n)))
+        return out[:, : n.value].copy()
+
     def set_profile(self, on: bool):
         F.check(F.lib().fsb_lm_set_profile(self._h, int(on)))
 

@@ -192,6 +192,35 @@ int fsb_lm_generate_static_batch(fsb_lm *lm, const uint32_t *const *prompts, con
  * stride `cap`; *out_len = frames written.  Lets a caller (and the parity tests) replay a generation step by step. */
 int fsb_lm_last_frames(fsb_lm *lm, int32_t row, uint32_t *out, size_t cap, size_t *out_len);
 
+/* ---- per-voice conditioning KV ------------------------------------------------------------------
+ * The server keeps the system + voice KV between the chunks of ONE request (`clear_slow_caches_until(n_cond)`,
+ * server/lib/handlers/speech.rs:40) and re-prefills it whenever the voice changes.  A snapshot holds the first
+ * `n_positions` cached positions of a row (every slow block, K and V) on the device and can be restored into any row:
+ * prefill the voice prompt once, snapshot, and start every later utterance of that voice with a restore +
+ * FSB_GEN_KEEP_SLOW_KV generation of the remaining text columns. */
+typedef struct fsb_kv_snapshot fsb_kv_snapshot;
+int fsb_lm_kv_snapshot_save(fsb_lm *lm, int32_t row, size_t n_positions, fsb_kv_snapshot **out);
+int fsb_lm_kv_snapshot_restore(fsb_lm *lm, const fsb_kv_snapshot *snap, int32_t row); /* row's KV length := n_positions */
+int fsb_lm_kv_snapshot_free(fsb_lm *lm, fsb_kv_snapshot *snap);
+
+/* ---- continuous batching ---------------------------------------------------------------------------
+ * The reference serialises whole generations behind one Mutex (server/lib/state.rs:13) and its static batch waits for
+ * the slowest row (static_batch.rs:160-173).  A session turns the `max_batch` rows of the handle into slots: an utterance
+ * is admitted into a free slot between two runs, decodes together with whatever else is in flight, and is collected as
+ * soon as it ends (<|im_end|> / budget) while the other slots keep going.  Row semantics are those of
+ * fsb_lm_generate_blocking with Philox row index == slot.  Needs the wide-batch kernel (bf16 weights, Fish shapes,
+ * max_batch >= 9); returns FSB_ERR_UNSUPPORTED otherwise.
+ *   begin   : sampling parameters + flags (FSB_GEN_FIXED_LEN) of every utterance of the session; all slots free
+ *   admit   : prefill `prompt` into `slot` and emit its first frame (the frame produced from the prompt itself)
+ *   run     : up to `max_frames` more frames for every live slot in ONE launch; active[slot] = 1 while a slot is still
+ *             generating (NULL allowed); *n_active = live slots left
+ *   collect : codes u32 (C, cap) of a finished slot (same filtering as generate_blocking) and frees the slot */
+int fsb_lm_session_begin(fsb_lm *lm, const fsb_sampling_args *sampling, uint32_t flags);
+int fsb_lm_session_admit(fsb_lm *lm, int32_t slot, const uint32_t *prompt, int32_t prompt_len, size_t max_new_tokens,
+                         int32_t fixed_len);
+int fsb_lm_session_run(fsb_lm *lm, int32_t max_frames, int32_t *active, int32_t *n_active);
+int fsb_lm_session_collect(fsb_lm *lm, int32_t slot, uint32_t *out_codes, size_t cap, size_t *out_len);
+
 int fsb_lm_get_stats(fsb_lm *lm, fsb_lm_stats *out);
 /* Profiling switch (the reference's only instrumentation is Instant + println!, single_batch.rs:233-303).
  * on != 0: generate calls run the frame loop eagerly and bracket every launch of the dominant

@@ -572,3 +572,88 @@ def test_generate_blocking_with_hidden(models):
         ora.clear_slow_layer_caches()
         assert hid.shape == (len(exp), 1, cfg["dim"])
         np.testing.assert_allclose(hid[:, 0], np.concatenate(exp, 0), atol=ATOL, rtol=0)
+
+
+def test_kv_snapshot_restores_the_voice_prefix(tiny_lm):
+    """the conditioning (system + voice) KV is prefilled once, snapshotted on the device and restored into
+    another row before an utterance; generation of the remaining columns on top of it (FSB_GEN_KEEP_SLOW_KV, the server's
+    `clear_slow_caches_until` flow, speech.rs:40) must equal the oracle's generation from the full prompt."""
+    cfg, tok, w = tiny_lm
+    gpu = DualARTransformer(w, cfg, tok, max_batch=3, max_seq_len=256)
+    ora = oracle_model(cfg, tok, w)
+    n_cond = 48
+    full = synth.make_prompt(cfg, tok, n_cond + 11, seed=808)
+    gpu.forward_generate(full[None, :, :n_cond], 0, want_logits=False)  # prefill of the conditioning on row 0
+    assert gpu.curr_kv_size() == n_cond
+    snap = gpu.kv_snapshot_save(0, n_cond)
+    gpu.clear_slow_layer_caches()
+    # (another voice / utterance trashes row 0 in between)
+    generate_blocking(gpu, synth.make_prompt(cfg, tok, 70, seed=1), 400, SamplingArgs(temp=0.0), fixed_len=3)
+    gpu.kv_snapshot_restore(snap, 0)
+    assert gpu.curr_kv_size() == n_cond
+    sa, so = SamplingArgs(0.7, 0.8, 256, 1.4, seed=4), osamp.SamplingArgs(0.7, 0.8, 256, 1.4, seed=4)
+    got = generate_blocking(gpu, full[:, n_cond:], 400, sa, fixed_len=9, keep_slow_kv=True)
+    assert gpu.curr_kv_size() == n_cond + 11 + 8
+    ora.clear_slow_layer_caches()
+    with torch.no_grad():
+        exp = ogen.generate_blocking(ora, t64(full), 400, so, fixed_len=9)
+    np.testing.assert_array_equal(got.astype(np.int64), exp.numpy())
+    gpu.kv_snapshot_free(snap)
+    gpu.close()
+
+
+@pytest.mark.parametrize("fixed", [True, False])
+def test_continuous_batching_session(fixed):
+    """13 utterances through 9 slots.  A slot is refilled as soon as its utterance ends while the other
+    slots keep decoding (the reference's static batch waits for the slowest row, static_batch.rs:160-173; its server
+    serialises whole generations, state.rs:13).  Every utterance is checked decision by decision against the oracle
+    (teacher-forced replay, Philox row == slot) and must have the length the bs=1 rules give it."""
+    nslots, nutt = 9, 13
+    cfg, tok, w, gpu, ora = wide_models(nslots, max_seq_len=160)
+    rng = np.random.default_rng(5)
+    prompts = [synth.make_prompt(cfg, tok, int(rng.integers(14, 60)), seed=4000 + i) for i in range(nutt)]
+    lens = [int(rng.integers(3, 19)) for _ in range(nutt)]  # fixed: exact frame counts; else: max_new_tokens budgets
+    sa, so = SamplingArgs(0.7, 0.8, 256, 1.4, seed=21), osamp.SamplingArgs(0.7, 0.8, 256, 1.4, seed=21)
+    gpu.session_begin(sa, fixed_len=fixed)
+    slot_utt = {}
+    results, frames_of, slot_of = {}, {}, {}
+    nxt = 0
+
+    def admit(slot):
+        nonlocal nxt
+        i = nxt
+        nxt += 1
+        P = prompts[i].shape[1]
+        gpu.session_admit(slot, prompts[i], 400 if fixed else P + lens[i] - 2, fixed_len=lens[i] if fixed else 0)
+        slot_utt[slot] = i
+        slot_of[i] = slot
+
+    for s in range(nslots):
+        admit(s)
+    launches = 0
+    while slot_utt:
+        act = gpu.session_run(4)
+        launches += 1
+        assert launches < 40
+        for s in list(slot_utt):
+            if not act[s]:
+                i = slot_utt.pop(s)
+                frames_of[i] = gpu.last_frames(s)
+                results[i] = gpu.session_collect(s, 64)
+                if nxt < nutt:
+                    admit(s)
+    assert sorted(results) == list(range(nutt))
+    tot = dict(decisions=0, exact=0, near_tie=0, violation=0)
+    for i in range(nutt):
+        fr = frames_of[i]
+        np.testing.assert_array_equal(results[i], fr[1:, [f for f in range(fr.shape[1]) if f == 0 or fr[0, f] != tok["im_end_id"]]])
+        if fixed:
+            assert fr.shape[1] == lens[i]
+        else:
+            assert fr.shape[1] == lens[i] or fr[0, -1] == tok["im_end_id"]  # Q3 budget or an earlier <|im_end|>
+        r = ogen.replay_frames(ora, t64(prompts[i]), fr, so, row=slot_of[i], fixed_len=lens[i] if fixed else None)
+        assert r["violation"] == 0, (i, r["events"][:4])
+        for k in tot:
+            tot[k] += r[k]
+    assert tot["exact"] >= 0.98 * tot["decisions"], tot
+    gpu.close()
