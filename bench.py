@@ -314,15 +314,20 @@ def run_ours(a):
         wl.step()
     sampler = ClockSampler(local)
     barrier()
-    if rank == 0:
-        sampler.start()
+    sampler.start()
     acc = time_workload(wl, a.steps, 0, barrier)
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop()
+    if world > 1:
+        # per-rank breakdown on stderr (the JSON line on stdout stays rank 0's alone)
+        print("[bench rank %d/%d] ms/step: prefill %.1f decode %.1f vocoder %.1f device %.1f wall %.1f | sm %s MHz (max %s) %s" % (
+            rank, world, acc["pre"] / a.steps, acc["dec"] / a.steps, acc["voc"] / a.steps, acc["dev"] / a.steps,
+            acc["wall_ms"] / a.steps, clocks["sm_mhz"], clocks["sm_max_mhz"], ",".join(clocks["reasons"])),
+            file=sys.stderr, flush=True)
     wb = lm.stats()["weight_bytes_per_frame"]
     dom_ms, dom_n, dom_bytes = acc["dom_ms"], acc["dom_n"], acc["dom_bytes"]
     if dom_n > 0:
         kname = ("megab_decode_kernel (wide-batch persistent frame loop: TMA weight ring -> tcgen05.mma with the batch rows as "
-                 "the N dimension, split-K fixups, GQA attention, per-row samplers" if wl.B > 8 else
+                 "the N dimension and three bf16 terms stacked along N, fused FFN + deterministic reduce, GQA attention, per-row samplers" if wl.B > 8 else
                  "mega1_decode_kernel (single-row persistent frame loop: TMA weight ring + register-resident activations; GEMV "
                  "phases + GQA attention + samplers" if wl.B == 1 else
                  "mega_decode_kernel (persistent frame loop: weight-streaming GEMV phases + GQA attention + samplers")
