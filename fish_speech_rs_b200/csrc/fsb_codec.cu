@@ -8,6 +8,7 @@
 #include <tuple>
 
 #include "fsb_codec_kernels.cuh"
+#include "fsb_tc_conv.cuh"
 #include "fsb_tc_gemm.cuh"
 
 namespace fsb {
@@ -18,6 +19,7 @@ struct ConvW {
     int Cin = 0, Cout = 0, K = 0;
     float *wt_tiled = nullptr;  // ResBlock convs: [C / BM][C / 16][16][K][BM] (one contiguous block per TMA bulk copy)
     int tile_bm = 0;
+    TcConvW tc;  // ResBlock convs with 64 / 128 / 256 channels: fp16 hi + lo weight image for tcconv_kernel
 };
 
 struct ConvNeXtW {
@@ -61,8 +63,10 @@ struct fsb_codec {
     int max_frames = 0;
     uint32_t *d_codes = nullptr;
     int *d_err = nullptr;
-    float *buf[6] = {};  // activation buffers of 32768 * max_frames floats (4 raw + 2 pre-activated copies for the TMA convs)
+    float *buf[7] = {};  // activation buffers of 32768 * max_frames floats (+ slack for the image padding rows): 4 raw + 2
+                         // pre-activated copies for the TMA convs + the chunked residual stream of the tcgen05 convs
     bool res_tma = false;  // ResBlock convs run on resconv_tma_kernel
+    bool res_tc = false;   // ... and those with >= 64 channels on tcconv_kernel (tcgen05)
     std::map<std::tuple<const void *, int, int, int>, TcMap> xmaps;  // (buffer, C, L, span) -> tensor map
     float *cn_h = nullptr, *cn_g = nullptr;
     long long *d_idx = nullptr;
@@ -156,6 +160,10 @@ static int load_conv(fsb_codec *c, const fsb_tensor *w, size_t n, const std::str
                 out->tile_bm = std::min(64, Cout);
                 relayout_res_tiled<<<256, 256, 0, c->stream>>>((const float *)raw.ptr, tl, Cin, K, out->tile_bm);
                 out->wt_tiled = tl;
+            }
+            if (st == FSB_OK && c->res_tc && tcv_supported(Cin)) {
+                st = tcv_prepare_weights((const float *)raw.ptr, Cin, K, &out->tc, c->stream);
+                if (st == FSB_OK) c->owned.push_back(out->tc.img);
             }
         }
         cudaError_t e = cudaGetLastError();
@@ -412,6 +420,34 @@ static int decode_device(fsb_codec *c, int T, float *pcm_dev_out /* device (2048
     const float third = (float)(1.0 / 3.0);
     for (int i = 0; i < 5; ++i) {
         float *M = cur, *U = nxt;
+        if (c->res_tc && c->res_c1[i][0][0].tc.img) {
+            // tcgen05 ResBlocks: activations as fp16 hi + lo images (time-major rows of 8 channels), residual stream chunked
+            float *Uc = c->buf[6], *Rc = c->buf[2];
+            __half *SUi = reinterpret_cast<__half *>(c->buf[4]), *SRi = reinterpret_cast<__half *>(c->buf[5]);
+            __half *X1i = reinterpret_cast<__half *>(c->buf[3]);
+            FSB_TRY(convT_fwd(c, c->ups[i], M, L, U, kUpRates[i], true));
+            L *= kUpRates[i];
+            FSB_TRY(tcv_chunk(U, c->ups[i].Cout, L, Uc, SUi, st));
+            c->launches++;
+            for (int j = 0; j < 3; ++j) {
+                const float *xin = Uc;
+                const __half *xin_img = SUi;
+                for (int m = 0; m < 3; ++m) {
+                    const int d = kResDilations[m];
+                    const ConvW &w1 = c->res_c1[i][j][m], &w2 = c->res_c2[i][j][m];
+                    FSB_TRY(tcv_conv(w1.tc, w1.bias, xin_img, L, d, nullptr, nullptr, X1i, nullptr, 0, 0.f, st));
+                    if (m < 2) {
+                        FSB_TRY(tcv_conv(w2.tc, w2.bias, X1i, L, d, xin, Rc, SRi, nullptr, 0, 0.f, st));
+                        xin = Rc;
+                        xin_img = SRi;
+                    } else {
+                        FSB_TRY(tcv_conv(w2.tc, w2.bias, X1i, L, d, xin, nullptr, nullptr, M, j == 0 ? 0 : (j == 1 ? 1 : 2), third, st));
+                    }
+                    c->launches += 2;
+                }
+            }
+            continue;
+        }
         if (c->res_tma) {
             // TMA-staged ResBlock convs read pre-activated inputs: every producer also writes silu(result) where its
             // consumer applies silu (hifi_gan.rs:76-79): SU = silu(U), SR = silu(R), X1 holds silu(conv1 output) only
@@ -468,6 +504,9 @@ static int codec_create_impl(fsb_codec *c, const fsb_tensor *w, size_t n) {
     FSB_CUDA_OK(cudaEventCreate(&c->ev1));
     FSB_CUDA_OK(cudaEventCreate(&c->evd0));
     FSB_CUDA_OK(cudaEventCreate(&c->evd1));
+    c->res_tma = getenv("FSB_CODEC_NO_TMA") == nullptr;
+    c->res_tc = c->res_tma && getenv("FSB_CODEC_NO_TC") == nullptr;
+    if (c->res_tc) FSB_TRY(tcv_init());
     // FSQ projections, gathered per group into one array each
     FSB_TRY(calloc_dev(c, &c->proj_out_w, (size_t)kGroups * 64 * 4));
     FSB_TRY(calloc_dev(c, &c->proj_out_b, (size_t)kGroups * 64));
@@ -546,8 +585,7 @@ static int codec_create_impl(fsb_codec *c, const fsb_tensor *w, size_t n) {
     const size_t T = (size_t)c->max_frames;
     FSB_TRY(calloc_dev(c, &c->d_codes, (size_t)kGroups * T));
     FSB_TRY(calloc_dev(c, &c->d_err, 1));
-    c->res_tma = getenv("FSB_CODEC_NO_TMA") == nullptr;
-    for (int i = 0; i < (c->res_tma ? 6 : 4); ++i) FSB_TRY(calloc_dev(c, &c->buf[i], 32768 * T));
+    for (int i = 0; i < (c->res_tc ? 7 : (c->res_tma ? 6 : 4)); ++i) FSB_TRY(calloc_dev(c, &c->buf[i], 32768 * T + 256 * 1024));
     FSB_TRY(calloc_dev(c, &c->cn_h, 4 * T * kDim));
     FSB_TRY(calloc_dev(c, &c->cn_g, 4 * T * kDim * 4));
     FSB_TRY(calloc_dev(c, &c->d_idx, (size_t)kGroups * T));
