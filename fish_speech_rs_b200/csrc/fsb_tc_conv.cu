@@ -87,6 +87,31 @@ __device__ __forceinline__ void tv_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         : "r"(taddr));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tv_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+template <int CB>
+__device__ __forceinline__ void tv_ld(uint32_t taddr, uint32_t (&r)[CB]) {
+    if constexpr (CB == 32) tv_ld32(taddr, r);
+    else tv_ld16(taddr, r);
+}
+// silu for the epilogue: x * 1 / (1 + 2^(-x log2 e)) on ex2.approx / rcp.approx (2^-22 relative, the precision of the image)
+__device__ __forceinline__ float tv_silu_fast(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+// two scaled values -> packed fp16 hi pair and lo pair
+__device__ __forceinline__ void tv_split2(float v0, float v1, uint32_t &hi, uint32_t &lo) {
+    v0 = fminf(fmaxf(v0, -60000.f), 60000.f);
+    v1 = fminf(fmaxf(v1, -60000.f), 60000.f);
+    const __half2 h = __floats2half2_rn(v0, v1);
+    const float2 f = __half22float2(h);
+    const __half2 l = __floats2half2_rn(v0 - f.x, v1 - f.y);
+    hi = *reinterpret_cast<const uint32_t *>(&h);
+    lo = *reinterpret_cast<const uint32_t *>(&l);
+}
 __device__ __forceinline__ bool tv_elect() {
     uint32_t pred;
     asm volatile(
@@ -119,7 +144,9 @@ __global__ void __launch_bounds__(kTcvThreads, 2) tcconv_kernel(const TcConvArgs
     const int rows_ld = 128 * MT + halo;                  // staged rows per (term, chunk)
     const uint32_t x_plane = (uint32_t)rows_ld * 16u;     // bytes of one (term, chunk) plane
     const uint32_t x_stage = 4u * x_plane;
-    constexpr uint32_t w_plane = (uint32_t)N * 16u, w_stage = 4u * w_plane;
+    constexpr uint32_t w_plane = (uint32_t)N * 16u, w_tap = 4u * w_plane;   // one (kb, tap): [2 terms][2 chunks][N][16 B]
+    const int tps = a.tps;                                                   // taps per weight stage (1, or K for small N)
+    const uint32_t w_stage = (uint32_t)tps * w_tap;
     const int NCH = a.C / 8, NKB = a.C / 16, co0 = blockIdx.y * N;
     uint64_t *xfull = reinterpret_cast<uint64_t *>(smem);  // [2]
     uint64_t *xempty = xfull + 2;                          // [2]
@@ -165,6 +192,7 @@ __global__ void __launch_bounds__(kTcvThreads, 2) tcconv_kernel(const TcConvArgs
             int wi = 0;
             uint32_t wph = 0;
             const __half *xbase = a.ximg + ((size_t)kTcvPadL + t0 - halo) * 8;
+            const __half *wsrc = a.wimg + (size_t)blockIdx.y * NKB * K * (w_tap / 2);
             for (int kb = 0; kb < NKB; ++kb) {
                 const int xsl = kb & 1;
                 tv_wait(xempty + xsl, ((kb >> 1) & 1) ^ 1);
@@ -176,11 +204,10 @@ __global__ void __launch_bounds__(kTcvThreads, 2) tcconv_kernel(const TcConvArgs
                     for (int ch = 0; ch < 2; ++ch)
                         tv_bulk(xd + (term * 2 + ch) * x_plane, xbase + ((size_t)(term * NCH + 2 * kb + ch) * Lp) * 8, x_plane,
                                 xfull + xsl);
-                for (int tap = 0; tap < K; ++tap) {
+                for (int tap = 0; tap < K; tap += tps) {
                     tv_wait(wempty + wi, wph ^ 1);
                     tv_expect_tx(wfull + wi, w_stage);
-                    tv_bulk(ws + (size_t)wi * w_stage, a.wimg + ((size_t)(blockIdx.y * NKB + kb) * K + tap) * (w_stage / 2), w_stage,
-                            wfull + wi);
+                    tv_bulk(ws + (size_t)wi * w_stage, wsrc + (size_t)(kb * K + tap) * (w_tap / 2), w_stage, wfull + wi);
                     if (++wi == S) {
                         wi = 0;
                         wph ^= 1;
@@ -199,26 +226,29 @@ __global__ void __launch_bounds__(kTcvThreads, 2) tcconv_kernel(const TcConvArgs
             const int xsl = kb & 1;
             tv_wait(xfull + xsl, (kb >> 1) & 1);
             const uint32_t xaddr = tv_smem_u32(xs + (size_t)xsl * x_stage_al);
-            for (int tap = 0; tap < K; ++tap) {
+            for (int tap0 = 0; tap0 < K; tap0 += tps) {
                 tv_wait(wfull + wi, wph);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (tv_elect()) {
-                    const uint32_t waddr = tv_smem_u32(ws + (size_t)wi * w_stage);
-                    const uint64_t b0 = b_hi | (uint64_t)((waddr >> 4) & 0x3FFF);
-                    const uint64_t b1 = b_hi | (uint64_t)(((waddr + 2 * w_plane) >> 4) & 0x3FFF);
-                    const uint32_t xrow = xaddr + (uint32_t)(tap * dil) * 16u;
-                    for (int mt = 0; mt < MT; ++mt) {
-                        const uint32_t xa = xrow + (uint32_t)mt * 2048u;
-                        const uint64_t a0 = a_hi | (uint64_t)((xa >> 4) & 0x3FFF);
-                        const uint64_t a1 = a_hi | (uint64_t)(((xa + 2 * x_plane) >> 4) & 0x3FFF);
-                        const uint32_t d = tmem_base + (uint32_t)(mt * N);
-                        tv_mma(d, a0, b0, idesc, (kb | tap) != 0 ? 1u : 0u);
-                        tv_mma(d, a0, b1, idesc, 1u);
-                        tv_mma(d, a1, b0, idesc, 1u);
+                    uint32_t waddr = tv_smem_u32(ws + (size_t)wi * w_stage);
+                    uint32_t xrow = xaddr + (uint32_t)(tap0 * dil) * 16u;
+                    for (int tp = 0; tp < tps; ++tp, waddr += w_tap, xrow += (uint32_t)dil * 16u) {
+                        const uint64_t b0 = b_hi | (uint64_t)((waddr >> 4) & 0x3FFF);
+                        const uint64_t b1 = b_hi | (uint64_t)(((waddr + 2 * w_plane) >> 4) & 0x3FFF);
+                        const uint32_t first = (kb | tap0 | tp) != 0 ? 1u : 0u;
+                        for (int mt = 0; mt < MT; ++mt) {
+                            const uint32_t xa = xrow + (uint32_t)mt * 2048u;
+                            const uint64_t a0 = a_hi | (uint64_t)((xa >> 4) & 0x3FFF);
+                            const uint64_t a1 = a_hi | (uint64_t)(((xa + 2 * x_plane) >> 4) & 0x3FFF);
+                            const uint32_t d = tmem_base + (uint32_t)(mt * N);
+                            tv_mma(d, a0, b0, idesc, first);
+                            tv_mma(d, a0, b1, idesc, 1u);
+                            tv_mma(d, a1, b0, idesc, 1u);
+                        }
                     }
                     tv_commit(wempty + wi);
-                    if (tap == K - 1) tv_commit(xempty + xsl);
-                    if (tap == K - 1 && kb == NKB - 1) tv_commit(accfull);
+                    if (tap0 + tps >= K) tv_commit(xempty + xsl);
+                    if (tap0 + tps >= K && kb == NKB - 1) tv_commit(accfull);
                 }
                 __syncwarp();
                 if (++wi == S) {
@@ -228,43 +258,44 @@ __global__ void __launch_bounds__(kTcvThreads, 2) tcconv_kernel(const TcConvArgs
             }
         }
     } else {
-        // ---- epilogue: warp w reads TMEM lanes [32 (w & 3), +32) (= time rows) and the column half (w >> 2) of every tile
-        const int q = warp & 3, half = warp >> 2;
+        // ---- epilogue: warp w reads TMEM lanes [32 (w & 3), +32) (= time rows); the (tile, column block) pairs are dealt
+        // alternately to the warp groups 0..3 and 4..7
+        const int q = warp & 3, grp = warp >> 2;
         const int row = q * 32 + lane;
-        constexpr int NH = N / 2;
-        if (a.yimg && t0 == 0 && row < kTcvPadL) {
+        constexpr int CB = N < 32 ? N : 32, NB = N / CB;  // column block
+        if (a.yimg && t0 == 0 && row < kTcvPadL && grp == 0) {
             // the consumer's causal left padding
             const uint4 z = make_uint4(0, 0, 0, 0);
-            for (int c = (co0 + half * NH) / 8; c < (co0 + (half + 1) * NH) / 8; ++c)
+            for (int c = co0 / 8; c < (co0 + N) / 8; ++c)
 #pragma unroll
                 for (int term = 0; term < 2; ++term)
                     *reinterpret_cast<uint4 *>(a.yimg + ((size_t)(term * NCH + c) * Lp + row) * 8) = z;
         }
         tv_wait(accfull, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        for (int mt = 0; mt < MT; ++mt) {
-            const int t = t0 + mt * 128 + row;
-            const bool ok = t < a.L;
+        const float inv_scale = a.inv_scale;
 #pragma unroll 1
-            for (int cb = 0; cb < NH; cb += 32) {
-                uint32_t v[32];
-                __syncwarp();
-                tv_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * N + half * NH + cb), v);
-                if (ok) {
+        for (int blk = grp; blk < MT * NB; blk += 2) {
+            const int mt = blk / NB, cb = (blk % NB) * CB;
+            const int t = t0 + mt * 128 + row;
+            uint32_t v[CB];
+            __syncwarp();
+            tv_ld<CB>(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * N + cb), v);
+            if (t < a.L) {
 #pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    const int co = co0 + half * NH + cb + g * 8, c = co >> 3;
+                for (int g = 0; g < CB / 8; ++g) {
+                    const int co = co0 + cb + g * 8, c = co >> 3;
                     const float4 b0 = __ldg(reinterpret_cast<const float4 *>(a.bias + co));
                     const float4 b1 = __ldg(reinterpret_cast<const float4 *>(a.bias + co + 4));
                     float o[8];
-                    o[0] = fmaf(__uint_as_float(v[g * 8 + 0]), a.inv_scale, b0.x);
-                    o[1] = fmaf(__uint_as_float(v[g * 8 + 1]), a.inv_scale, b0.y);
-                    o[2] = fmaf(__uint_as_float(v[g * 8 + 2]), a.inv_scale, b0.z);
-                    o[3] = fmaf(__uint_as_float(v[g * 8 + 3]), a.inv_scale, b0.w);
-                    o[4] = fmaf(__uint_as_float(v[g * 8 + 4]), a.inv_scale, b1.x);
-                    o[5] = fmaf(__uint_as_float(v[g * 8 + 5]), a.inv_scale, b1.y);
-                    o[6] = fmaf(__uint_as_float(v[g * 8 + 6]), a.inv_scale, b1.z);
-                    o[7] = fmaf(__uint_as_float(v[g * 8 + 7]), a.inv_scale, b1.w);
+                    o[0] = fmaf(__uint_as_float(v[g * 8 + 0]), inv_scale, b0.x);
+                    o[1] = fmaf(__uint_as_float(v[g * 8 + 1]), inv_scale, b0.y);
+                    o[2] = fmaf(__uint_as_float(v[g * 8 + 2]), inv_scale, b0.z);
+                    o[3] = fmaf(__uint_as_float(v[g * 8 + 3]), inv_scale, b0.w);
+                    o[4] = fmaf(__uint_as_float(v[g * 8 + 4]), inv_scale, b1.x);
+                    o[5] = fmaf(__uint_as_float(v[g * 8 + 5]), inv_scale, b1.y);
+                    o[6] = fmaf(__uint_as_float(v[g * 8 + 6]), inv_scale, b1.z);
+                    o[7] = fmaf(__uint_as_float(v[g * 8 + 7]), inv_scale, b1.w);
                     const size_t ro = ((size_t)c * a.L + t) * 8;
                     if (a.res) {
                         const float4 r0 = *reinterpret_cast<const float4 *>(a.res + ro);
@@ -277,14 +308,13 @@ __global__ void __launch_bounds__(kTcvThreads, 2) tcconv_kernel(const TcConvArgs
                         *reinterpret_cast<float4 *>(a.y + ro + 4) = make_float4(o[4], o[5], o[6], o[7]);
                     }
                     if (a.yimg) {
-                        __half hi[8], lo[8];
+                        uint32_t hi[4], lo[4];
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) tv_split(silu_f(o[j]) * kTcvXScale, hi[j], lo[j]);
+                        for (int j = 0; j < 4; ++j)
+                            tv_split2(tv_silu_fast(o[2 * j]) * kTcvXScale, tv_silu_fast(o[2 * j + 1]) * kTcvXScale, hi[j], lo[j]);
                         const size_t io = ((size_t)c * Lp + kTcvPadL + t) * 8;
-                        *reinterpret_cast<uint4 *>(a.yimg + io) =
-                            make_uint4(tv_pack(hi[0], hi[1]), tv_pack(hi[2], hi[3]), tv_pack(hi[4], hi[5]), tv_pack(hi[6], hi[7]));
-                        *reinterpret_cast<uint4 *>(a.yimg + (size_t)NCH * Lp * 8 + io) =
-                            make_uint4(tv_pack(lo[0], lo[1]), tv_pack(lo[2], lo[3]), tv_pack(lo[4], lo[5]), tv_pack(lo[6], lo[7]));
+                        *reinterpret_cast<uint4 *>(a.yimg + io) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                        *reinterpret_cast<uint4 *>(a.yimg + (size_t)NCH * Lp * 8 + io) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
                     }
                     if (a.m) {
 #pragma unroll
@@ -296,7 +326,6 @@ __global__ void __launch_bounds__(kTcvThreads, 2) tcconv_kernel(const TcConvArgs
                             a.m[mo] = r;
                         }
                     }
-                }
                 }
             }
         }
@@ -360,10 +389,10 @@ __global__ void tcv_chunk_kernel(const float *__restrict__ u, int C, int L, floa
 
 constexpr size_t kTcvSmemMax = 200 * 1024;
 
-size_t tcv_smem_bytes(int N, int MT, int K, int dil, int S) {
+size_t tcv_smem_bytes(int N, int MT, int K, int dil, int S, int tps) {
     const size_t rows_ld = 128 * (size_t)MT + (size_t)(K - 1) * dil;
     const size_t x_stage = (4 * rows_ld * 16 + 127) & ~(size_t)127;
-    return 128 + kTcvBarBytes + 2 * x_stage + (size_t)S * 64 * N;
+    return 128 + kTcvBarBytes + 2 * x_stage + (size_t)S * tps * 64 * N;
 }
 
 int g_tcv_sms = 0;
@@ -375,6 +404,8 @@ int tcv_init() {
     if (done) return FSB_OK;
     FSB_CUDA_OK(cudaFuncSetAttribute(tcconv_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcvSmemMax));
     FSB_CUDA_OK(cudaFuncSetAttribute(tcconv_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcvSmemMax));
+    FSB_CUDA_OK(cudaFuncSetAttribute(tcconv_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcvSmemMax));
+    FSB_CUDA_OK(cudaFuncSetAttribute(tcconv_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcvSmemMax));
     int dev = 0;
     FSB_CUDA_OK(cudaGetDevice(&dev));
     FSB_CUDA_OK(cudaDeviceGetAttribute(&g_tcv_sms, cudaDevAttrMultiProcessorCount, dev));
@@ -436,24 +467,28 @@ int tcv_conv(const TcConvW &w, const float *bias, const __half *ximg, int L, int
     TcConvArgs a;
     a.ximg = ximg; a.wimg = w.img; a.bias = bias; a.res = res; a.y = y; a.yimg = yimg; a.m = m;
     a.C = w.C; a.L = L; a.K = K; a.dil = dil; a.acc_mode = acc_mode; a.scale = scale; a.inv_scale = w.inv_scale;
-    // MT tiles of 128 time steps per CTA: MT * N <= 512 TMEM columns.  Weight traffic per MMA cycle falls as 1 / MT, so take
-    // the largest MT that still fills the GPU; MT * N <= 256 lets two CTAs share an SM (one drains while the other issues)
+    // MT tiles of 128 time steps per CTA (MT * N TMEM columns).  Weight traffic per MMA cycle falls as 1 / MT; MT * N <= 256
+    // and <= 110 KB of smem let two CTAs share an SM (one drains its accumulators while the other issues MMAs).
+    // Small channel counts keep all taps of a 16-channel block in one weight stage.
     const int n128 = (L + 127) / 128, sms = g_tcv_sms > 0 ? g_tcv_sms : 148;
-    const int mt_max = std::min(4, 512 / N);
-    int MT = std::min(mt_max, 256 / N);
-    while (MT > 1 && ((n128 + MT - 1) / MT) * (w.C / N) < 2 * sms) --MT;
-    if (const char *s = getenv("FSB_TCV_MT")) MT = std::max(1, std::min(mt_max, atoi(s)));
+    const int tps = N <= 32 ? K : 1;
+    const int nkb = w.C / 16;
+    const size_t budget = 110 * 1024;
+    int MT = std::min(4, 256 / N);
+    while (MT > 1 && (((n128 + MT - 1) / MT) * (w.C / N) < 2 * sms || tcv_smem_bytes(N, MT, K, dil, 2, tps) > budget)) --MT;
+    if (const char *s = getenv("FSB_TCV_MT")) MT = std::max(1, std::min(std::min(4, 512 / N), atoi(s)));
     a.MT = MT;
-    const bool two = MT * N <= 256;
-    const size_t budget = two ? 110 * 1024 : kTcvSmemMax;
-    int S = 16;
-    while (S > 2 && tcv_smem_bytes(N, MT, K, dil, S) > budget) --S;
+    a.tps = tps;
+    int S = tps == 1 ? 16 : std::min(4, nkb);
+    while (S > 2 && tcv_smem_bytes(N, MT, K, dil, S, tps) > budget) --S;
     a.wstages = S;
-    const size_t smem = tcv_smem_bytes(N, MT, K, dil, S);
+    const size_t smem = tcv_smem_bytes(N, MT, K, dil, S, tps);
     FSB_REQUIRE(smem <= kTcvSmemMax, FSB_ERR_UNSUPPORTED, "tcconv tile needs %zu B of smem", smem);
     const dim3 grid((n128 + MT - 1) / MT, w.C / N);
     if (N == 128) tcconv_kernel<128><<<grid, kTcvThreads, smem, st>>>(a);
-    else tcconv_kernel<64><<<grid, kTcvThreads, smem, st>>>(a);
+    else if (N == 64) tcconv_kernel<64><<<grid, kTcvThreads, smem, st>>>(a);
+    else if (N == 32) tcconv_kernel<32><<<grid, kTcvThreads, smem, st>>>(a);
+    else tcconv_kernel<16><<<grid, kTcvThreads, smem, st>>>(a);
     FSB_CUDA_OK(cudaGetLastError());
     return FSB_OK;
 }

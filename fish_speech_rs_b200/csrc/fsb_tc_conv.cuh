@@ -30,13 +30,13 @@ struct TcConvArgs {
     float *y;             // chunked f32 raw result, or null (may alias res)
     __half *yimg;         // image of silu(result) for the next conv, or null
     float *m;             // (C, L) channel-major mean accumulator, or null
-    int C, L, K, dil, MT, wstages;
+    int C, L, K, dil, MT, wstages, tps;
     int acc_mode;         // for m: 0: m = v;  1: m = m + v;  2: m = (m + v) * scale   (hifi_gan.rs:113-118)
     float scale, inv_scale;
 };
 
 // true when the ResBlock convs of a stage with C channels can run on tcconv_kernel
-inline bool tcv_supported(int C) { return C == 256 || C == 128 || C == 64; }
+inline bool tcv_supported(int C) { return C == 256 || C == 128 || C == 64 || C == 32 || C == 16; }
 
 // (Cout, Cin, K) f32 weights -> TcConvW (allocates the image; the caller owns it)
 int tcv_prepare_weights(const float *raw_dev, int C, int K, TcConvW *out, cudaStream_t st);
