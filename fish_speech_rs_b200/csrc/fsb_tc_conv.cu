@@ -317,14 +317,17 @@ __global__ void __launch_bounds__(kTcvThreads, 2) tcconv_kernel(const TcConvArgs
                         *reinterpret_cast<uint4 *>(a.yimg + (size_t)NCH * Lp * 8 + io) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
                     }
                     if (a.m) {
+                        // all loads first: the stores below may alias them as far as the compiler knows
+                        float *mp = a.m + (size_t)co * a.L + t;
+                        float pm[8];
+                        if (a.acc_mode != 0) {
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const size_t mo = (size_t)(co + j) * a.L + t;
-                            float r = o[j];
-                            if (a.acc_mode == 1) r = a.m[mo] + r;
-                            else if (a.acc_mode == 2) r = (a.m[mo] + r) * a.scale;
-                            a.m[mo] = r;
+                            for (int j = 0; j < 8; ++j) pm[j] = mp[(size_t)j * a.L];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) o[j] = a.acc_mode == 2 ? (pm[j] + o[j]) * a.scale : pm[j] + o[j];
                         }
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) mp[(size_t)j * a.L] = o[j];
                     }
                 }
             }
