@@ -141,7 +141,7 @@ static int load_vec(fsb_codec *c, const fsb_tensor *w, size_t n, const std::stri
 
 // Conv1d weight (Cout, Cin, K) / ConvTranspose1d weight (Cin, Cout, K) -> ConvW
 static int load_conv(fsb_codec *c, const fsb_tensor *w, size_t n, const std::string &prefix, int Cin, int Cout, int K,
-                     bool transposed, ConvW *out, bool res_tiled = false) {
+                     bool transposed, ConvW *out, bool res_tiled = false, bool tc_only = false) {
     DevTensor raw;
     std::vector<void *> tmp_owned;
     std::vector<int64_t> shape = transposed ? std::vector<int64_t>{Cin, Cout, K} : std::vector<int64_t>{Cout, Cin, K};
@@ -165,6 +165,15 @@ static int load_conv(fsb_codec *c, const fsb_tensor *w, size_t n, const std::str
                 st = tcv_prepare_weights((const float *)raw.ptr, Cin, K, &out->tc, c->stream);
                 if (st == FSB_OK) c->owned.push_back(out->tc.img);
             }
+        }
+        if (st == FSB_OK && tc_only && !transposed && Cin == Cout && c->res_tc && tcv_supported(Cin)) {
+            st = tcv_prepare_weights((const float *)raw.ptr, Cin, K, &out->tc, c->stream);
+            if (st == FSB_OK) c->owned.push_back(out->tc.img);
+        }
+        if (st == FSB_OK && tc_only && transposed && c->res_tc && K % 2 == 0 && Cin % 16 == 0) {
+            // HiFi-GAN upsampling: ConvTranspose1d with kernel 2 * stride as a 2-tap conv over stride * Cout columns
+            st = tcv_prepare_weights_t((const float *)raw.ptr, Cin, Cout, K / 2, &out->tc, c->stream);
+            if (st == FSB_OK) c->owned.push_back(out->tc.img);
         }
         cudaError_t e = cudaGetLastError();
         if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
@@ -415,7 +424,15 @@ static int decode_device(fsb_codec *c, int T, float *pcm_dev_out /* device (2048
         std::swap(cur, nxt);
     }
     // HiFiGAN::forward (hifi_gan.rs:207-216)
-    FSB_TRY(conv_fwd(c, c->conv_pre, cur, L, nxt, 1, 1, false, nullptr, 0, 0.f, false, nullptr));
+    if (c->res_tc && c->conv_pre.tc.img) {
+        // conv_pre on the tensor cores: image of the raw input (no activation), result straight into the (C, L) buffer
+        __half *img = reinterpret_cast<__half *>(c->buf[4]);
+        FSB_TRY(tcv_chunk(cur, c->conv_pre.Cin, L, nullptr, img, st, false));
+        FSB_TRY(tcv_conv(c->conv_pre.tc, c->conv_pre.bias, img, L, 1, nullptr, nullptr, nullptr, nxt, 0, 0.f, st));
+        c->launches += 2;
+    } else {
+        FSB_TRY(conv_fwd(c, c->conv_pre, cur, L, nxt, 1, 1, false, nullptr, 0, 0.f, false, nullptr));
+    }
     std::swap(cur, nxt);  // cur = M (stage input), nxt = U
     const float third = (float)(1.0 / 3.0);
     for (int i = 0; i < 5; ++i) {
@@ -425,10 +442,19 @@ static int decode_device(fsb_codec *c, int T, float *pcm_dev_out /* device (2048
             float *Uc = c->buf[6], *Rc = c->buf[2];
             __half *SUi = reinterpret_cast<__half *>(c->buf[4]), *SRi = reinterpret_cast<__half *>(c->buf[5]);
             __half *X1i = reinterpret_cast<__half *>(c->buf[3]);
-            FSB_TRY(convT_fwd(c, c->ups[i], M, L, U, kUpRates[i], true));
-            L *= kUpRates[i];
-            FSB_TRY(tcv_chunk(U, c->ups[i].Cout, L, Uc, SUi, st));
-            c->launches++;
+            if (c->ups[i].tc.img) {
+                // upsampling on the tensor cores too: image of silu(M), then the phases of the transposed conv as GEMM
+                // columns; the epilogue writes the chunked residual stream and the image of silu(U) directly
+                FSB_TRY(tcv_chunk(M, c->ups[i].Cin, L, nullptr, SRi, st, true));
+                FSB_TRY(tcv_conv(c->ups[i].tc, c->ups[i].bias, SRi, L, 1, nullptr, Uc, SUi, nullptr, 0, 0.f, st));
+                L *= kUpRates[i];
+                c->launches += 2;
+            } else {
+                FSB_TRY(convT_fwd(c, c->ups[i], M, L, U, kUpRates[i], true));
+                L *= kUpRates[i];
+                FSB_TRY(tcv_chunk(U, c->ups[i].Cout, L, Uc, SUi, st));
+                c->launches++;
+            }
             for (int j = 0; j < 3; ++j) {
                 const float *xin = Uc;
                 const __half *xin_img = SUi;
@@ -489,6 +515,14 @@ static int decode_device(fsb_codec *c, int T, float *pcm_dev_out /* device (2048
         }
         // M holds the stage output; U is free
     }
+    if (c->conv_post.Cout == 1 && c->conv_post.Cin * c->conv_post.K <= kPostMaxCK && !getenv("FSB_CODEC_OLD_POST")) {
+        const int C = c->conv_post.Cin, K = c->conv_post.K;
+        const size_t smem = ((size_t)C * (kPostTT + K - 1) + (size_t)C * K) * sizeof(float);
+        conv_post_kernel<<<(L + kPostTT - 1) / kPostTT, kPostThreads, smem, st>>>(cur, c->conv_post.wt, c->conv_post.bias, pcm_dev_out,
+                                                                                 C, K, L);
+        CLAUNCH_CHECK(c);
+        return FSB_OK;
+    }
     FSB_TRY(conv_fwd(c, c->conv_post, cur, L, pcm_dev_out, 1, 1, true, nullptr, 0, 0.f, true, nullptr));
     return FSB_OK;
 }
@@ -531,10 +565,13 @@ static int codec_create_impl(fsb_codec *c, const fsb_tensor *w, size_t n) {
         FSB_TRY(load_conv(c, w, n, p + "0.conv", kDim, kDim, 2, true, &c->up_conv[i]));
         FSB_TRY(load_convnext(c, w, n, p + "1.", kDim, &c->up_block[i]));
     }
-    FSB_TRY(load_conv(c, w, n, "head.conv_pre.conv", kDim, kDim, 13, false, &c->conv_pre));
+    // (conv_pre stays on the FP32-FMA kernel unless FSB_CODEC_TC_PRE is set: 22-bit operands at the very first conv move the
+    // PCM by 6e-5, too close to the 1e-4 parity bar; the ResBlock / upsampling convs together stay at 1-2e-5)
+    FSB_TRY(load_conv(c, w, n, "head.conv_pre.conv", kDim, kDim, 13, false, &c->conv_pre, false, getenv("FSB_CODEC_TC_PRE") != nullptr));
     for (int i = 0; i < 5; ++i) {
         const int cin = kDim >> i, cout = kDim >> (i + 1);
-        FSB_TRY(load_conv(c, w, n, "head.ups." + std::to_string(i) + ".conv", cin, cout, kUpKernels[i], true, &c->ups[i]));
+        FSB_TRY(load_conv(c, w, n, "head.ups." + std::to_string(i) + ".conv", cin, cout, kUpKernels[i], true, &c->ups[i], false,
+                          kUpKernels[i] == 2 * kUpRates[i] && getenv("FSB_CODEC_NO_TC_UPS") == nullptr));
         for (int j = 0; j < 3; ++j)
             for (int m = 0; m < 3; ++m) {
                 const std::string p = "head.resblocks." + std::to_string(i) + ".blocks." + std::to_string(j) + ".";
@@ -585,7 +622,7 @@ static int codec_create_impl(fsb_codec *c, const fsb_tensor *w, size_t n) {
     const size_t T = (size_t)c->max_frames;
     FSB_TRY(calloc_dev(c, &c->d_codes, (size_t)kGroups * T));
     FSB_TRY(calloc_dev(c, &c->d_err, 1));
-    for (int i = 0; i < (c->res_tc ? 7 : (c->res_tma ? 6 : 4)); ++i) FSB_TRY(calloc_dev(c, &c->buf[i], 32768 * T + 256 * 1024));
+    for (int i = 0; i < (c->res_tc ? 7 : (c->res_tma ? 6 : 4)); ++i) FSB_TRY(calloc_dev(c, &c->buf[i], 32768 * T + 512 * 1024));
     FSB_TRY(calloc_dev(c, &c->cn_h, 4 * T * kDim));
     FSB_TRY(calloc_dev(c, &c->cn_g, 4 * T * kDim * 4));
     FSB_TRY(calloc_dev(c, &c->d_idx, (size_t)kGroups * T));

@@ -325,6 +325,39 @@ __global__ void __launch_bounds__(256) resconv_tma_kernel(const __grid_constant_
     }
 }
 
+// ------------------------------------------------------------------ conv_post (hifi_gan.rs:213-215): C -> 1, K taps, causal
+//   y[t] = tanh( bias + sum_ci sum_k W[ci, k] * silu(x[ci, t + k - (K - 1)]) )
+// One output channel: an implicit-GEMM tile would idle 15 of 16 rows, so every thread owns outputs instead (kPostTT per
+// block), the silu'd input tile and the C x K weights sit in shared memory.
+constexpr int kPostTT = 512, kPostThreads = 256, kPostMaxCK = 16 * 13;
+__global__ void __launch_bounds__(kPostThreads) conv_post_kernel(const float *__restrict__ x, const float *__restrict__ wt /* (C, K, 1) */,
+                                                                 const float *__restrict__ bias, float *__restrict__ y, int C, int K,
+                                                                 int L) {
+    extern __shared__ float cp_smem[];
+    const int span = kPostTT + K - 1;
+    float *xs = cp_smem;             // [C][span]
+    float *ws = cp_smem + C * span;  // [C * K]
+    const int t0 = blockIdx.x * kPostTT;
+    for (int i = threadIdx.x; i < C * K; i += kPostThreads) ws[i] = wt[i];
+    for (int i = threadIdx.x; i < C * span; i += kPostThreads) {
+        const int ci = i / span, j = i - ci * span, t = t0 + j - (K - 1);
+        xs[i] = (t >= 0 && t < L) ? silu_f(x[(size_t)ci * L + t]) : 0.f;
+    }
+    __syncthreads();
+    const float bv = bias[0];
+#pragma unroll
+    for (int r = 0; r < kPostTT / kPostThreads; ++r) {
+        const int j = threadIdx.x + r * kPostThreads, t = t0 + j;
+        if (t >= L) continue;
+        float acc = 0.f;
+        for (int ci = 0; ci < C; ++ci) {
+            const float *xr = xs + ci * span + j, *wr = ws + ci * K;
+            for (int k = 0; k < K; ++k) acc = fmaf(wr[k], xr[k], acc);
+        }
+        y[t] = tanhf(acc + bv);
+    }
+}
+
 // ------------------------------------------------------------------ ConvNeXt block pieces (convnext.rs:109-127)
 // depthwise causal conv k=7 (pad 6) + LayerNorm over channels (biased variance, eps) -> h (L, C) time-major.
 // One warp per time step.
