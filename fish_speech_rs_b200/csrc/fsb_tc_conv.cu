@@ -146,7 +146,12 @@ __global__ void __launch_bounds__(kTcvThreads, 1) tcconv_kernel(const TcConvArgs
     const int rows_ld = 128 * MT + halo;                  // staged rows per (term, chunk)
     const uint32_t x_plane = (uint32_t)rows_ld * 16u;     // bytes of one (term, chunk) plane
     const uint32_t x_stage = 4u * x_plane;
-    constexpr uint32_t w_plane = (uint32_t)N * 16u, w_tap = 4u * w_plane;   // one (kb, tap): [2 terms][2 chunks][N][16 B]
+    constexpr uint32_t w_plane = (uint32_t)N * 16u, w_tap = 4u * w_plane;   // one (kb, tap): [2 chunks][hi | lo][N][16 B]
+    // N <= 64: the hi and lo weight rows of a chunk form ONE B operand of 2 N rows, so x_hi * [w_hi ; w_lo] is a single MMA
+    // into an accumulator tile of 2 N columns (hi*hi | hi*lo) and x_lo * w_hi a second one into its first N columns: the
+    // activation tile -- the bulk of the shared-memory operand traffic that bounds this kernel -- is read twice, not 3 times
+    constexpr bool STK = N <= 64;
+    constexpr int AW = STK ? 2 * N : N;  // accumulator columns per M tile
     const int tps = a.tps;                                                   // taps per weight stage (1, or K for small N)
     const uint32_t w_stage = (uint32_t)tps * w_tap;
     const int NCH = a.C / 8, NKB = a.C / 16, NCT = a.ncols / N;  // input chunks / 16-channel blocks, column tiles
@@ -167,7 +172,7 @@ __global__ void __launch_bounds__(kTcvThreads, 1) tcconv_kernel(const TcConvArgs
     // (ostride = 1, r = 0 for a plain conv; the transposed convs interleave their `ostride` phases)
     const int nch_out = a.cout / 8, Lout = a.L * a.ostride;
     const size_t Lp_out = tcv_image_rows(Lout);
-    const uint32_t acc_cols = (uint32_t)(MT * N);
+    const uint32_t acc_cols = (uint32_t)(MT * AW);
     const int kb_rot = a.rot ? (int)(blockIdx.x % (unsigned)NKB) : 0;  // experiment: per-CTA cyclic order of the channel blocks
 
     if (threadIdx.x == 0) {
@@ -237,7 +242,8 @@ __global__ void __launch_bounds__(kTcvThreads, 1) tcconv_kernel(const TcConvArgs
         // ---- MMA issuer (whole warp converged, one elected lane issues)
         // D[t, co] += X_term[t + tap * dil, 16 ci] * W_term[co, 16 ci]:  hi*hi, hi*lo, lo*hi
         constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);  // f16 x f16 -> f32
-        const uint64_t a_hi = tv_desc_hi(x_plane), b_hi = tv_desc_hi(w_plane);
+        constexpr uint32_t idesc2 = (1u << 4) | ((uint32_t)((2 * N) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint64_t a_hi = tv_desc_hi(x_plane), b_hi = tv_desc_hi(2 * w_plane);
         int wi = 0, xi = 0, it = 0;
         uint32_t wph = 0, xph = 0;
         long long tw_acc = 0, tw_x = 0, tw_w = 0, tw_issue = 0, tq = 0, n_st = 0;
@@ -266,16 +272,21 @@ __global__ void __launch_bounds__(kTcvThreads, 1) tcconv_kernel(const TcConvArgs
                         uint32_t xrow = xaddr + (uint32_t)(tap0 * dil) * 16u;
                         for (int tp = 0; tp < ntp; ++tp, waddr += w_tap, xrow += (uint32_t)dil * 16u) {
                             const uint64_t b0 = b_hi | (uint64_t)((waddr >> 4) & 0x3FFF);
-                            const uint64_t b1 = b_hi | (uint64_t)(((waddr + 2 * w_plane) >> 4) & 0x3FFF);
+                            const uint64_t b1 = b_hi | (uint64_t)(((waddr + w_plane) >> 4) & 0x3FFF);
                             const uint32_t first = (kbi | tap0 | tp) != 0 ? 1u : 0u;
                             for (int mt = 0; mt < MT; ++mt) {
                                 const uint32_t xa = xrow + (uint32_t)mt * 2048u;
                                 const uint64_t a0 = a_hi | (uint64_t)((xa >> 4) & 0x3FFF);
                                 const uint64_t a1 = a_hi | (uint64_t)(((xa + 2 * x_plane) >> 4) & 0x3FFF);
-                                const uint32_t d = dbase + (uint32_t)(mt * N);
-                                tv_mma(d, a0, b0, idesc, first);
-                                tv_mma(d, a0, b1, idesc, 1u);
-                                tv_mma(d, a1, b0, idesc, 1u);
+                                const uint32_t d = dbase + (uint32_t)(mt * AW);
+                                if constexpr (STK) {
+                                    tv_mma(d, a0, b0, idesc2, first);  // [hi*hi | hi*lo]
+                                    tv_mma(d, a1, b0, idesc, 1u);      // lo*hi into the first N columns
+                                } else {
+                                    tv_mma(d, a0, b0, idesc, first);
+                                    tv_mma(d, a0, b1, idesc, 1u);
+                                    tv_mma(d, a1, b0, idesc, 1u);
+                                }
                             }
                         }
                         tv_commit(wempty + wi);
@@ -343,7 +354,13 @@ __global__ void __launch_bounds__(kTcvThreads, 1) tcconv_kernel(const TcConvArgs
                 const int t = t0 + mt * 128 + row;
                 uint32_t v[CB];
                 __syncwarp();
-                tv_ld<CB>(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)buf * acc_cols + (uint32_t)(mt * N + cb), v);
+                tv_ld<CB>(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)buf * acc_cols + (uint32_t)(mt * AW + cb), v);
+                if constexpr (STK) {
+                    uint32_t v2[CB];
+                    tv_ld<CB>(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)buf * acc_cols + (uint32_t)(mt * AW + N + cb), v2);
+#pragma unroll
+                    for (int j = 0; j < CB; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
+                }
                 float o[CB];
                 if (t < a.L) {
 #pragma unroll
@@ -419,7 +436,7 @@ __global__ void __launch_bounds__(kTcvThreads, 1) tcconv_kernel(const TcConvArgs
     }
 }
 
-// (Cout, Cin, K) f32 -> [co tile][kb][tap][term][chunk][NT co][8 ci] fp16, scaled
+// (Cout, Cin, K) f32 -> [co tile][kb][tap][chunk][term][NT co][8 ci] fp16, scaled (hi rows, then lo rows, per 8-channel chunk)
 __global__ void tcv_weight_image_kernel(const float *__restrict__ raw, __half *__restrict__ img, int C, int K, int NT, float s_w) {
     const size_t n = (size_t)C * C * K;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
@@ -428,9 +445,9 @@ __global__ void tcv_weight_image_kernel(const float *__restrict__ raw, __half *_
         __half hi, lo;
         tv_split(raw[i] * s_w, hi, lo);
         const int ct = co / NT, col = co % NT;
-        const size_t o = (((((size_t)(ct * (C / 16) + kb) * K + tap) * 2 + 0) * 2 + ch) * NT + col) * 8 + j;
+        const size_t o = (((((size_t)(ct * (C / 16) + kb) * K + tap) * 2 + ch) * 2 + 0) * NT + col) * 8 + j;
         img[o] = hi;
-        img[o + (size_t)2 * NT * 8] = lo;
+        img[o + (size_t)NT * 8] = lo;
     }
 }
 
@@ -446,9 +463,9 @@ __global__ void tcv_weight_image_t_kernel(const float *__restrict__ raw, __half 
         const int kb = ci >> 4, ch = (ci >> 3) & 1, j = ci & 7;
         __half hi, lo;
         tv_split(raw[i] * s_w, hi, lo);
-        const size_t o = (((((size_t)(ct * (Cin / 16) + kb) * 2 + tap) * 2 + 0) * 2 + ch) * NT + cl) * 8 + j;
+        const size_t o = (((((size_t)(ct * (Cin / 16) + kb) * 2 + tap) * 2 + ch) * 2 + 0) * NT + cl) * 8 + j;
         img[o] = hi;
-        img[o + (size_t)2 * NT * 8] = lo;
+        img[o + (size_t)NT * 8] = lo;
     }
 }
 
@@ -623,7 +640,8 @@ int tcv_conv(const TcConvW &w, const float *bias, const __half *ximg, int L, int
     // per-tile time ~ (MT + 1) units (MT tiles of MMAs + the MT-independent weight staging): minimise rounds * (MT + 1)
     int MT = 1;
     long best = -1;
-    for (int mt = std::min(8, 256 / N); mt >= 1; --mt) {
+    const int aw = N <= 64 ? 2 * N : N;  // accumulator columns per M tile (stacked hi | lo products for N <= 64)
+    for (int mt = std::min(8, 256 / aw); mt >= 1; --mt) {
         if (tcv_smem_bytes(N, mt, K, dil, 2, tps) > budget) continue;
         const long tiles = (long)((n128 + mt - 1) / mt) * nct;
         const long cost = ((tiles + sms - 1) / sms) * (mt + 1);
@@ -632,7 +650,7 @@ int tcv_conv(const TcConvW &w, const float *bias, const __half *ximg, int L, int
             MT = mt;
         }
     }
-    if (const char *s = getenv("FSB_TCV_MT")) MT = std::max(1, std::min(256 / N, atoi(s)));
+    if (const char *s = getenv("FSB_TCV_MT")) MT = std::max(1, std::min(256 / aw, atoi(s)));
     a.MT = MT;
     a.tps = tps;
     int S = tps == 1 ? 16 : 4;
