@@ -87,6 +87,32 @@ pub struct fsb_codec_options {
 
 pub enum fsb_lm {}
 pub enum fsb_codec {}
+pub enum fsb_kv_snapshot {}
+
+/// fsb_lm_stats (include/fsb.h), same field order
+#[repr(C)]
+#[derive(Default, Clone, Copy)]
+pub struct fsb_lm_stats {
+    pub prefill_ms: f64,
+    pub decode_ms: f64,
+    pub frames: u64,
+    pub kernel_launches: u64,
+    pub dominant_kernel_ms: f64,
+    pub dominant_kernel_launches: u64,
+    pub weight_bytes_per_frame: u64,
+    pub dominant_kernel_bytes: u64,
+}
+
+/// fsb_codec_stats (include/fsb.h), same field order
+#[repr(C)]
+#[derive(Default, Clone, Copy)]
+pub struct fsb_codec_stats {
+    pub decode_ms: f64,
+    pub device_ms: f64,
+    pub kernel_launches: u64,
+    pub dominant_kernel_ms: f64,
+    pub dominant_kernel_launches: u64,
+}
 
 #[link(name = "fsb")]
 extern "C" {
@@ -112,6 +138,23 @@ extern "C" {
         lm: *mut fsb_lm, prompt: *const u32, prompt_len: i32, max_new_tokens: usize, sampling: *const fsb_sampling_args,
         flags: u32, fixed_len: i32, out_codes: *mut u32, cap: usize, out_len: *mut usize,
     ) -> c_int;
+    pub fn fsb_lm_generate_blocking_with_hidden(
+        lm: *mut fsb_lm, prompt: *const u32, prompt_len: i32, max_new_tokens: usize, sampling: *const fsb_sampling_args,
+        flags: u32, fixed_len: i32, out_codes: *mut u32, cap: usize, out_len: *mut usize, hidden: *mut f32,
+        hidden_cap: usize, n_hidden: *mut usize,
+    ) -> c_int;
+    pub fn fsb_lm_last_frames(lm: *mut fsb_lm, row: i32, out: *mut u32, cap: usize, out_len: *mut usize) -> c_int;
+    pub fn fsb_lm_kv_snapshot_save(lm: *mut fsb_lm, row: i32, n_positions: usize, out: *mut *mut fsb_kv_snapshot) -> c_int;
+    pub fn fsb_lm_kv_snapshot_restore(lm: *mut fsb_lm, snap: *const fsb_kv_snapshot, row: i32) -> c_int;
+    pub fn fsb_lm_kv_snapshot_free(lm: *mut fsb_lm, snap: *mut fsb_kv_snapshot) -> c_int;
+    pub fn fsb_lm_session_begin(lm: *mut fsb_lm, sampling: *const fsb_sampling_args, flags: u32) -> c_int;
+    pub fn fsb_lm_session_admit(
+        lm: *mut fsb_lm, slot: i32, prompt: *const u32, prompt_len: i32, max_new_tokens: usize, fixed_len: i32,
+    ) -> c_int;
+    pub fn fsb_lm_session_run(lm: *mut fsb_lm, max_frames: i32, active: *mut i32, n_active: *mut i32) -> c_int;
+    pub fn fsb_lm_session_collect(lm: *mut fsb_lm, slot: i32, out_codes: *mut u32, cap: usize, out_len: *mut usize) -> c_int;
+    pub fn fsb_lm_get_stats(lm: *mut fsb_lm, out: *mut fsb_lm_stats) -> c_int;
+    pub fn fsb_lm_set_profile(lm: *mut fsb_lm, on: c_int) -> c_int;
     pub fn fsb_lm_generate_static_batch(
         lm: *mut fsb_lm, prompts: *const *const u32, prompt_lens: *const i32, bsz: i32, max_new_tokens: usize,
         sampling: *const fsb_sampling_args, flags: u32, fixed_len: i32, out_codes: *const *mut u32, cap: usize,
@@ -121,6 +164,10 @@ extern "C" {
     pub fn fsb_codec_create(weights: *const fsb_tensor, n_weights: usize, opts: *const fsb_codec_options, out: *mut *mut fsb_codec) -> c_int;
     pub fn fsb_codec_destroy(codec: *mut fsb_codec) -> c_int;
     pub fn fsb_codec_decode(codec: *mut fsb_codec, codes: *const u32, n_frames: i32, pcm: *mut f32) -> c_int;
+    pub fn fsb_codec_decode_batch(
+        codec: *mut fsb_codec, codes: *const *const u32, n_frames: *const i32, n: i32, pcm: *const *mut f32,
+    ) -> c_int;
+    pub fn fsb_codec_get_stats(codec: *mut fsb_codec, out: *mut fsb_codec_stats) -> c_int;
     pub fn fsb_codec_decode_block(codec: *mut fsb_codec, codes: *const u32, n_frames_total: i32, t0: i32, t1: i32, pcm: *mut f32) -> c_int;
     pub fn fsb_codec_decode_block_s16(codec: *mut fsb_codec, codes: *const u32, n_frames_total: i32, t0: i32, t1: i32, to_rate: u32, out: *mut i16, cap: usize, out_len: *mut usize) -> c_int;
     pub fn fsb_codec_log_mel(codec: *mut fsb_codec, pcm: *const f32, n_samples: i64, mel: *mut f32, cap_frames: usize, out_frames: *mut usize) -> c_int;
