@@ -1237,10 +1237,17 @@ static int generate_impl(fsb_lm *lm, const uint32_t *const *prompts, const int32
         static const char *kn[7] = {"qkv", "attn", "wo", "w13|ffn", "w2|fred", "head", "sample"};
         for (int k = 0; k < 7; ++k) {  // wide-batch kernel: sub-steps of a projection phase on its owner CTA
             const unsigned long long *u = h + 192 + k * 8;
-            if (u[5])
+            if (u[5] && k != 1)
                 fprintf(stderr, "[megab owner] %-7s n=%6llu stage %5.2f  acc-wait %5.2f  epilogue|swiglu %5.2f  acc2-wait %5.2f  epilogue2 %5.2f us/phase\n",
                         kn[k], u[5], u[0] / 1965.0 / u[5], u[1] / 1965.0 / u[5], u[2] / 1965.0 / u[5], u[3] / 1965.0 / u[5],
                         u[4] / 1965.0 / u[5]);
+        }
+        {
+            const unsigned long long *u = h + 192 + 1 * 8;  // attention on CTA 0: [slow range, slow tail, n, fast range, fast tail, n]
+            if (u[2] || u[5])
+                fprintf(stderr, "[megab attn cta 0] slow: range %5.2f tail %5.2f us (n=%llu)   fast: range %5.2f tail %5.2f us (n=%llu)\n",
+                        u[2] ? u[0] / 1965.0 / u[2] : 0.0, u[2] ? u[1] / 1965.0 / u[2] : 0.0, u[2], u[5] ? u[3] / 1965.0 / u[5] : 0.0,
+                        u[5] ? u[4] / 1965.0 / u[5] : 0.0, u[5]);
         }
         for (int k = 0; k < 7; ++k) {  // wide-batch kernel: third timed CTA (74: owns a WO tile)
             const unsigned long long *e = h + 128 + k * 4;
