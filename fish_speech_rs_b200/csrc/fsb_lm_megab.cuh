@@ -172,7 +172,7 @@ struct MegaB {
         xf = reinterpret_cast<uint64_t *>(q); q += 16;
         acc_full = reinterpret_cast<uint64_t *>(q); q += 8;
         hr = reinterpret_cast<uint64_t *>(q); q += 8;
-        a2f = reinterpret_cast<uint64_t *>(q); q += 8;
+        a2f = reinterpret_cast<uint64_t *>(q); q += 8 * (kD / 128);  // one per accumulator tile of the second FFN GEMM
         tmem_slot = reinterpret_cast<uint32_t *>(q); q += 8;
         cmd = reinterpret_cast<volatile int *>(q); q += 4;
         go_frames = reinterpret_cast<volatile int *>(q); q += 4;
@@ -425,7 +425,7 @@ struct MegaB {
                                             (term | k) != 0 ? 1u : 0u);
                         }
                         mb_commit(empty + slot);
-                        if (r == kD / 128 - 1) mb_commit(a2f);
+                        mb_commit(a2f + r);  // tile r can be drained while the MMAs of the later tiles run
                     }
                     __syncwarp();
                     if (++slot == (unsigned)depth) { slot = 0; spar ^= 1; }
@@ -703,13 +703,14 @@ struct MegaB {
         }
         if (tm) { c1 = clock64(); td[2] += c1 - c0; c0 = c1; }
         mb_wait(a2f, pa2f);
-        pa2f ^= 1;
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if (tm) { c1 = clock64(); td[3] += c1 - c0; c0 = c1; }
         // partial y[t][b][128 r + row] (summed over the 64 blocks by fred_phase)
         float *yp = e.ws + (size_t)t * NPAD * kD + qd * 32 + lane;
 #pragma unroll 1
         for (int r8 = 0; r8 < kD / 128; ++r8) {
+            // the store-bound drain of tile r8 (16 KB per tile and CTA) overlaps the MMAs of the tiles behind it
+            mb_wait(a2f + r8, pa2f);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             float r[NPAD / 2];
             if (kStack2) {
                 drain_stacked(kAccCols + r8 * kAcc2Cols, r);
@@ -724,6 +725,7 @@ struct MegaB {
             for (int j = 0; j < NPAD / 2; ++j)
                 if (cc0 + j < p.nb) yp[(size_t)(cc0 + j) * kD + 128 * r8] = r[j];
         }
+        pa2f ^= 1;
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         if (tm) { td[4] += clock64() - c0; td[5] += 1; }
     }
@@ -1291,7 +1293,7 @@ megab_decode_kernel(const __grid_constant__ MegaParams p, const __grid_constant_
         }
         m1_mbar_init(m.acc_full, 1);
         m1_mbar_init(m.hr, 1);
-        m1_mbar_init(m.a2f, 1);
+        for (int i = 0; i < 8; ++i) m1_mbar_init(m.a2f + i, 1);
         *m.go_frames = 1;
         *m.done_flag = 0;
         *m.cmd = 0;

@@ -183,3 +183,33 @@ def test_sky_wav_through_the_gpu_front_end(codec, codec_weights):
     got = codec.encode(pcm)
     assert got.shape == (1, 8, 274)
     assert_index_mismatches_are_rounding_ties(got, pre.numpy(), exp.numpy())
+
+
+def test_tensor_core_vocoder_agrees_with_the_fp32_fma_vocoder(codec_weights):
+    """The HiFi-GAN ResBlock / upsampling convs run on tcgen05 (fp16 hi + lo split, three products per MAC,
+    csrc/fsb_tc_conv.cu); FSB_CODEC_NO_TC=1 keeps the round-2a FP32-FMA kernels.  Both must sit inside the PCM
+    tolerance of the oracle and close to each other, on a length that exercises several tiles per stage, a ragged
+    last tile and the persistent tile loop (148 CTAs < tiles at the late stages)."""
+    T = 97
+    codes = np.random.default_rng(1234).integers(0, 1000, size=(1, 8, T)).astype(np.uint32)
+    with torch.no_grad():
+        exp = ocodec.decode(torch.from_numpy(codes.astype(np.int64)), codec_weights).numpy()
+    outs, launches = {}, {}
+    for name, env in (("tc", None), ("fma", "1")):
+        old = os.environ.pop("FSB_CODEC_NO_TC", None)
+        if env is not None:
+            os.environ["FSB_CODEC_NO_TC"] = env
+        try:
+            c = FireflyCodec(codec_weights, max_frames=T)
+            outs[name] = c.decode(codes)
+            launches[name] = c.stats()["kernel_launches"]
+            c.close()
+        finally:
+            os.environ.pop("FSB_CODEC_NO_TC", None)
+            if old is not None:
+                os.environ["FSB_CODEC_NO_TC"] = old
+    for name, got in outs.items():
+        err = np.abs(got - exp).max()
+        assert err <= PCM_ATOL, f"{name}: max abs PCM error {err}"
+    assert np.abs(outs["tc"] - outs["fma"]).max() <= 5e-5
+    assert not np.array_equal(outs["tc"], outs["fma"])  # two different code paths really ran
