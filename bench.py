@@ -291,6 +291,8 @@ def run_ours(a):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     if world > 1:
+        # NCCL's own banner / debug lines go to stderr: stdout carries rank 0's JSON line and nothing else
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     c = CONFIGS[a.config]
     extras = [] if (world > 1 or not a.extras or a.config != "cfg5" or a.frames) else ["cfg3", "cfg2"]
