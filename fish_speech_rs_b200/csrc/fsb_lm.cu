@@ -1256,8 +1256,8 @@ static int generate_impl(fsb_lm *lm, const uint32_t *const *prompts, const int32
                         e[2] / 1965.0 / e[3]);
         }
         if (h[103])
-            fprintf(stderr, "[sample_fast] rep-pen %.2f  logits %.2f  block_sample %.2f us (n=%llu)\n", h[100] / 1965.0 / h[103],
-                    h[101] / 1965.0 / h[103], h[102] / 1965.0 / h[103], h[103]);
+            fprintf(stderr, "[sample_fast] rep-pen %.2f  logits %.2f  block_sample %.2f  tail (next input) %.2f us (n=%llu)\n", h[100] / 1965.0 / h[103],
+                    h[101] / 1965.0 / h[103], h[102] / 1965.0 / h[103], h[116] / 1965.0 / h[103], h[103]);
         if (h[107])
             fprintf(stderr, "[block_sample] max+softmax+keys %.2f  sort|select %.2f  scan|rank %.2f  (walk %.2f) us (n=%llu)\n",
                     h[104] / 1965.0 / h[107], h[105] / 1965.0 / h[107], h[106] / 1965.0 / h[107], h[108] / 1965.0 / h[107], h[107]);

@@ -1146,12 +1146,15 @@ struct MegaB {
         if (!s_active[0]) return;
         const bool eos = s_eos[0] != 0;
         const int frame = s_frame[0];
+        const bool tms = p.dbg != nullptr && tid == 0 && blockIdx.x == 0;
+        long long c0 = tms ? clock64() : 0, c1 = 0, c2 = 0, c3 = 0;
         if (!eos) {
             RepPenState *rp = s_rep + cb;
             if (frame > 0) {
                 if (tid == 0) rep_pen_update(rp, s_prev[1 + cb]);
                 wsync();
             }
+            if (tms) c1 = clock64();
             const float *lg = p.logits + (size_t)b * p.ldl;
             for (int i = tid; i < n; i += kMBWorkers) {
                 float v = __ldcg(lg + i);
@@ -1159,8 +1162,10 @@ struct MegaB {
                 vals[i] = v;
             }
             wsync();
+            if (tms) c2 = clock64();
             const float u = philox_uniform(st.sp.seed, (uint64_t)frame * C1 + cb + 1, (uint32_t)(p.row0 + b));
             const int a = block_sample_sel<MBSync>(vals, scratch, sred, n, st.sp, u);
+            if (tms) c3 = clock64();
             if (tid == 0) {
                 s_cur[1 + cb] = (uint32_t)a;
                 st.cur[b * C1 + 1 + cb] = (uint32_t)a;
@@ -1206,6 +1211,10 @@ struct MegaB {
             if (cont) embed_next_input();
         }
         wsync();
+        if (tms && !eos) {
+            const long long c4 = clock64();
+            p.dbg[100] += c1 - c0; p.dbg[101] += c2 - c1; p.dbg[102] += c3 - c2; p.dbg[103] += 1; p.dbg[116] += c4 - c3;
+        }
     }
 
     // ------------------------------------------------------------ frame loop (workers)
@@ -1223,6 +1232,7 @@ struct MegaB {
             store_xop4(e.xop_x, blockIdx.x, 4 * tid, make_float4(__fmul_rn(v.x, g4.x), __fmul_rn(v.y, g4.y), __fmul_rn(v.z, g4.z), __fmul_rn(v.w, g4.w)));
             finish_row(v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w, e.ssq_x + (size_t)blockIdx.x * kMBSsq);
         }
+        if (blockIdx.x == 0 && tid == 0 && p.dbg) g_sample_dbg = p.dbg + 104;
         frame_prep();
         grid_arrive();
         grid_wait();

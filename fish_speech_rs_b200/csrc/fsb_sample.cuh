@@ -95,7 +95,7 @@ struct SyncNamed {
 template <int E, class SY>
 __device__ __forceinline__ int block_sample_t(float *vals, unsigned long long *keys, float *red, int n, int n_pad,
                                               const SampleParams &sp, float u) {
-    const bool tm_ = g_sample_dbg != nullptr && threadIdx.x == 0;
+    const bool tm_ = g_sample_dbg != nullptr && threadIdx.x == 0 && blockIdx.x == 0;
     const long long q0 = tm_ ? clock64() : 0;
     const int tid = threadIdx.x, nthreads = SY::nthreads();
     const int lane = tid & 31, warp = tid >> 5, nwarps = nthreads >> 5;
@@ -327,7 +327,7 @@ __device__ __noinline__ int block_sample_sel_t(const float *vals, unsigned char 
     unsigned *hist = reinterpret_cast<unsigned *>(sorted + 256);                  // 3 x nwarps x 32
     unsigned *counter = hist + 3 * nwarps * 32;
     int *red_i = reinterpret_cast<int *>(red + 32);
-    const bool tm_ = g_sample_dbg != nullptr && threadIdx.x == 0;
+    const bool tm_ = g_sample_dbg != nullptr && threadIdx.x == 0 && blockIdx.x == 0;
     const long long q0 = tm_ ? clock64() : 0;
     float v[E];
     // ---- max (and first argmax) ----
@@ -433,11 +433,19 @@ __device__ __noinline__ int block_sample_sel_t(const float *vals, unsigned char 
         const unsigned ball = __ballot_sync(0xffffffffu, cum >= (unsigned)krem);
         const int d = __ffs(ball) - 1;  // ball != 0: the matching elements number >= krem by construction
         const unsigned below = __shfl_sync(0xffffffffu, cum - tot, d);
+        const unsigned in_bucket = __shfl_sync(0xffffffffu, tot, d);
         krem -= (int)below;
         prefix = (prefix << 5) | (unsigned)d;
         if (tm_) {
             const long long r3 = clock64();
             g_sample_dbg[9] += r1 - r0; g_sample_dbg[10] += r2 - r1; g_sample_dbg[11] += r3 - r2;
+        }
+        // every key of this bucket is among the k smallest: the threshold is the largest key with this prefix and the
+        // remaining digits need no refinement (block-uniform: all threads read the same totals).  Typically 4-5 rounds
+        // instead of 9 for 1024 keys.
+        if ((unsigned)krem == in_bucket) {
+            prefix = (prefix << shift) | ((1ull << shift) - 1ull);
+            break;
         }
     }
     const unsigned long long kth = prefix;
