@@ -561,6 +561,27 @@ struct MegaB {
         if (gw) compute_invd(ssq);
         const float gnext = kind == K_WO ? __ldg(consumer_norm(s) + 128 * t + (warp & 3) * 32 + lane) : 0.f;
         if (tm) { c1 = clock64(); td[0] += c1 - c0; c0 = c1; }
+        const int qd = warp & 3, cc0 = (warp >> 2) * (NPAD / 2);
+        const int row = qd * 32 + lane;
+        // operands of the epilogue that do not depend on the accumulator are requested BEFORE waiting for it: the residual
+        // rows (WO) / the RoPE table entries (QKV) arrive while the MMAs run instead of costing an L2 round trip afterwards
+        float xo[NPAD / 2], sn[NPAD / 2];  // WO: xo = residual;  QKV: xo = cos, sn = sin
+        if (kind == K_WO) {
+#pragma unroll
+            for (int j = 0; j < NPAD / 2; ++j)
+                xo[j] = cc0 + j < p.nb ? __ldcg(stream + (size_t)(cc0 + j) * kD + 128 * t + row) : 0.f;
+        } else if (kind == K_QKV) {
+            const int rr = 128 * t + row;
+            const int pi = (rr & 63) >> 1;
+            const bool roped = rr < kD + kKV * kHd;
+#pragma unroll
+            for (int j = 0; j < NPAD / 2; ++j) {
+                const int b = min(cc0 + j, p.nb - 1);
+                const int pos = slow ? (act_s[b] ? pos_s[b] : 0) : cb;  // a finished row may sit at max_len
+                xo[j] = roped ? __ldg(p.cosT + (size_t)pos * 32 + pi) : 1.f;
+                sn[j] = roped ? __ldg(p.sinT + (size_t)pos * 32 + pi) : 0.f;
+            }
+        }
         wsync();  // invd visible
         mb_wait(acc_full, pacc);
         pacc ^= 1;
@@ -568,14 +589,8 @@ struct MegaB {
         if (tm) { c1 = clock64(); td[1] += c1 - c0; c0 = c1; }
         float r[NPAD / 2];
         drain_stacked(0, r);
-        const int qd = warp & 3, cc0 = (warp >> 2) * (NPAD / 2);
-        const int row = qd * 32 + lane;
         if (kind == K_WO) {
             // residual add (dual_ar.rs:436-440) + this warp's share of sum(x^2) for the next RMSNorm
-            float xo[NPAD / 2];
-#pragma unroll
-            for (int j = 0; j < NPAD / 2; ++j)  // (all loads in flight before the first use)
-                xo[j] = cc0 + j < p.nb ? __ldcg(stream + (size_t)(cc0 + j) * kD + 128 * t + row) : 0.f;
 #pragma unroll
             for (int j = 0; j < NPAD / 2; ++j) {
                 const int b = cc0 + j;
@@ -594,16 +609,8 @@ struct MegaB {
             float *kcl = (slow ? p.kc : p.fkc) + s.l * kv_stride, *vcl = (slow ? p.vc : p.fvc) + s.l * kv_stride;
             const int cache_len = slow ? p.max_len : kC;
             const int rr = 128 * t + row;
-            const int pi = (rr & 63) >> 1;
             const bool roped = rr < kD + kKV * kHd;
-            float cs[NPAD / 2], sn[NPAD / 2];
-#pragma unroll
-            for (int j = 0; j < NPAD / 2; ++j) {
-                const int b = min(cc0 + j, p.nb - 1);
-                const int pos = slow ? (act_s[b] ? pos_s[b] : 0) : cb;  // a finished row may sit at max_len
-                cs[j] = roped ? __ldg(p.cosT + (size_t)pos * 32 + pi) : 1.f;
-                sn[j] = roped ? __ldg(p.sinT + (size_t)pos * 32 + pi) : 0.f;
-            }
+            const float(&cs)[NPAD / 2] = xo;
 #pragma unroll
             for (int j = 0; j < NPAD / 2; ++j) {
                 const int b = cc0 + j;
