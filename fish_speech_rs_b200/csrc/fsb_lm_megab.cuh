@@ -749,6 +749,13 @@ struct MegaB {
         const int b = c >> 2, sub = lane & 3;
         const int col = (c & 3) * 256 + warp * 32 + (lane >> 2) * 4;
         const float *yp = e.ws + ((size_t)(sub * 16) * NPAD + b) * kD + col;
+        // (the residual row and the consumer's norm weight are requested together with the partials)
+        float4 *xp = reinterpret_cast<float4 *>(stream + (size_t)b * kD + col);
+        float4 xo = make_float4(0.f, 0.f, 0.f, 0.f), g4 = xo;
+        if (sub == 0) {
+            xo = __ldcg(xp);
+            g4 = __ldg(reinterpret_cast<const float4 *>(consumer_norm(s) + col));
+        }
         float4 a = __ldcg(reinterpret_cast<const float4 *>(yp));
 #pragma unroll
         for (int j = 1; j < 16; ++j) {
@@ -764,12 +771,9 @@ struct MegaB {
         }
         float sq = 0.f;
         if (sub == 0) {
-            float4 *xp = reinterpret_cast<float4 *>(stream + (size_t)b * kD + col);
-            const float4 xo = __ldcg(xp);
             const float4 nv = make_float4(__fadd_rn(xo.x, a.x), __fadd_rn(xo.y, a.y), __fadd_rn(xo.z, a.z), __fadd_rn(xo.w, a.w));
             *xp = nv;
             sq = nv.x * nv.x + nv.y * nv.y + nv.z * nv.z + nv.w * nv.w;
-            const float4 g4 = __ldg(reinterpret_cast<const float4 *>(consumer_norm(s) + col));
             store_xop4(slow ? e.xop_x : e.xop_fx, b, col,
                        make_float4(__fmul_rn(nv.x, g4.x), __fmul_rn(nv.y, g4.y), __fmul_rn(nv.z, g4.z), __fmul_rn(nv.w, g4.w)));
         }
@@ -1006,16 +1010,27 @@ struct MegaB {
             if (bcast_s[0]) {
                 __threadfence();
                 const float *pp = e.apart + ((size_t)b * kH + h) * kMBMaxSplit * (kHd + 4);
+                // every partial (m, l, o) of the row is requested at once: one L2 round trip instead of two dependent ones
+                float2 ml[kMBMaxSplit], ov[kMBMaxSplit];
+#pragma unroll
+                for (int i = 0; i < kMBMaxSplit; ++i) {
+                    ml[i] = make_float2(-INFINITY, 0.f);
+                    ov[i] = make_float2(0.f, 0.f);
+                    if (i < ns) {
+                        ml[i] = __ldcg(reinterpret_cast<const float2 *>(pp + i * (kHd + 4) + kHd));
+                        ov[i] = __ldcg(reinterpret_cast<const float2 *>(pp + i * (kHd + 4) + lane * 2));
+                    }
+                }
                 float M = -INFINITY;
-                for (int i = 0; i < ns; ++i) M = fmaxf(M, __ldcg(pp + i * (kHd + 4) + kHd));
+#pragma unroll
+                for (int i = 0; i < kMBMaxSplit; ++i) M = fmaxf(M, ml[i].x);
                 float L = 0.f, a0 = 0.f, a1 = 0.f;
-                for (int i = 0; i < ns; ++i) {
-                    const float mi = __ldcg(pp + i * (kHd + 4) + kHd), li = __ldcg(pp + i * (kHd + 4) + kHd + 1);
-                    const float w = (mi == -INFINITY) ? 0.f : expf(mi - M);
-                    const float2 ov = __ldcg(reinterpret_cast<const float2 *>(pp + i * (kHd + 4) + lane * 2));
-                    L = fmaf(li, w, L);
-                    a0 = fmaf(ov.x, w, a0);
-                    a1 = fmaf(ov.y, w, a1);
+#pragma unroll
+                for (int i = 0; i < kMBMaxSplit; ++i) {
+                    const float w = (ml[i].x == -INFINITY) ? 0.f : expf(ml[i].x - M);
+                    L = fmaf(ml[i].y, w, L);
+                    a0 = fmaf(ov[i].x, w, a0);
+                    a1 = fmaf(ov[i].y, w, a1);
                 }
                 store_xop1(e.xop_att, b, h * kHd + lane * 2, a0 / L);
                 store_xop1(e.xop_att, b, h * kHd + lane * 2 + 1, a1 / L);
