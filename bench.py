@@ -290,9 +290,12 @@ def run_ours(a):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    # stdout carries rank 0's ONE JSON line and nothing else: native libraries that write to fd 1 (NCCL prints its version
+    # banner there) are sent to stderr, the JSON line goes out through a private duplicate of the original stdout
+    sys.stdout.flush()
+    json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if world > 1:
-        # NCCL's own banner / debug lines go to stderr: stdout carries rank 0's JSON line and nothing else
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     c = CONFIGS[a.config]
     extras = [] if (world > 1 or not a.extras or a.config != "cfg5" or a.frames) else ["cfg3", "cfg2"]
@@ -419,7 +422,8 @@ def run_ours(a):
             threads = os.cpu_count() or 1
             v, desc = cpu_reference_sample(a.config, lm_w, codec_w, a.cpu_sample_frames, threads)
             out["cpu_baseline"] = {"value": v, "unit": "frames/s", "cores": threads, "kind": "port", "sample": desc}
-        print(json.dumps(out))
+        json_out.write(json.dumps(out) + "\n")
+        json_out.flush()
     lm.close()
     codec.close()
     if world > 1:
