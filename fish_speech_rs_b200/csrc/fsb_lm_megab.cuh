@@ -742,10 +742,51 @@ struct MegaB {
     // summing 16 blocks, combined by a fixed shuffle tree.
     __device__ __forceinline__ void fred_phase(const Step &s) {
         const int c = blockIdx.x;
-        if (c >= 4 * p.nb) return;
         const bool slow = s.pass == 0;
         float *stream = slow ? p.x : p.fx;
         float *ssq = slow ? e.ssq_x : e.ssq_fx;
+        if constexpr (NPAD == 16) {
+            // at most 16 rows: EIGHT CTAs per row (128 columns each, 8 lanes per column quad, 8 blocks per lane) so that
+            // 128 instead of 64 SMs pull the 4 MB of partials
+            if (c >= 8 * p.nb) return;
+            const int b = c >> 3, sub = lane & 7;
+            const int col = (c & 7) * 128 + warp * 16 + (lane >> 3) * 4;
+            const float *yp = e.ws + ((size_t)(sub * 8) * NPAD + b) * kD + col;
+            float4 *xp = reinterpret_cast<float4 *>(stream + (size_t)b * kD + col);
+            float4 xo = make_float4(0.f, 0.f, 0.f, 0.f), g4 = xo;
+            if (sub == 0) {
+                xo = __ldcg(xp);
+                g4 = __ldg(reinterpret_cast<const float4 *>(consumer_norm(s) + col));
+            }
+            float4 a = __ldcg(reinterpret_cast<const float4 *>(yp));
+#pragma unroll
+            for (int j = 1; j < 8; ++j) {
+                const float4 q = __ldcg(reinterpret_cast<const float4 *>(yp + (size_t)j * NPAD * kD));
+                a.x += q.x; a.y += q.y; a.z += q.z; a.w += q.w;
+            }
+#pragma unroll
+            for (int o = 1; o < 8; o <<= 1) {
+                a.x += __shfl_xor_sync(0xffffffffu, a.x, o);
+                a.y += __shfl_xor_sync(0xffffffffu, a.y, o);
+                a.z += __shfl_xor_sync(0xffffffffu, a.z, o);
+                a.w += __shfl_xor_sync(0xffffffffu, a.w, o);
+            }
+            float sq = 0.f;
+            if (sub == 0) {
+                const float4 nv = make_float4(__fadd_rn(xo.x, a.x), __fadd_rn(xo.y, a.y), __fadd_rn(xo.z, a.z), __fadd_rn(xo.w, a.w));
+                *xp = nv;
+                sq = nv.x * nv.x + nv.y * nv.y + nv.z * nv.z + nv.w * nv.w;
+                store_xop4(slow ? e.xop_x : e.xop_fx, b, col,
+                           make_float4(__fmul_rn(nv.x, g4.x), __fmul_rn(nv.y, g4.y), __fmul_rn(nv.z, g4.z), __fmul_rn(nv.w, g4.w)));
+            }
+            sq = warp_sum(sq);
+            // 8 CTAs x 8 warps share the row's kMBSsq = 32 slots: warp pairs are combined through shared memory
+            if (lane == 0) red[64 + warp] = sq;
+            wsync();
+            if (tid < 4) ssq[(size_t)b * kMBSsq + (c & 7) * 4 + tid] = red[64 + 2 * tid] + red[64 + 2 * tid + 1];
+            return;
+        }
+        if (c >= 4 * p.nb) return;
         const int b = c >> 2, sub = lane & 3;
         const int col = (c & 3) * 256 + warp * 32 + (lane >> 2) * 4;
         const float *yp = e.ws + ((size_t)(sub * 16) * NPAD + b) * kD + col;
