@@ -149,25 +149,43 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
             for (int i = 0; i < 3; ++i)
                 tma_load_2d(st + A_BYTES + i * B_BYTES, &tmX, full + s, (kb0 + kb) * kBK, i * x_seg_rows + p0);
         }
-    } else if (warp == 1 && lane == 0) {
-        // ---- MMA issuer: D (TMEM, 128 lanes x BN fp32 columns) += W_tile (M = 128) x X_tile^T (N = BN), K = 16 per instruction
+    } else if (warp == 1) {
+        // ---- MMA issuer: D (TMEM, 128 lanes x BN fp32 columns) += W_tile (M = 128) x X_tile^T (N = BN), K = 16 per instruction.
+        // The whole warp stays converged and one elected lane issues; the descriptors differ only in their 14-bit start-address
+        // field, so they are a base plus constants (the first version rebuilt both descriptors per MMA from a divergent
+        // single-lane branch: ~15 instructions per MMA against 64 cycles of tensor time at BN = 128)
         const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+        const uint64_t desc0 = umma_desc_k_sw128(smem_u32(tc_smem));
+        int s = 0;
+        uint32_t par = 0;
         for (int kb = 0; kb < nk; ++kb) {
-            const int s = kb % kStages;
-            mbar_wait(full + s, (kb / kStages) & 1);
+            mbar_wait(full + s, par);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t a_addr = smem_u32(tc_smem + (size_t)s * STAGE);
+            uint32_t elected;
+            asm volatile(
+                "{\n\t"
+                ".reg .pred p;\n\t"
+                "elect.sync _|p, 0xffffffff;\n\t"
+                "selp.u32 %0, 1, 0, p;\n\t"
+                "}\n"
+                : "=r"(elected));
+            if (elected) {
+                const uint64_t ad = desc0 + (uint64_t)(s * (STAGE >> 4));
 #pragma unroll
-            for (int i = 0; i < 3; ++i) {
-                const uint32_t b_addr = a_addr + A_BYTES + i * B_BYTES;
+                for (int i = 0; i < 3; ++i) {
+                    const uint64_t bd = ad + (uint64_t)((A_BYTES + i * B_BYTES) >> 4);
 #pragma unroll
-                for (int k = 0; k < kBK / 16; ++k)
-                    umma_bf16(tmem_base, umma_desc_k_sw128(a_addr + k * 32), umma_desc_k_sw128(b_addr + k * 32), idesc,
-                              (kb | i | k) != 0 ? 1u : 0u);
+                    for (int k = 0; k < kBK / 16; ++k) umma_bf16(tmem_base, ad + 2 * k, bd + 2 * k, idesc, (kb | i | k) != 0 ? 1u : 0u);
+                }
+                umma_commit(empty + s);  // frees the smem stage once these MMAs have read it
+                if (kb == nk - 1) umma_commit(tmem_full);
             }
-            umma_commit(empty + s);  // frees the smem stage once these MMAs have read it
+            __syncwarp();
+            if (++s == kStages) {
+                s = 0;
+                par ^= 1;
+            }
         }
-        umma_commit(tmem_full);
     } else if (warp >= 2) {
         // ---- epilogue: warp (w % 4) owns TMEM lanes [32 (w % 4), +32) == weight rows of the tile
         mbar_wait(tmem_full, 0);
