@@ -351,6 +351,16 @@ static int prefill_pass(fsb_lm *lm, const std::vector<PrefillSeg> &segs) {
     }
     const float scale = 1.0f / sqrtf((float)hd);
     const bool tc = lm->tc_ok;
+    // Fish shapes (head_dim 64, 8 query heads per KV head): register-blocked attention kernel
+    const bool pf8 = hd == 64 && H == 8 * KV && getenv("FSB_PREFILL_ATT_V1") == nullptr;
+    if (pf8) {
+        static bool attr_done = false;
+        if (!attr_done) {
+            FSB_CUDA_OK(cudaFuncSetAttribute(attn_prefill8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)(kPf2SmemFloats * sizeof(float))));
+            attr_done = true;
+        }
+    }
     const int bn = tc_pick_bn(S), bi = bn == 32 ? 0 : (bn == 64 ? 1 : 2);
     const int seg = lm->prefill_rows;
     // segment table for the batched RoPE / attention launches (rope_delta != 0 only occurs on the single-row step API)
@@ -382,8 +392,13 @@ static int prefill_pass(fsb_lm *lm, const std::vector<PrefillSeg> &segs) {
             rope_append_rows_kernel<<<dim3(max_n, (unsigned)segs.size()), 256, 0, st>>>(
                 s.qkv, s.q, slow_k(lm, l), slow_v(lm, l), lm->cosT, lm->sinT, 0, 0, 0, H, KV, hd, lm->max_len, lm->d_segs);
             LAUNCH_CHECK(lm);
-            attn_prefill_kernel<<<dim3((max_n + kPrefQ - 1) / kPrefQ, KV, (unsigned)segs.size()), 512, 0, st>>>(
-                s.q, slow_k(lm, l), slow_v(lm, l), 0, 0, 0, H, KV, hd, lm->max_len, scale, s.att, lm->d_segs);
+            if (pf8)
+                attn_prefill8_kernel<<<dim3((max_n + kPf2Q - 1) / kPf2Q, KV, (unsigned)segs.size()), kPf2Threads,
+                                       kPf2SmemFloats * sizeof(float), st>>>(s.q, slow_k(lm, l), slow_v(lm, l), 0, 0, 0, H, KV,
+                                                                             lm->max_len, s.att, lm->d_segs);
+            else
+                attn_prefill_kernel<<<dim3((max_n + kPrefQ - 1) / kPrefQ, KV, (unsigned)segs.size()), 512, 0, st>>>(
+                    s.q, slow_k(lm, l), slow_v(lm, l), 0, 0, 0, H, KV, hd, lm->max_len, scale, s.att, lm->d_segs);
             LAUNCH_CHECK(lm);
         } else {
             for (const PrefillSeg &g : segs) {
@@ -391,9 +406,14 @@ static int prefill_pass(fsb_lm *lm, const std::vector<PrefillSeg> &segs) {
                                                              slow_k(lm, l), slow_v(lm, l), lm->cosT, lm->sinT, g.b, g.pos0,
                                                              g.rope_delta, H, KV, hd, lm->max_len);
                 LAUNCH_CHECK(lm);
-                attn_prefill_kernel<<<dim3((g.n + kPrefQ - 1) / kPrefQ, KV), 512, 0, st>>>(
-                    s.q + (size_t)g.off * H * hd, slow_k(lm, l), slow_v(lm, l), g.b, g.pos0, g.n, H, KV, hd, lm->max_len, scale,
-                    s.att + (size_t)g.off * H * hd);
+                if (pf8)
+                    attn_prefill8_kernel<<<dim3((g.n + kPf2Q - 1) / kPf2Q, KV), kPf2Threads, kPf2SmemFloats * sizeof(float), st>>>(
+                        s.q + (size_t)g.off * H * hd, slow_k(lm, l), slow_v(lm, l), g.b, g.pos0, g.n, H, KV, lm->max_len,
+                        s.att + (size_t)g.off * H * hd);
+                else
+                    attn_prefill_kernel<<<dim3((g.n + kPrefQ - 1) / kPrefQ, KV), 512, 0, st>>>(
+                        s.q + (size_t)g.off * H * hd, slow_k(lm, l), slow_v(lm, l), g.b, g.pos0, g.n, H, KV, hd, lm->max_len, scale,
+                        s.att + (size_t)g.off * H * hd);
                 LAUNCH_CHECK(lm);
             }
         }

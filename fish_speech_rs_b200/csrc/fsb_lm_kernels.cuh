@@ -539,6 +539,152 @@ __global__ void __launch_bounds__(512) attn_prefill_kernel(const float *__restri
     }
 }
 
+// Register-blocked variant for the Fish shapes (head_dim 64, 8 query heads per KV head): one CTA = 16 consecutive queries x
+// the 8 heads of a KV group = 128 (query, head) rows; K / V tiles of 32 positions in shared memory.  Thread (ty, tx) owns
+// rows 4 ty .. 4 ty + 3 (ONE query, four heads) in both products: S = Q K^T as a 4 x 4 block (columns tx + 8 j), then
+// O += P V as a 4 x 8 block (dims 4 tx .. and 32 + 4 tx ..), P handed over through shared memory within the 8 lanes that own
+// the rows (no block barrier between the two products).  ~9 FMAs per 16-byte shared-memory load against ~0.7 in
+// attn_prefill_kernel (one (query, head) item per warp, a full dot product per lane).
+constexpr int kPf2Q = 16, kPf2Threads = 256, kPf2QS = 68, kPf2KS = 68, kPf2PS = 36;
+constexpr int kPf2SmemFloats = 128 * kPf2QS + 32 * kPf2KS + 32 * 64 + 128 * kPf2PS;
+__global__ void __launch_bounds__(kPf2Threads) attn_prefill8_kernel(const float *__restrict__ q, const float *__restrict__ kc,
+                                                                    const float *__restrict__ vc, int b, int pos0, int S, int H,
+                                                                    int KV, int max_len, float *__restrict__ y,
+                                                                    const int4 *segs = nullptr) {
+    if (segs) {
+        const int4 sg = segs[blockIdx.z];
+        if ((int)blockIdx.x * kPf2Q >= sg.z) return;
+        b = sg.x;
+        pos0 = sg.y;
+        S = sg.z;
+        q += (size_t)sg.w * H * 64;
+        y += (size_t)sg.w * H * 64;
+    }
+    extern __shared__ float pf2_smem[];
+    float *Qs = pf2_smem, *Ks = Qs + 128 * kPf2QS, *Vs = Ks + 32 * kPf2KS, *Ps = Vs + 32 * 64;
+    const int tid = threadIdx.x, ty = tid >> 3, tx = tid & 7;
+    const int kvh = blockIdx.y, s0 = blockIdx.x * kPf2Q;
+    const int nq = min(kPf2Q, S - s0);
+    const float *kb = kc + ((size_t)b * KV + kvh) * max_len * 64;
+    const float *vb = vc + ((size_t)b * KV + kvh) * max_len * 64;
+    // Q tile: row r = 8 qi + hh <- q[(s0 + qi) H + 8 kvh + hh], scaled by 1 / sqrt(64) (a power of two: bit-identical to
+    // scaling the scores, dual_ar.rs:258-260)
+    for (int i = tid; i < 128 * 16; i += kPf2Threads) {
+        const int r = i >> 4, c4 = i & 15, qi = r >> 3, hh = r & 7;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (qi < nq) {
+            v = *reinterpret_cast<const float4 *>(q + ((size_t)(s0 + qi) * H + kvh * 8 + hh) * 64 + c4 * 4);
+            v.x *= 0.125f; v.y *= 0.125f; v.z *= 0.125f; v.w *= 0.125f;
+        }
+        *reinterpret_cast<float4 *>(Qs + r * kPf2QS + c4 * 4) = v;
+    }
+    const int qi = ty >> 1;                  // the thread's query (rows 4 ty .. 4 ty + 3 = heads 4 (ty & 1) ..)
+    const int len = pos0 + s0 + qi + 1;      // positions this query sees (get_mask_abs, dual_ar.rs:702-712)
+    const int len_max = pos0 + s0 + nq;      // ... and the last query of the CTA
+    float m[4], l[4], o[4][8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        m[i] = -INFINITY;
+        l[i] = 0.f;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[i][e] = 0.f;
+    }
+    for (int t0 = 0; t0 < len_max; t0 += 32) {
+        __syncthreads();  // previous tile consumed (first pass: Q tile written)
+        for (int i = tid; i < 32 * 16; i += kPf2Threads) {
+            const int j = i >> 4, c4 = i & 15;
+            float4 kk = make_float4(0.f, 0.f, 0.f, 0.f), vv = kk;
+            if (t0 + j < len_max) {
+                kk = *reinterpret_cast<const float4 *>(kb + (size_t)(t0 + j) * 64 + c4 * 4);
+                vv = *reinterpret_cast<const float4 *>(vb + (size_t)(t0 + j) * 64 + c4 * 4);
+            }
+            *reinterpret_cast<float4 *>(Ks + j * kPf2KS + c4 * 4) = kk;
+            *reinterpret_cast<float4 *>(Vs + j * 64 + c4 * 4) = vv;
+        }
+        __syncthreads();
+        // (a query that sees nothing of this tile still walks it with every column masked: m stays, corr = 1, p = 0 -- the
+        // shuffles and __syncwarp below need the whole warp, and a warp holds two queries)
+        // ---- S = Q K^T, rows 4 ty + i, columns tx + 8 j
+        float sc[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) sc[i][j] = 0.f;
+#pragma unroll 4
+        for (int d = 0; d < 64; d += 4) {
+            float4 qv[4], kv[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) qv[i] = *reinterpret_cast<const float4 *>(Qs + (4 * ty + i) * kPf2QS + d);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) kv[j] = *reinterpret_cast<const float4 *>(Ks + (tx + 8 * j) * kPf2KS + d);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    sc[i][j] = fmaf(qv[i].w, kv[j].w, fmaf(qv[i].z, kv[j].z, fmaf(qv[i].y, kv[j].y, fmaf(qv[i].x, kv[j].x, sc[i][j]))));
+        }
+        // ---- online softmax per row (the row's 32 scores live in the 8 lanes tx = 0..7 of this ty)
+        bool ok[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) ok[j] = t0 + tx + 8 * j < len;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float mx = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) mx = ok[j] ? fmaxf(mx, sc[i][j]) : mx;
+#pragma unroll
+            for (int off = 1; off < 8; off <<= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+            const float m_new = fmaxf(m[i], mx);  // finite: position t0 is visible to this query
+            const float corr = expf(m[i] - m_new);
+            float rs = 0.f;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float pr = ok[j] ? expf(sc[i][j] - m_new) : 0.f;
+                Ps[(4 * ty + i) * kPf2PS + tx + 8 * j] = pr;
+                rs += pr;
+            }
+#pragma unroll
+            for (int off = 1; off < 8; off <<= 1) rs += __shfl_xor_sync(0xffffffffu, rs, off);
+            l[i] = fmaf(l[i], corr, rs);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[i][e] *= corr;
+            m[i] = m_new;
+        }
+        __syncwarp();  // the 8 lanes of a ty sit in one warp: P is visible to its readers
+        // ---- O += P V, rows 4 ty + i, dims 4 tx .. 4 tx + 3 and 32 + 4 tx ..
+#pragma unroll 2
+        for (int k = 0; k < 32; k += 4) {
+            float4 pv[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) pv[i] = *reinterpret_cast<const float4 *>(Ps + (4 * ty + i) * kPf2PS + k);
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                const float4 v0 = *reinterpret_cast<const float4 *>(Vs + (k + kk) * 64 + 4 * tx);
+                const float4 v1 = *reinterpret_cast<const float4 *>(Vs + (k + kk) * 64 + 32 + 4 * tx);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float pr = kk == 0 ? pv[i].x : kk == 1 ? pv[i].y : kk == 2 ? pv[i].z : pv[i].w;
+                    o[i][0] = fmaf(pr, v0.x, o[i][0]); o[i][1] = fmaf(pr, v0.y, o[i][1]);
+                    o[i][2] = fmaf(pr, v0.z, o[i][2]); o[i][3] = fmaf(pr, v0.w, o[i][3]);
+                    o[i][4] = fmaf(pr, v1.x, o[i][4]); o[i][5] = fmaf(pr, v1.y, o[i][5]);
+                    o[i][6] = fmaf(pr, v1.z, o[i][6]); o[i][7] = fmaf(pr, v1.w, o[i][7]);
+                }
+            }
+        }
+        __syncwarp();  // P of this tile consumed before the next tile's rows overwrite it
+    }
+    if (qi < nq) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int hh = 4 * (ty & 1) + i;
+            const float inv = 1.0f / l[i];
+            float *dst = y + ((size_t)(s0 + qi) * H + kvh * 8 + hh) * 64;
+            *reinterpret_cast<float4 *>(dst + 4 * tx) = make_float4(o[i][0] * inv, o[i][1] * inv, o[i][2] * inv, o[i][3] * inv);
+            *reinterpret_cast<float4 *>(dst + 32 + 4 * tx) = make_float4(o[i][4] * inv, o[i][5] * inv, o[i][6] * inv, o[i][7] * inv);
+        }
+    }
+}
+
 // ------------------------------------------------------------------ samplers
 // Slow head: constrained logits (generate/utils.rs:6-33) -> token (utils.rs:36-56),
 // EOS bookkeeping (single_batch.rs:153-156,199-204).  grid B, block 1024.
