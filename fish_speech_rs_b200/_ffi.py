@@ -6,7 +6,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfsb.so")
+# FSB_LIB: same-box A/B runs of two builds of the library (tools/gpu_ab2.sh); the default is the in-tree build
+LIB_PATH = os.environ.get("FSB_LIB") or os.path.join(_HERE, "libfsb.so")
 
 FSB_F32, FSB_BF16, FSB_F16, FSB_U32, FSB_I64, FSB_U8, FSB_F64 = range(7)
 FSB_FISH_1_2, FSB_FISH_1_4, FSB_FISH_1_5 = 12, 14, 15

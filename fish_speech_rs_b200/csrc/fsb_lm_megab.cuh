@@ -590,46 +590,64 @@ struct MegaB {
         float r[NPAD / 2];
         drain_stacked(0, r);
         if (kind == K_WO) {
-            // residual add (dual_ar.rs:436-440) + this warp's share of sum(x^2) for the next RMSNorm
+            // residual add (dual_ar.rs:436-440) + this warp's share of sum(x^2) for the next RMSNorm.  All batch columns
+            // are computed unconditionally (padding columns hold zeros) so that the NPAD / 2 butterfly chains are
+            // independent instruction streams; only the stores are predicated.  (With the work inside `if (b < nb)`
+            // the columns ran one after the other: 3.5-4.6 us per phase at 32 rows.)
+            float nv[NPAD / 2], sq[NPAD / 2];
+#pragma unroll
+            for (int j = 0; j < NPAD / 2; ++j) {
+                nv[j] = __fadd_rn(xo[j], r[j]);
+                sq[j] = nv[j] * nv[j];
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {  // same tree as warp_sum
+#pragma unroll
+                for (int j = 0; j < NPAD / 2; ++j) sq[j] += __shfl_xor_sync(0xffffffffu, sq[j], o);
+            }
+            unsigned char *xop = slow ? e.xop_x : e.xop_fx;
+            float mine = 0.f;  // lane j keeps column j's sum: one store instruction for all columns
 #pragma unroll
             for (int j = 0; j < NPAD / 2; ++j) {
                 const int b = cc0 + j;
+                if (lane == j) mine = sq[j];
                 if (b < p.nb) {
-                    const float nv = __fadd_rn(xo[j], r[j]);
-                    stream[(size_t)b * kD + 128 * t + row] = nv;
-                    store_xop1(slow ? e.xop_x : e.xop_fx, b, 128 * t + row, __fmul_rn(nv, gnext));
-                    const float q = warp_sum(nv * nv);
-                    if (lane == 0) ssq[(size_t)b * kMBSsq + t * 4 + qd] = q;
+                    stream[(size_t)b * kD + 128 * t + row] = nv[j];
+                    store_xop1(xop, b, 128 * t + row, __fmul_rn(nv[j], gnext));
                 }
             }
+            if (lane < NPAD / 2 && cc0 + lane < p.nb) ssq[(size_t)(cc0 + lane) * kMBSsq + t * 4 + qd] = mine;
         } else if (kind == K_QKV) {
             // rope_i on row pairs (dual_ar.rs:246-247; adjacent rows = adjacent lanes) -> q buffer / K cache; V rows ->
-            // V cache (Tensor::cat, :316-324)
+            // V cache (Tensor::cat, :316-324).  Values for all columns first (independent chains), predicated stores after.
             const size_t kv_stride = slow ? p.slow_kv_stride : p.fast_kv_stride;
             float *kcl = (slow ? p.kc : p.fkc) + s.l * kv_stride, *vcl = (slow ? p.vc : p.fvc) + s.l * kv_stride;
             const int cache_len = slow ? p.max_len : kC;
             const int rr = 128 * t + row;
             const bool roped = rr < kD + kKV * kHd;
             const float(&cs)[NPAD / 2] = xo;
+            float ov[NPAD / 2];
 #pragma unroll
             for (int j = 0; j < NPAD / 2; ++j) {
-                const int b = cc0 + j;
-                if (b < p.nb) {
-                    const float v = r[j] * invd[b];
-                    const float w = __shfl_xor_sync(0xffffffffu, v, 1);
-                    const int pos = slow ? (act_s[b] ? pos_s[b] : 0) : cb;
-                    if (roped) {
-                        const float o = (lane & 1) ? __fadd_rn(__fmul_rn(w, sn[j]), __fmul_rn(v, cs[j]))
-                                                   : __fsub_rn(__fmul_rn(v, cs[j]), __fmul_rn(w, sn[j]));
-                        if (rr < kD) {
-                            p.q[(size_t)b * kD + rr] = o;
-                        } else if (act_s[b]) {
-                            const int rk = rr - kD, kvh = rk >> 6, d = rk & 63;
-                            kcl[(((size_t)b * kKV + kvh) * cache_len + pos) * kHd + d] = o;
-                        }
-                    } else if (act_s[b]) {
-                        const int rv = rr - kD - kKV * kHd, kvh = rv >> 6, d = rv & 63;
-                        vcl[(((size_t)b * kKV + kvh) * cache_len + pos) * kHd + d] = v;
+                const float v = r[j] * invd[min(cc0 + j, p.nb - 1)];
+                const float w = __shfl_xor_sync(0xffffffffu, v, 1);
+                const float o = (lane & 1) ? __fadd_rn(__fmul_rn(w, sn[j]), __fmul_rn(v, cs[j]))
+                                           : __fsub_rn(__fmul_rn(v, cs[j]), __fmul_rn(w, sn[j]));
+                ov[j] = roped ? o : v;
+            }
+            if (rr < kD) {
+#pragma unroll
+                for (int j = 0; j < NPAD / 2; ++j)
+                    if (cc0 + j < p.nb) p.q[(size_t)(cc0 + j) * kD + rr] = ov[j];
+            } else {
+                const int rk = roped ? rr - kD : rr - kD - kKV * kHd, kvh = rk >> 6, d = rk & 63;
+                float *cl = roped ? kcl : vcl;
+#pragma unroll
+                for (int j = 0; j < NPAD / 2; ++j) {
+                    const int b = cc0 + j;
+                    if (b < p.nb && act_s[b]) {
+                        const int pos = slow ? pos_s[b] : cb;
+                        cl[(((size_t)b * kKV + kvh) * cache_len + pos) * kHd + d] = ov[j];
                     }
                 }
             }
@@ -681,18 +699,24 @@ struct MegaB {
             // accumulator lanes [0, 64) = w1 rows, [64, 128) = w3 rows of the block: pair them through shared memory
             float r[NPAD / 2];
             drain_stacked(0, r);
-            float *exch = reinterpret_cast<float *>(xs + kXBuf);  // [NPAD][64]; both slice buffers are idle now
-            if (qd >= 2) {
+            // all eight warps take part in SwiGLU: a w1 warp (qd < 2) keeps the first half of its batch columns and hands
+            // the second half to the w3 warp of the same rows, which hands over its first half: [2][NPAD][64] floats
+            float *exch = reinterpret_cast<float *>(xs + kXBuf);  // both slice buffers are idle now
+            constexpr int kHalf = NPAD / 4;
+            const int i = (qd & 1) * 32 + lane;  // column of the block == k index of the second GEMM
+            const int jg = qd < 2 ? kHalf : 0;   // the columns this thread gives away
+            float *mine = exch + (qd < 2 ? 0 : NPAD * 64), *theirs = exch + (qd < 2 ? NPAD * 64 : 0);
 #pragma unroll
-                for (int j = 0; j < NPAD / 2; ++j) exch[(cc0 + j) * 64 + (qd - 2) * 32 + lane] = r[j];
-            }
+            for (int j = 0; j < kHalf; ++j) mine[(cc0 + jg + j) * 64 + i] = qd < 2 ? r[kHalf + j] : r[j];
             wsync();
-            if (qd < 2) {
-                const int i = qd * 32 + lane;  // column of the block == k index of the second GEMM
+            {
+                const int jk = kHalf - jg;  // the columns this thread keeps
 #pragma unroll
-                for (int j = 0; j < NPAD / 2; ++j) {
-                    const int b = cc0 + j;
-                    const float g1 = r[j] * invd[b < p.nb ? b : 0], g3 = exch[b * 64 + i] * invd[b < p.nb ? b : 0];
+                for (int j = 0; j < kHalf; ++j) {
+                    const int b = cc0 + jk + j;
+                    const float other = theirs[b * 64 + i], own = qd < 2 ? r[j] : r[kHalf + j];
+                    const float sc = invd[b < p.nb ? b : 0];
+                    const float g1 = (qd < 2 ? own : other) * sc, g3 = (qd < 2 ? other : own) * sc;
                     const float hv = b < p.nb ? __fmul_rn(silu_f(g1), g3) : 0.f;
                     unsigned short hh, hm, hl;
                     mb_split3(hv, hh, hm, hl);
