@@ -12,6 +12,15 @@
 
 namespace fsb {
 
+// mod.rs:67 gates the top-p branch in f64 (`top_p <= 0.0 || top_p >= sum_p as f64`); sum_p is an f32, so the gate is
+// `sum_p <= (largest f32 that is <= top_p)`, which the device can test without doubles
+static float top_p_gate_of(double top_p) {
+    if (top_p <= 0.0) return INFINITY;
+    float f = (float)top_p;
+    if ((double)f > top_p) f = std::nextafterf(f, -INFINITY);
+    return f;
+}
+
 struct LayerW {
     DevTensor wqkv, wo, w1, w2, w3;
     TcMap m_wqkv, m_wo, m_w1, m_w2, m_w3;  // TMA maps of the bf16 matrices (tcgen05 prefill)
@@ -1097,6 +1106,7 @@ static int generate_impl(fsb_lm *lm, const uint32_t *const *prompts, const int32
     g.sp.greedy = sa->temp <= 1e-7 ? 1 : 0;
     g.sp.inv_temp = g.sp.greedy ? 1.0f : (float)(1.0 / sa->temp);
     g.sp.top_p = (float)sa->top_p;
+    g.sp.top_p_gate = top_p_gate_of(sa->top_p);
     g.sp.top_k = sa->top_k;
     g.sp.penalty = sa->repetition_penalty;
     g.sp.seed = sa->seed;
@@ -1684,6 +1694,7 @@ int fsb_lm_session_begin(fsb_lm *lm, const fsb_sampling_args *sa, uint32_t flags
     g.sp.greedy = sa->temp <= 1e-7 ? 1 : 0;
     g.sp.inv_temp = g.sp.greedy ? 1.0f : (float)(1.0 / sa->temp);
     g.sp.top_p = (float)sa->top_p;
+    g.sp.top_p_gate = top_p_gate_of(sa->top_p);
     g.sp.top_k = sa->top_k;
     g.sp.penalty = sa->repetition_penalty;
     g.sp.seed = sa->seed;

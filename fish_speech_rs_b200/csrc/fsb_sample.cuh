@@ -49,7 +49,9 @@ __device__ __forceinline__ void rep_pen_update(RepPenState *st, uint32_t tok) {
 
 struct SampleParams {
     float inv_temp;     // f32(1 / temp)
-    float top_p;
+    float top_p;        // f32(top_p): the threshold sample_topp compares running sums with (mod.rs:70 `top_p as f32`)
+    float top_p_gate;   // largest f32 <= the caller's f64 top_p (+inf if top_p <= 0): `sum_p <= top_p_gate` is exactly the
+                        // reference's f64 gate `top_p <= 0.0 || top_p >= sum_p as f64` (mod.rs:67) for an f32 sum_p
     uint32_t top_k;
     int greedy;         // temp <= 1e-7
     float penalty;      // f32 repetition penalty
@@ -235,7 +237,7 @@ __device__ __forceinline__ int block_sample_t(float *vals, unsigned long long *k
         const float sum_p = __shfl_sync(0xffffffffu, incl, 31);
         int kept = k;
         float total = sum_p;
-        const bool do_topp = !(sp.top_p <= 0.f || sp.top_p >= sum_p) || (sp.top_k >= (uint32_t)n);
+        const bool do_topp = !(sum_p <= sp.top_p_gate) || (sp.top_k >= (uint32_t)n);
         if (do_topp) {
             // an entry survives iff the running sum BEFORE it is still below top_p (mod.rs:119-129)
             int kl = 0;
@@ -517,7 +519,7 @@ __device__ __noinline__ int block_sample_sel_t(const float *vals, unsigned char 
         const float sum_p = __shfl_sync(0xffffffffu, incl, 31);
         int kept = k;
         float total = sum_p;
-        const bool do_topp = !(sp.top_p <= 0.f || sp.top_p >= sum_p) || (sp.top_k >= (uint32_t)n);
+        const bool do_topp = !(sum_p <= sp.top_p_gate) || (sp.top_k >= (uint32_t)n);
         if (do_topp) {
             int kl = 0;
             float tl = 0.f, c = excl;

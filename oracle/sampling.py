@@ -59,7 +59,8 @@ def sample_from_probs(probs: np.ndarray, top_k: int, top_p: float, u: np.float32
     for v in w:
         sum_p = np.float32(sum_p + v)
     top_p32 = np.float32(top_p)
-    if not (top_p <= 0.0 or top_p32 >= sum_p) or top_k >= n:
+    # the gate is evaluated in f64 (mod.rs:67: `top_p <= 0.0 || top_p >= sum_p as f64`), the cut below in f32 (`top_p as f32`)
+    if not (top_p <= 0.0 or float(top_p) >= float(sum_p)) or top_k >= n:
         # sample_topp: zero everything once the running sum has reached top_p (mod.rs:119-129)
         cumsum = np.float32(0.0)
         for i in range(k):
