@@ -891,9 +891,11 @@ struct MegaB {
 #pragma unroll
         for (int c = 0; c < kNB - 1; ++c) stage(c);
         for (int c = 0; c < nchunks; ++c) {
-            stage(c + kNB - 1);  // into the buffer consumed in iteration c - 1 (released by the barrier below)
-            asm volatile("cp.async.wait_group %0;" ::"n"(kNB - 1) : "memory");  // chunk c has landed
+            // ONE barrier per chunk: it publishes chunk c (every thread waited for its own copies) and it proves that every
+            // warp is done with chunk c - 1, whose buffer takes chunk c + kNB - 1 right behind it
+            asm volatile("cp.async.wait_group %0;" ::"n"(kNB - 2) : "memory");  // chunk c has landed
             wsync();
+            stage(c + kNB - 1);
             const int n = min(kCh, j1 - (j0 + c * kCh));
             const float *ks = kvb + (c % kNB) * kBuf, *vs = ks + kCh * kMBKvStride;
             // The whole chunk in ONE step: lane group g takes positions g, g + 8, g + 16, g + 24.  A warp issues in order and
@@ -902,6 +904,8 @@ struct MegaB {
             // 15.7 us per 576-position range).  Measured and NOT kept: -30 % instructions (ex2.approx, rescale only when the
             // maximum moves) alone changed nothing; an L2 bulk prefetch of the range one phase ahead changed nothing; four
             // heads per warp (4x less LDS traffic) was slower (19.3 us), with TMA bulk staging slower still (22.8 us).
+            // Head PAIRS per warp on half of a chunk's positions (2x less LDS traffic, same four chains per lane): 15.3 -> 14.7 us
+            // per range, but the cross-warp merge it needs costs the 32 short fast-layer phases of a frame 1.2 us each: net loss.
             {
                 bool vld[4];
                 int row[4];
@@ -958,7 +962,6 @@ struct MegaB {
                     }
                 }
             }
-            wsync();  // buffer c % kNB may be refilled (with chunk c + kNB) by the next iteration
         }
         cp_async_wait_all();
         // merge the 8 position groups (lanes with equal `sub`)
