@@ -736,6 +736,8 @@ struct MegaB {
         mb_wait(a2f, pa2f);
         if (tm) { c1 = clock64(); td[3] += c1 - c0; c0 = c1; }
         // partial y[t][b][128 r + row] (summed over the 64 blocks by fred_phase)
+        // (Measured and NOT kept: staging the tiles in shared memory and handing each 512-byte batch row to the bulk-copy
+        // engine -- 11 us instead of 2.8; the WO epilogue transposed through shared memory for 16-byte stores -- no change.)
         float *yp = e.ws + (size_t)t * NPAD * kD + qd * 32 + lane;
 #pragma unroll 1
         for (int r8 = 0; r8 < kD / 128; ++r8) {

@@ -8,7 +8,7 @@ for d in build/v_*; do /usr/local/cuda/bin/nvcc -shared -o $d/libfsb.so $OTHERS 
 run_tests() { timeout -s KILL 400 python -m pytest tests/test_lm_gpu.py -x -q -m gpu -k "wide or batch or session or snapshot or ragged" 2>&1 | tail -2; }
 echo "== tests cur"; run_tests
 for t in ${AB_TEST_VARIANTS:-all}; do echo "== tests $t"; FSB_LIB=$PWD/build/v_$t/libfsb.so run_tests; done
-for v in prev cur $(ls build | grep '^v_' | sed 's/^v_//'); do
+for v in $( [ -f build/wt_prev_so/libfsb.so ] && echo prev ) cur $(ls build | grep '^v_' | sed 's/^v_//'); do
   if [ $v = prev ]; then export FSB_LIB=$PWD/build/wt_prev_so/libfsb.so; elif [ $v = cur ]; then unset FSB_LIB; else export FSB_LIB=$PWD/build/v_$v/libfsb.so; fi
   for cfg in cfg5 cfg3; do
   timeout -s KILL 300 python bench.py --config $cfg --steps 2 --warmup 1 --no-cpu-baseline --no-extras 2>gpurun_out/ab_${v}_${cfg}.err | python -c "
