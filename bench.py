@@ -364,7 +364,7 @@ def run_ours(a):
         e2e = frames_all / (wall_ms_max / 1e3)
         traffic, traffic_note = None, None
         try:
-            tr = json.load(open(os.path.join(ROOT, "profiles", "r02_megab_traffic.json" if wl.B > 8 else
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r02e_megab_traffic.json" if wl.B > 8 else
                                              ("r01_mega1_traffic.json" if wl.B == 1 else "r01_mega_traffic.json"))))
             if dom_n > 0 and a.dtype == "bf16":
                 # DRAM bytes per frame from the committed ncu capture x frames in this launch
