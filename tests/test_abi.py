@@ -28,6 +28,18 @@ def test_header_symbols_exported():
     assert sorted(F.SYMBOLS) == names
 
 
+def test_rust_binding_declares_the_same_symbols():
+    """shim/fsb_sys.rs is shipped as source (no Rust toolchain in the image): its `extern "C"` block must name exactly
+    the functions of include/fsb.h, and every one of them must be used by the safe wrappers or re-exported."""
+    rs = open(os.path.join(ROOT, "shim", "fsb_sys.rs")).read()
+    rs = re.sub(r"//.*", "", rs)
+    assert sorted(set(re.findall(r"\bpub fn (fsb_[a-z0-9_]+)\s*\(", rs))) == declared_symbols()
+    # INTEGRATION.md shows the reference-side binding: every entry point it names exists
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    for n in set(re.findall(r"\b(fsb_[a-z0-9_]+)\s*\(", doc)):
+        assert n in declared_symbols() or n.startswith("fsb_sys"), f"INTEGRATION.md mentions {n}, not in include/fsb.h"
+
+
 def test_abi_version_and_error_string():
     lib = F.lib()
     assert lib.fsb_abi_version() == 1
