@@ -170,6 +170,29 @@ def make_weights(version, want_lm=True, want_codec=True, with_encoder=False):
     return lm_w, codec_w
 
 
+def frame_weight_bytes_estimate(version, dtype):
+    """Weight bytes one frame-step streams (slow stack + constrained head + 8 x (fast stack + fast head)), from the model
+    shapes alone -- the GPU arm reports the library's exact figure in `roofline.frame_bytes`; this one only feeds the
+    `config.l2` note, which both arms must print identically."""
+    from fish_speech_rs_b200 import synth
+    m = synth.FISH15 if version == "1.5" else synth.FISH14
+    t = synth.FISH15_TOKENS if version == "1.5" else synth.FISH14_TOKENS
+    D, I = m["dim"], m["intermediate_size"]
+    layer = (m["n_head"] + 2 * m["n_local_heads"]) * m["head_dim"] * D + D * D + 3 * I * D
+    end = t.get("semantic_end_id")
+    n_slow = (end - t["semantic_start_id"] + 2) if end is not None else 2  # Fish <= 1.4: the two-way PAD / EOS head (Q8)
+    elems = m["n_layer"] * layer + n_slow * D + m["num_codebooks"] * (m["n_fast_layer"] * layer + m["codebook_size"] * D)
+    return elems * (2 if dtype == "bf16" else 4)
+
+
+def config_dict(cfgname, c, world, per_gpu, frames, dtype):
+    """`config` of the JSON line: the workload, identical for the GPU arm and the reference arm."""
+    return {"workload": cfgname, "desc": c["desc"], "utterances_per_gpu": per_gpu, "utterances_total": c["batch"] * world,
+            "frames": frames, "sharding": "fish_speech_rs_b200.shard.assign (length-balanced static partition, no collective)",
+            "weights": "seeded random init, Fish %s shapes" % c["version"], "codec_dtype": "f32",
+            "l2": "no flush: per-frame weight stream (%.1f GB) >> 126 MB L2" % (frame_weight_bytes_estimate(c["version"], dtype) / 1e9)}
+
+
 def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -187,7 +210,9 @@ def run_reference(a):
     out = {"impl": "reference", "metric": "codec_tokens_per_sec", "value": v, "unit": "frames/s", "n_gpus": a.gpus,
            "steps": a.steps, "warmup": a.warmup, "ms_per_step": c["batch"] * c["frames"] / v * 1e3,
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": a.config, "desc": c["desc"]},
+           "config": config_dict(a.config, c, max(a.gpus, 1), c["batch"], a.frames or c["frames"], a.dtype),
+           "extrapolated": "value = the bounded sample of cpu_baseline.sample scaled to the workload; ms_per_step is the "
+                           "extrapolated time of one whole step, not the time this run took",
            "audio_samples_per_sec": v * 2048, "rtf": v / FRAME_RATE,
            "cpu_baseline": {"value": v, "unit": "frames/s", "cores": threads, "kind": "port", "sample": desc},
            "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -383,10 +408,7 @@ def run_ours(a):
             "metric": "codec_tokens_per_sec", "value": value, "unit": "frames/s", "n_gpus": world, "steps": steps,
             "warmup": a.warmup, "ms_per_step": dev_ms_max / steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": a.dtype, "data": "synthetic",
-            "config": {"workload": a.config, "desc": c["desc"], "utterances_per_gpu": wl.B, "utterances_total": c["batch"] * world,
-                       "frames": N, "sharding": "fish_speech_rs_b200.shard.assign (length-balanced static partition, no collective)",
-                       "weights": "seeded random init, Fish %s shapes" % c["version"], "codec_dtype": "f32",
-                       "l2": "no flush: per-frame weight stream (%.0f MB) >> 126 MB L2" % (wb / 1e6)},
+            "config": config_dict(a.config, c, world, wl.B, N, a.dtype),
             "audio_samples_per_sec": value * 2048, "rtf": value / FRAME_RATE,
             "breakdown_ms_per_step": {"lm_prefill": acc["pre"] / steps, "lm_decode": acc["dec"] / steps,
                                       "vocoder": acc["voc"] / steps, "encoder": acc["enc"] / steps},
