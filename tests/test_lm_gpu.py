@@ -657,3 +657,28 @@ def test_continuous_batching_session(fixed):
             tot[k] += r[k]
     assert tot["exact"] >= 0.98 * tot["decisions"], tot
     gpu.close()
+
+
+def test_sharded_synthesizer_drives_the_library(tiny_lm):
+    """fish_speech_rs_b200.shard.ShardedSynthesizer: two ranks emulated one after the other on this GPU; each
+    runs only its launches through generate_static_batch, greedy rows equal the oracle's single-utterance output whatever
+    launch and position they landed in, and the two shares cover the job exactly once."""
+    from fish_speech_rs_b200 import shard
+    cfg, tok, w = tiny_lm
+    gpu = DualARTransformer(w, cfg, tok, max_batch=3, max_seq_len=256)
+    ora = oracle_model(cfg, tok, w)
+    prompts = [synth.make_prompt(cfg, tok, P, seed=700 + i) for i, P in enumerate((21, 48, 33, 64, 17, 40, 55))]
+    got = {}
+    for r in range(2):
+        syn = shard.ShardedSynthesizer(lm=gpu, rank=r, world_size=2, sampling_args=SamplingArgs(temp=0.0), max_rows=3,
+                                       vocode=lambda codes: [c.shape[1] for c in codes])
+        res = syn.synthesize(prompts, 400, fixed_len=6)
+        assert all(len(b) <= 3 for b in syn.launches) and not set(res) & set(got)
+        got.update(res)
+    assert sorted(got) == list(range(len(prompts)))
+    with torch.no_grad():  # (clears the oracle's slow KV before every row)
+        exp = ogen.generate_independent_batch(ora, [t64(p) for p in prompts], 400, osamp.SamplingArgs(temp=0.0), fixed_len=6)
+    for i in range(len(prompts)):
+        np.testing.assert_array_equal(got[i][0].astype(np.int64), exp[i].numpy())
+        assert got[i][1] == 6
+    gpu.close()
