@@ -58,9 +58,9 @@ def hf_llama(cfg, w, prefix, n_layers, norm_key, permute=True):
     return m
 
 
-@pytest.fixture(scope="module")
-def setup():
-    cfg, tok = dict(synth.TINY), dict(synth.TINY_TOKENS)
+@pytest.fixture(scope="module", params=["TINY", "WIDE"])  # WIDE: full-width Fish blocks (dim 1024, 16 q / 2 kv heads, FFN 4096)
+def setup(request):
+    cfg, tok = dict(getattr(synth, request.param)), dict(synth.TINY_TOKENS)
     w = synth.make_lm_weights(cfg, seed=1234)
     ora = olm.DualARTransformer(w, olm.BaseModelArgs(**cfg), olm.TokenConfig(**tok))
     return cfg, tok, w, ora
