@@ -40,3 +40,26 @@ def test_recorded_lines_carry_the_contract_keys():
     ref = json.load(open(os.path.join(ROOT, "profiles", "r02e_final_bench_reference_arm.json")))
     assert ref["impl"] == "reference" and ref["cpu_baseline"]["kind"] == "port"
     assert ref["e2e"]["h2d_bytes_per_step"] == 0 and ref["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def test_reference_arm_under_torchrun_prints_one_line_from_rank_0():
+    """`bench.py --impl reference` launched like the driver launches it for N > 1: rank 0 alone times the oracle on the
+    host cores and prints ONE JSON line with the GPU arm's config; the other rank exits 0 without work."""
+    import socket
+    import subprocess
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "bench.py"),
+                        "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0", "--cpu-sample-frames", "2"],
+                       capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["value"] > 0
+    c = bench.CONFIGS["cfg5"]
+    assert d["config"] == bench.config_dict("cfg5", c, 2, c["batch"], c["frames"], "bf16")
+    assert d["e2e"] == {"value": d["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
