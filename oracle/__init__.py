@@ -15,8 +15,14 @@ oracle is therefore a PyTorch CPU fp32 restatement written op-for-op from
   fish_speech_core/lib/codec/*.rs
   fish_speech_core/lib/audio/{spectrogram,stft}.rs
 
-pinned only by the closed-form known answers the reference does carry
-(mel filterbank bytes, FSQ implicit codebook, causal-mask truth table, id
-rescaling round trip, rep-pen window behaviour, repeat_kv test shapes) -- see
-``tests/test_oracle_kat.py``.
+pinned by what the reference does carry -- its loader dumps
+(docs/llama-weight-dict.txt, docs/weight-dims-default.txt), its mel filterbank
+bytes, tests/resources/sky.wav, voices-template/default.npy -- and by the
+closed forms in its source (FSQ implicit codebook, causal-mask truth table, id
+rescaling round trip, rep-pen window behaviour, repeat_kv test shapes): see
+``tests/test_oracle_kat.py`` and DESIGN.md section 5.  The float arithmetic of
+the two transformer stacks is additionally tied to an independently written
+Llama (Hugging Face ``transformers``, ``tests/test_oracle_vs_hf_llama.py``:
+2e-6 after mapping the interleaved RoPE pairs); that is a check of the
+restatement, not of the reference, so the label above stays.
 """
